@@ -1,0 +1,486 @@
+// The bark.h C API (include/bark.h) and the host control plane behind it: tokenizer, the three
+// stage loops, host sampling, statistics.  Semantics follow the reference's bark.cpp — including
+// its quirks — because token parity depends on them; the code is new.
+//
+//   tokenizer ............ bark.cpp:480-662   (accent strip, [[:punct:]]|[[:alpha:]]+|[[:digit:]]+, greedy WordPiece)
+//   sampling ............. bark.cpp:184-270   (+ libstdc++ std::discrete_distribution / std::mt19937)
+//   semantic loop ........ bark.cpp:1645-1743
+//   coarse loop .......... bark.cpp:1745-1905
+//   fine loop ............ bark.cpp:1961-2104
+//   generate / lifecycle . bark.cpp:1165-1184, 2125-2232, 2379-2407
+#include "../../include/bark_b200.h"
+#include "context.h"
+#include "gpt_kernels.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+using namespace bark;
+
+namespace {
+
+int  g_device_override = -1;
+bool quiet() { static const bool q = [] { const char * e = getenv("BARK_B200_QUIET"); return e && *e && *e != '0'; }(); return q; }
+
+// ---------------------------------------------------------------------------------------------
+// tokenizer
+// ---------------------------------------------------------------------------------------------
+inline bool is_alpha(unsigned char c) { return (c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z'); }
+inline bool is_digit(unsigned char c) { return c >= '0' && c <= '9'; }
+inline bool is_punct(unsigned char c) { return c > 32 && c < 127 && !is_alpha(c) && !is_digit(c); }
+
+// Latin-1 letters with diacritics (two-byte UTF-8, lead 0xC3) -> base ASCII letter; 0 if not mapped.
+// Same 52 code points as the reference's table (bark.cpp:488-541).
+char fold_accent(unsigned char second) {
+    const unsigned cp = 0xC0u + (second - 0x80u);          // U+00C0 .. U+00FF
+    const bool lower = cp >= 0xE0;
+    const unsigned up = lower ? cp - 0x20 : cp;
+    char base = 0;
+    if (up >= 0xC0 && up <= 0xC5) base = 'A';
+    else if (up == 0xC7) base = 'C';
+    else if (up >= 0xC8 && up <= 0xCB) base = 'E';
+    else if (up >= 0xCC && up <= 0xCF) base = 'I';
+    else if (up == 0xD1) base = 'N';
+    else if (up >= 0xD2 && up <= 0xD6) base = 'O';
+    else if (up >= 0xD9 && up <= 0xDC) base = 'U';
+    else if (up == 0xDD) base = 'Y';
+    if (!base) return 0;
+    return lower ? (char)(base + 32) : base;
+}
+
+std::string strip_accents_utf8(const std::string & in) {
+    std::string out;
+    for (size_t i = 0; i < in.size();) {
+        const unsigned char c = (unsigned char) in[i];
+        const unsigned hi = c >> 4;
+        size_t len = hi < 12 ? 1 : hi < 14 ? 2 : hi == 14 ? 3 : 4;      // lead-byte length table, bark.cpp:480-484
+        len = std::min(len, in.size() - i);
+        char folded = 0;
+        if (len == 2 && c == 0xC3) { const unsigned char d = (unsigned char) in[i + 1]; if (d >= 0x80 && d <= 0xBF) folded = fold_accent(d); }
+        if (folded) out.push_back(folded); else out.append(in, i, len);
+        i += len;
+    }
+    return out;
+}
+
+// bert_tokenize (bark.cpp:558-620)
+void wordpiece(const std::map<std::string, int32_t> & vocab, const std::string & text, std::vector<int32_t> & out, int n_max_tokens) {
+    const std::string s = strip_accents_utf8(text);
+    out.clear();
+    size_t i = 0;
+    while (i < s.size()) {
+        const unsigned char c = (unsigned char) s[i];
+        size_t j = i;
+        if (is_punct(c)) j = i + 1;
+        else if (is_alpha(c)) { while (j < s.size() && is_alpha((unsigned char) s[j])) j++; }
+        else if (is_digit(c)) { while (j < s.size() && is_digit((unsigned char) s[j])) j++; }
+        else { i++; continue; }
+        const std::string word = s.substr(i, j - i);
+        i = j;
+        size_t p = 0; bool cont = false;
+        while (p < word.size()) {
+            if ((int) out.size() >= n_max_tokens - 1) break;
+            size_t e = word.size(); bool hit = false;
+            for (; e > p; e--) {
+                auto it = vocab.find((cont ? "##" : "") + word.substr(p, e - p));
+                if (it != vocab.end()) { out.push_back(it->second); p = e; cont = true; hit = true; break; }
+            }
+            if (!hit) { fprintf(stderr, "%s: unknown token '%c'\n", "bert_tokenize", word[p]); cont = true; p++; }
+        }
+    }
+}
+
+void tokenize_input(bark_context * ctx, const std::string & text) {               // bark.cpp:622-662
+    const bark_context_params & P = ctx->params;
+    const int max_ctx = std::min(ctx->semantic.block_size, 256);
+    std::vector<int32_t> pieces;
+    wordpiece(ctx->token_to_id, text, pieces, max_ctx);
+    std::vector<int32_t> t((size_t) max_ctx, 0);
+    std::copy(pieces.begin(), pieces.end(), t.begin());
+    for (auto & v : t) v += P.text_encoding_offset;                               // offset applied to every slot before padding (quirk D.4)
+    for (size_t k = pieces.size(); k < t.size(); k++) t[k] = P.text_pad_token;
+    t.insert(t.end(), 256, P.semantic_pad_token);                                 // empty semantic history
+    t.push_back(P.semantic_infer_token);
+    ctx->tokens = t;
+    if (!quiet()) {
+        printf("%s: prompt: '%s'\n", "bark_tokenize_input", text.c_str());
+        printf("%s: number of tokens in prompt = %zu, first 8 tokens: ", "bark_tokenize_input", ctx->tokens.size());
+        for (size_t k = 0; k < std::min<size_t>(8, ctx->tokens.size()); k++) printf("%d ", ctx->tokens[k]);
+        printf("\n\n");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// sampling (gpt_sample, bark.cpp:249-270)
+// ---------------------------------------------------------------------------------------------
+int32_t sample_token(bark_context * ctx, GPTModel & m, const float * logits, int n, float temp, float * eos_p) {
+    const int64_t t0 = now_us();
+    std::vector<float> p(logits, logits + n);
+    const float div = temp == 0.0f ? 0.7f : temp;                                 // argmax path still divides by 0.7 (quirk D.3)
+    for (float & v : p) v /= div;
+    float mx = -INFINITY;
+    for (float v : p) mx = std::max(mx, v);
+    float sum = 0.0f;
+    for (float & v : p) { v = (float) exp((double)(v - mx)); sum += v; }          // reference calls the double exp() on a float argument
+    for (float & v : p) v /= sum;
+    int32_t next = 0;
+    if (temp == 0.0f) {
+        float best = -INFINITY;
+        for (int i = 0; i < n; i++) if (p[(size_t) i] > best) { best = p[(size_t) i]; next = i; }
+    } else {
+        std::discrete_distribution<int32_t> dist(p.begin(), p.end());
+        next = dist(ctx->rng);
+    }
+    if (eos_p) *eos_p = p.back();                                                 // probability of the LAST logit (quirk D.2)
+    m.t_sample_us += now_us() - t0;
+    m.n_sample += 1;
+    return next;
+}
+
+void print_stage_stats(const GPTModel & m) {                                      // bark_print_statistics, bark.cpp:176-182
+    if (quiet()) return;
+    printf("\n\n");
+    printf("%s:   sample time = %8.2f ms / %lld tokens\n", "bark_print_statistics", m.t_sample_us / 1000.0f, (long long) m.n_sample);
+    printf("%s:  predict time = %8.2f ms / %.2f ms per token\n", "bark_print_statistics", m.t_predict_us / 1000.0f,
+           m.n_sample ? m.t_predict_us / (double) m.n_sample / 1000.0 : 0.0);
+    printf("%s:    total time = %8.2f ms\n", "bark_print_statistics", m.t_main_us / 1000.0f);
+    printf("\n");
+}
+
+// ---------------------------------------------------------------------------------------------
+// stage loops
+// ---------------------------------------------------------------------------------------------
+bool run_semantic(bark_context * ctx) {
+    const int64_t t_start = now_us();
+    GPTModel & m = ctx->semantic;
+    const bark_context_params & P = ctx->params;
+    std::vector<float> logits((size_t) m.n_out_vocab);
+    std::vector<int32_t> input = ctx->tokens, output;
+    int n_past = 0; float eos_p = 0.0f;
+    for (int i = 0; i < P.n_steps_text_encoder; i++) {
+        if (P.progress_callback) P.progress_callback(ctx, SEMANTIC, 100 * (i + 1) / P.n_steps_text_encoder, P.progress_callback_user_data);
+        if (!gpt_eval(ctx, m, input.data(), (int) input.size(), &n_past, true, logits.data())) { fprintf(stderr, "%s: Could not generate token\n", __func__); return false; }
+        // the reference samples over ALL n_out_vocab logits, not the 10001 "relevant" ones (quirk D.1)
+        const int32_t next = sample_token(ctx, m, logits.data(), m.n_out_vocab, P.temp, &eos_p);
+        if (next == P.semantic_vocab_size || eos_p >= P.min_eos_p) break;
+        input.assign(1, next);
+        output.push_back(next);
+    }
+    ctx->semantic_tokens = output;
+    ctx->stats.n_sample_semantic = (int32_t) m.n_sample;
+    m.t_main_us = now_us() - t_start;
+    ctx->stats.t_semantic_us = m.t_main_us;
+    print_stage_stats(m);
+    return true;
+}
+
+bool run_coarse(bark_context * ctx) {
+    const int64_t t_start = now_us();
+    GPTModel & m = ctx->coarse;
+    const bark_context_params & P = ctx->params;
+    const std::vector<int32_t> & sem = ctx->semantic_tokens;
+    std::vector<float> logits((size_t) m.n_out_vocab);
+    const float stc_ratio = P.coarse_rate_hz / P.semantic_rate_hz * P.n_coarse_codebooks;
+    const int max_semantic_history = (int) floorf(P.max_coarse_history / stc_ratio);
+    const int n_steps = (int)(floorf(sem.size() * stc_ratio / P.n_coarse_codebooks) * P.n_coarse_codebooks);
+    if (n_steps <= 0 || P.n_coarse_codebooks != 2) { fprintf(stderr, "%s: nothing to generate (%zu semantic tokens)\n", __func__, sem.size()); return false; }
+    const int n_windows = (int) ceilf((float) n_steps / P.sliding_window_size);
+    std::vector<int32_t> out; out.reserve((size_t) n_steps);
+    int step = 0;
+    for (int w = 0; w < n_windows; w++) {
+        const int semantic_idx = (int) roundf(step / stc_ratio);
+        // window input: semantic tokens from the history start TO THE END, cut/padded to 256 (quirk D.5), infer token, coarse history
+        std::vector<int32_t> in(sem.begin() + std::max(semantic_idx - max_semantic_history, 0), sem.end());
+        in.resize(256, P.coarse_semantic_pad_token);
+        in.push_back(P.coarse_infer_token);
+        const size_t hist = std::min<size_t>((size_t) P.max_coarse_history, out.size());
+        in.insert(in.end(), out.end() - (std::ptrdiff_t) hist, out.end());
+        int n_past = 0;
+        for (int j = 0; j < P.sliding_window_size && step < n_steps; j++) {
+            if (P.progress_callback) P.progress_callback(ctx, COARSE, 100 * (step + 1) / n_steps, P.progress_callback_user_data);
+            if (!gpt_eval(ctx, m, in.data(), (int) in.size(), &n_past, false, logits.data())) { fprintf(stderr, "%s: Could not generate token\n", __func__); return false; }
+            const bool major = step % P.n_coarse_codebooks == 0;
+            const int lo = P.semantic_vocab_size + (major ? 0 : 1) * P.codebook_size;
+            const int32_t next = lo + sample_token(ctx, m, logits.data() + lo, P.codebook_size, P.temp, nullptr);
+            in.assign(1, next);
+            out.push_back(next);
+            step++;
+        }
+    }
+    ctx->coarse_tokens.resize(out.size());
+    for (size_t i = 0; i + 1 < out.size(); i += 2) {
+        ctx->coarse_tokens[i] = out[i] - P.semantic_vocab_size;
+        ctx->coarse_tokens[i + 1] = out[i + 1] - P.semantic_vocab_size - P.codebook_size;
+    }
+    ctx->stats.n_sample_coarse = (int32_t) m.n_sample;
+    m.t_main_us = now_us() - t_start;
+    ctx->stats.t_coarse_us = m.t_main_us;
+    print_stage_stats(m);
+    return true;
+}
+
+bool run_fine(bark_context * ctx) {
+    const int64_t t_start = now_us();
+    GPTModel & m = ctx->fine;
+    const bark_context_params & P = ctx->params;
+    const int n_coarse = P.n_coarse_codebooks, n_cb = P.n_fine_codebooks, cb_size = P.codebook_size;
+    if (n_cb != 8 || n_coarse != 2 || cb_size != 1024) { fprintf(stderr, "%s: unsupported codebook configuration\n", __func__); return false; }
+    const int T = (int) ctx->coarse_tokens.size() / 2;
+    const int len = std::max(T, 1024);
+    std::vector<int32_t> arr((size_t) len * 8, cb_size);                          // [len][8], padded with codebook_size (bark.cpp:1982-1996)
+    for (int t = 0; t < T; t++) { arr[(size_t) t * 8] = ctx->coarse_tokens[(size_t) t * 2]; arr[(size_t) t * 8 + 1] = ctx->coarse_tokens[(size_t) t * 2 + 1]; }
+    const int n_loops = std::max(0, (int) ceilf((len - 1024) / 512.f)) + 1;
+    std::vector<float> logits((size_t) 1024 * m.n_out_vocab);
+    std::vector<int32_t> buf((size_t) 8 * 1024);
+    for (int n = 0; n < n_loops; n++) {
+        const int start = std::min(n * 512, len - 1024), fill = std::min(n * 512, len - 512), rel = fill - start;
+        for (int c = 0; c < 8; c++) for (int j = 0; j < 1024; j++) buf[(size_t) c * 1024 + j] = arr[(size_t)(start + j) * 8 + c];
+        for (int nn = n_coarse; nn < n_cb; nn++) {
+            if (P.progress_callback) P.progress_callback(ctx, FINE, 100 * (n * (n_cb - n_coarse) + (nn - n_coarse + 1)) / (n_loops * (n_cb - n_coarse)), P.progress_callback_user_data);
+            if (!fine_eval(ctx, buf.data(), nn, logits.data())) { fprintf(stderr, "%s: Could not generate token\n", __func__); return false; }
+            for (int i = 0; i < 1024; i++) {
+                const int32_t next = sample_token(ctx, m, logits.data() + (size_t) i * m.n_out_vocab, cb_size, P.fine_temp, nullptr);
+                // For clips <= 1024 frames (rel == 0) this is the reference's write (bark.cpp:2037).  For longer clips the
+                // reference indexes buf[nn*1024 + rel + i] and runs off the buffer (SURVEY finding 5); there we keep the
+                // original Bark semantics: every row is sampled (same RNG consumption) and rows >= rel are written in place.
+                if (i >= rel) buf[(size_t) nn * 1024 + i] = next;
+            }
+        }
+        for (int nn = n_coarse; nn < n_cb; nn++) for (int j = 0; j < 1024 - rel; j++) arr[(size_t)(fill + j) * 8 + nn] = buf[(size_t) nn * 1024 + rel + j];
+    }
+    ctx->fine_tokens.assign(arr.begin(), arr.begin() + (std::ptrdiff_t) T * 8);
+    ctx->stats.n_sample_fine = (int32_t) m.n_sample;
+    m.t_main_us = now_us() - t_start;
+    ctx->stats.t_fine_us = m.t_main_us;
+    print_stage_stats(m);
+    return true;
+}
+
+void alloc_workspace(bark_context * ctx) {
+    int E = 0, H = 0; size_t kp_bytes = 0, n_logits = 0;
+    for (GPTModel * m : {&ctx->semantic, &ctx->coarse, &ctx->fine}) {
+        E = std::max(E, (int) m->n_embd); H = std::max(H, (int) m->n_head);
+        const size_t es = m->wtype == W_F16 ? 2 : 4;
+        kp_bytes = std::max(kp_bytes, (size_t) li_padded_k(4 * m->n_embd, (int) es) * es);
+    }
+    n_logits = std::max<size_t>({(size_t) ctx->semantic.n_out_vocab, (size_t) ctx->coarse.n_out_vocab, (size_t) 1024 * ctx->fine.n_out_vocab});
+    Workspace & ws = ctx->ws;
+    const size_t R = 1024;
+    ws.max_rows = (int) R; ws.E = E;
+    ws.x    = (float *) ctx_alloc(ctx, R * E * 4);
+    ws.act  = ctx_alloc(ctx, R * kp_bytes);
+    ws.act2 = ctx_alloc(ctx, R * kp_bytes);
+    ws.q    = (float *) ctx_alloc(ctx, R * E * 4);
+    ws.kbuf = (float *) ctx_alloc(ctx, R * E * 4);
+    ws.vbuf = (float *) ctx_alloc(ctx, R * E * 4);
+    ws.scores = (float *) ctx_alloc(ctx, (size_t) H * R * R * 4);
+    ws.logits = (float *) ctx_alloc(ctx, n_logits * 4);
+    ws.tok  = (int32_t *) ctx_alloc(ctx, 8 * 1024 * 4);
+    BARK_CUDA_CHECK(cudaMallocHost(&ctx->h_logits, n_logits * 4));
+    BARK_CUDA_CHECK(cudaMallocHost(&ctx->h_tok, 8 * 1024 * 4));
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// ggml.h shim
+// ---------------------------------------------------------------------------------------------
+extern "C" void    ggml_time_init(void) {}
+extern "C" int64_t ggml_time_us(void) { return now_us(); }
+extern "C" int64_t ggml_time_ms(void) { return now_us() / 1000; }
+
+// ---------------------------------------------------------------------------------------------
+// bark.h
+// ---------------------------------------------------------------------------------------------
+extern "C" struct bark_context_params bark_context_default_params(void) {
+    bark_context_params p;
+    memset(&p, 0, sizeof(p));
+    p.verbosity = LOW;
+    p.temp = 0.7f; p.fine_temp = 0.5f; p.min_eos_p = 0.2f;
+    p.sliding_window_size = 60; p.max_coarse_history = 630;
+    p.sample_rate = 24000; p.target_bandwidth = 6;
+    p.cls_token_id = 101; p.sep_token_id = 102;
+    p.n_steps_text_encoder = 768;
+    p.text_pad_token = 129595; p.text_encoding_offset = 10048;
+    p.semantic_rate_hz = 49.9f; p.semantic_pad_token = 10000; p.semantic_vocab_size = 10000; p.semantic_infer_token = 129599;
+    p.coarse_rate_hz = 75.0f; p.coarse_infer_token = 12050; p.coarse_semantic_pad_token = 12048;
+    p.n_coarse_codebooks = 2; p.n_fine_codebooks = 8; p.codebook_size = 1024;
+    p.progress_callback = nullptr; p.progress_callback_user_data = nullptr;
+    return p;
+}
+
+extern "C" void bark_b200_set_device(int device) { g_device_override = device; }
+
+extern "C" struct bark_context * bark_load_model(const char * model_path, struct bark_context_params params, uint32_t seed) {
+    const int64_t t0 = now_us();
+    if (!model_path) { fprintf(stderr, "%s: null model path\n", __func__); return nullptr; }
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+        fprintf(stderr, "%s: no CUDA device available — this library has no CPU path\n", __func__);
+        return nullptr;
+    }
+    int dev = g_device_override;
+    if (dev < 0) { const char * e = getenv("BARK_B200_DEVICE"); dev = e ? atoi(e) : 0; }
+    if (dev < 0 || dev >= n_dev) { fprintf(stderr, "%s: CUDA device %d out of range (%d present)\n", __func__, dev, n_dev); return nullptr; }
+    BARK_CUDA_CHECK(cudaSetDevice(dev));
+    cudaDeviceProp prop;
+    BARK_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10) {
+        fprintf(stderr, "%s: device %d is sm_%d%d; this library is built for sm_100a (B200) only\n", __func__, dev, prop.major, prop.minor);
+        return nullptr;
+    }
+    bark_context * ctx = new bark_context();
+    ctx->device = dev;
+    ctx->params = params;
+    BARK_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    if (!load_model_file(model_path, ctx)) {
+        fprintf(stderr, "%s: failed to load model weights from '%s'\n", __func__, model_path);
+        bark_free(ctx);
+        return nullptr;
+    }
+    alloc_workspace(ctx);
+    BARK_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    ctx->rng = std::mt19937(seed);
+    ctx->stats.t_load_us = now_us() - t0;
+    return ctx;
+}
+
+extern "C" void bark_reset_statistics(struct bark_context * ctx) {
+    if (!ctx) return;
+    const int64_t load = ctx->stats.t_load_us;
+    memset(&ctx->stats, 0, sizeof(ctx->stats));
+    ctx->stats.t_load_us = load;          // the reference zeroes the whole struct (bark.cpp:2403-2407) and so reports load time 0 after
+                                          // the first generate; keeping it is the useful reading of "load time of the model"
+}
+
+extern "C" bool bark_b200_forward_text_encoder(struct bark_context * ctx, int) { return ctx && run_semantic(ctx); }
+extern "C" bool bark_b200_forward_coarse_encoder(struct bark_context * ctx, int) { return ctx && run_coarse(ctx); }
+extern "C" bool bark_b200_forward_fine_encoder(struct bark_context * ctx, int) { return ctx && run_fine(ctx); }
+// the reference also exports these three as C++ symbols without a header (bark.cpp:1703,1865,2061)
+bool bark_forward_text_encoder(struct bark_context * ctx, int n) { return bark_b200_forward_text_encoder(ctx, n); }
+bool bark_forward_coarse_encoder(struct bark_context * ctx, int n) { return bark_b200_forward_coarse_encoder(ctx, n); }
+bool bark_forward_fine_encoder(struct bark_context * ctx, int n) { return bark_b200_forward_fine_encoder(ctx, n); }
+
+extern "C" bool bark_generate_audio(struct bark_context * ctx, const char * text, int n_threads) {
+    (void) n_threads;                      // CPU thread count of the reference's backend; nothing to size here
+    if (!ctx) { fprintf(stderr, "%s: invalid bark context\n", __func__); return false; }
+    if (!text) { fprintf(stderr, "%s: null prompt\n", __func__); return false; }
+    bark_reset_statistics(ctx);
+    const int64_t t0 = now_us();
+    BARK_CUDA_CHECK(cudaSetDevice(ctx->device));
+    tokenize_input(ctx, text);
+    if (!run_semantic(ctx)) { fprintf(stderr, "%s: failed to forward text encoder\n", __func__); return false; }
+    if (!run_coarse(ctx))   { fprintf(stderr, "%s: failed to forward coarse encoder\n", __func__); return false; }
+    if (!run_fine(ctx))     { fprintf(stderr, "%s: failed to forward fine encoder\n", __func__); return false; }
+    // [T][8] -> [8][T]: EnCodec wants one contiguous time series per codebook (bark.cpp:2151-2159)
+    const int T = (int) ctx->fine_tokens.size() / 8;
+    std::vector<int32_t> codes((size_t) 8 * T);
+    for (int c = 0; c < 8; c++) for (int t = 0; t < T; t++) codes[(size_t) c * T + t] = ctx->fine_tokens[(size_t) t * 8 + c];
+    if (ctx->params.target_bandwidth != 6 || ctx->params.sample_rate != 24000) {
+        fprintf(stderr, "%s: only target_bandwidth 6 / 24 kHz is implemented\n", __func__); return false;
+    }
+    if (!codec_decode(ctx, codes.data(), T)) { printf("%s: Could not generate waveform from tokens with Encodec\n", __func__); return false; }
+    ctx->stats.t_eval_us = now_us() - t0;
+    return true;
+}
+
+extern "C" float * bark_get_audio_data(struct bark_context * ctx) {
+    if (!ctx) { fprintf(stderr, "%s: invalid bark context\n", __func__); return nullptr; }
+    return ctx->audio.empty() ? nullptr : ctx->audio.data();
+}
+extern "C" int bark_get_audio_data_size(struct bark_context * ctx) {
+    if (!ctx) { fprintf(stderr, "%s: invalid bark context\n", __func__); return 0; }
+    return (int) ctx->audio.size();
+}
+extern "C" int64_t bark_get_load_time(struct bark_context * ctx) {
+    if (!ctx) { fprintf(stderr, "%s: invalid bark context\n", __func__); return 0; }
+    return ctx->stats.t_load_us;
+}
+extern "C" int64_t bark_get_eval_time(struct bark_context * ctx) {
+    if (!ctx) { fprintf(stderr, "%s: invalid bark context\n", __func__); return 0; }
+    return ctx->stats.t_eval_us;
+}
+
+extern "C" bool bark_model_quantize(const char * fname_inp, const char * fname_out, enum ggml_ftype ftype) {
+    (void) fname_inp; (void) fname_out;
+    fprintf(stderr, "%s: re-quantising model files (ftype %d) is not part of this library's scope; use the reference `quantize` tool "
+                    "(examples/quantize) to produce the file\n", __func__, (int) ftype);
+    return false;
+}
+
+extern "C" void bark_free(struct bark_context * ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (void * p : ctx->device_allocs) cudaFree(p);
+    for (int i = 0; i < 3; i++) if (ctx->c_buf[i]) cudaFree(ctx->c_buf[i]);
+    if (ctx->c_gi) cudaFree(ctx->c_gi);
+    if (ctx->d_codes) cudaFree(ctx->d_codes);
+    if (ctx->h_logits) cudaFreeHost(ctx->h_logits);
+    if (ctx->h_tok) cudaFreeHost(ctx->h_tok);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+// ---------------------------------------------------------------------------------------------
+// additive entry points (include/bark_b200.h): per-call hooks for parity tests and the benchmark
+// ---------------------------------------------------------------------------------------------
+static GPTModel * pick(bark_context * ctx, int which) { return which == 0 ? &ctx->semantic : which == 1 ? &ctx->coarse : which == 2 ? &ctx->fine : nullptr; }
+
+extern "C" int bark_b200_gpt_eval(struct bark_context * ctx, int which, const int32_t * tokens, int n, int * n_past, int merge_ctx, float * logits_out) {
+    if (!ctx || which < 0 || which > 1 || !tokens || !logits_out) return 0;
+    BARK_CUDA_CHECK(cudaSetDevice(ctx->device));
+    return gpt_eval(ctx, *pick(ctx, which), tokens, n, n_past, merge_ctx != 0, logits_out) ? 1 : 0;
+}
+extern "C" int bark_b200_fine_eval(struct bark_context * ctx, const int32_t * in_buffer, int nn, float * logits_out) {
+    if (!ctx || !in_buffer || !logits_out) return 0;
+    BARK_CUDA_CHECK(cudaSetDevice(ctx->device));
+    return fine_eval(ctx, in_buffer, nn, logits_out) ? 1 : 0;
+}
+extern "C" int bark_b200_encodec_decode(struct bark_context * ctx, const int32_t * codes, int n_frames, float * out, int out_cap) {
+    if (!ctx || !codes) return -1;
+    BARK_CUDA_CHECK(cudaSetDevice(ctx->device));
+    if (!codec_decode(ctx, codes, n_frames)) return -1;
+    const int n = (int) ctx->audio.size();
+    if (out) memcpy(out, ctx->audio.data(), sizeof(float) * (size_t) std::min(n, out_cap));
+    return n;
+}
+extern "C" int bark_b200_sample(struct bark_context * ctx, int which, const float * logits, int n, float temp, float * eos_p) {
+    if (!ctx || !logits || n < 1) return -1;
+    return sample_token(ctx, *pick(ctx, which < 0 || which > 2 ? 0 : which), logits, n, temp, eos_p);
+}
+extern "C" void bark_b200_reseed(struct bark_context * ctx, uint32_t seed) { if (ctx) ctx->rng = std::mt19937(seed); }
+extern "C" void bark_b200_tokenize(struct bark_context * ctx, const char * text, int32_t * out513) {
+    if (!ctx || !text || !out513) return;
+    tokenize_input(ctx, text);
+    memcpy(out513, ctx->tokens.data(), sizeof(int32_t) * 513);
+}
+extern "C" int bark_b200_get_tokens(struct bark_context * ctx, int stage, int32_t * out, int cap) {
+    if (!ctx) return -1;
+    const std::vector<int32_t> * v = stage == 0 ? &ctx->semantic_tokens : stage == 1 ? &ctx->coarse_tokens : stage == 2 ? &ctx->fine_tokens : stage == 3 ? &ctx->tokens : nullptr;
+    if (!v) return -1;
+    if (out) memcpy(out, v->data(), sizeof(int32_t) * std::min(v->size(), (size_t) std::max(cap, 0)));
+    return (int) v->size();
+}
+extern "C" void bark_b200_set_tokens(struct bark_context * ctx, int stage, const int32_t * in, int n) {
+    if (!ctx || !in || n < 0) return;
+    if (stage == 0) ctx->semantic_tokens.assign(in, in + n); else if (stage == 1) ctx->coarse_tokens.assign(in, in + n); else if (stage == 3) ctx->tokens.assign(in, in + n);
+}
+extern "C" void bark_b200_get_stats(struct bark_context * ctx, struct bark_statistics * out, int64_t * per_model9) {
+    if (!ctx) return;
+    if (out) *out = ctx->stats;
+    if (per_model9) { const GPTModel * m[3] = {&ctx->semantic, &ctx->coarse, &ctx->fine}; for (int i = 0; i < 3; i++) { per_model9[3 * i] = m[i]->t_predict_us; per_model9[3 * i + 1] = m[i]->t_sample_us; per_model9[3 * i + 2] = m[i]->n_sample; } }
+}
+extern "C" void bark_b200_get_hparams(struct bark_context * ctx, int which, int32_t * out10) {
+    if (!ctx || !out10) return;
+    const GPTModel * m = pick(ctx, which); if (!m) return;
+    const int32_t v[10] = {m->n_layer, m->n_head, m->n_embd, m->block_size, m->bias, m->n_in_vocab, m->n_out_vocab, m->n_lm_heads, m->n_wtes, m->ftype};
+    memcpy(out10, v, sizeof(v));
+}
+extern "C" unsigned long long bark_b200_kernel_launches(void) { return g_kernel_launches; }
+extern "C" unsigned bark_b200_layernorm_fallbacks(struct bark_context * ctx) {
+    if (!ctx) return 0;
+    unsigned v = 0; BARK_CUDA_CHECK(cudaMemcpy(&v, ctx->d_ln_fallbacks, sizeof(v), cudaMemcpyDeviceToHost)); return v;
+}
+extern "C" const char * bark_b200_version(void) { return "bark_b200 r1 (sm_100a, parity path)"; }

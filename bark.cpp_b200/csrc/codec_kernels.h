@@ -1,0 +1,13 @@
+// Host-callable launchers of the EnCodec decoder kernels (codec_kernels.cu).
+#pragma once
+#include "model.h"
+
+namespace bark {
+
+void rvq_decode(const CodecModel & cm, const int32_t * d_codes /*[8][T]*/, int T, float * x /*[hidden][T]*/, cudaStream_t s);
+void conv1d(const float * x, int Cin, int T, const ConvW & cv, bool elu_in, const float * resid, float * y, cudaStream_t s);
+void convtr1d(const float * x, int Cin, int T, const ConvW & cv, int stride, float * y /*[Cout][T*stride]*/, cudaStream_t s);
+void lstm_layer(const float * x, int C, int T, const __half * wih, const __half * whh, const float * bih, const float * bhh,
+                const float * skip, float * gi_scratch /*[T][4C]*/, float * out, cudaStream_t s);
+
+}  // namespace bark

@@ -1,0 +1,139 @@
+// Shared device/host helpers for the B200-native bark hot path (sm_100a only).
+//
+// "Lane order": the reference's CPU dot products (ggml.c:2144 ggml_vec_dot_f32, ggml.c:2251
+// ggml_vec_dot_f16, pinned AVX2/FMA build) keep 32 independent float accumulators — element k goes
+// to virtual lane v = k % 32 and is folded in with one fused multiply-add, in increasing k — and
+// then add the 32 partials in a fixed tree (GGML_F32x8_REDUCE, ggml.c:1405-1422).  A CUDA warp has
+// exactly 32 lanes, so lane v of a warp owns virtual lane v: the serial chain lives in one thread,
+// the tree is five xor-shuffles.  Every bit-exact kernel in this library is built on that mapping.
+#pragma once
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#define BARK_CUDA_CHECK(expr)                                                                         \
+    do {                                                                                              \
+        cudaError_t err__ = (expr);                                                                   \
+        if (err__ != cudaSuccess) {                                                                   \
+            fprintf(stderr, "bark_b200: CUDA error %s at %s:%d: %s\n", cudaGetErrorName(err__), __FILE__, __LINE__, \
+                    cudaGetErrorString(err__));                                                       \
+            abort();                                                                                  \
+        }                                                                                             \
+    } while (0)
+
+namespace bark {
+
+// number of kernels this library launched (bench.py reports it as gpu_launches)
+extern unsigned long long g_kernel_launches;
+#define BARK_LAUNCH(kernel, grid, block, smem, stream, ...)                                           \
+    do {                                                                                              \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                                   \
+        ++::bark::g_kernel_launches;                                                                  \
+    } while (0)
+
+// weight element types as stored in ggml_weights.bin (ggml_type values)
+enum WType : int { W_F32 = 0, W_F16 = 1, W_Q4_0 = 2 };
+
+// ---------------------------------------------------------------------------------------------
+// Lane-interleaved ("LI") matrix layout.
+// A row of K elements (K % 32 == 0) is cut into chain steps c = k / 32 for virtual lane v = k % 32.
+// G consecutive chain steps of one lane are stored contiguously as one 16-byte vector
+// (G = 8 for f16, 4 for f32), vectors of the 32 lanes are adjacent:
+//     offset(k) = ((c / G) * 32 + v) * G + (c % G)          [elements, within the row]
+// so one warp-wide 16-byte load fetches G chain steps for all 32 lanes, fully coalesced (512 B).
+// Rows are padded to a multiple of 32*G elements; kernels never touch chain steps >= K/32.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline int li_group(int elem_bytes) { return 16 / elem_bytes; }
+__host__ __device__ inline int li_padded_k(int K, int elem_bytes) { const int q = 32 * li_group(elem_bytes); return (K + q - 1) / q * q; }
+__host__ __device__ inline int li_offset(int k, int G) { const int v = k & 31, c = k >> 5; return ((c / G) * 32 + v) * G + (c % G); }
+
+#ifdef __CUDACC__
+// GGML_F32x8_REDUCE (ggml.c:1405-1422) over the 32 lane partials; every lane returns the result.
+// x0+=x2, x1+=x3 (xor 16); x0+=x1 (xor 8); t[l]=x0[l]+x0[l+4] (xor 4); (t0+t1)+(t2+t3) (xor 1, xor 2).
+__device__ __forceinline__ float lane_tree_reduce(float a) {
+    a = __fadd_rn(a, __shfl_xor_sync(0xffffffffu, a, 16));
+    a = __fadd_rn(a, __shfl_xor_sync(0xffffffffu, a, 8));
+    a = __fadd_rn(a, __shfl_xor_sync(0xffffffffu, a, 4));
+    a = __fadd_rn(a, __shfl_xor_sync(0xffffffffu, a, 1));
+    a = __fadd_rn(a, __shfl_xor_sync(0xffffffffu, a, 2));
+    return a;
+}
+
+// same tree, over a 32-entry array held by ONE thread (index = virtual lane)
+__device__ __forceinline__ float lane_tree_reduce_local(const float (&a)[32]) {
+    float x0[8];
+#pragma unroll
+    for (int l = 0; l < 8; l++) x0[l] = __fadd_rn(__fadd_rn(a[l], a[16 + l]), __fadd_rn(a[8 + l], a[24 + l]));
+    float t0 = __fadd_rn(x0[0], x0[4]), t1 = __fadd_rn(x0[1], x0[5]), t2 = __fadd_rn(x0[2], x0[6]), t3 = __fadd_rn(x0[3], x0[7]);
+    return __fadd_rn(__fadd_rn(t0, t1), __fadd_rn(t2, t3));
+}
+
+// f32 -> f16 -> f32 round trip (what converting an activation row to the f16 vec_dot_type does,
+// ggml.c:12551-12555 + ggml_fp32_to_fp16_row RNE)
+__device__ __forceinline__ float round_f16(float x) { return __half2float(__float2half_rn(x)); }
+
+// ggml_v_expf, AVX2+FMA flavour (ggml.c:2706-2746), one lane
+__device__ __forceinline__ float ggml_v_expf_dev(float x) {
+    const float r = 0x1.8p23f;
+    const float z = __fmaf_rn(x, 0x1.715476p+0f, r);
+    const float n = __fsub_rn(z, r);
+    const float b = __fmaf_rn(-n, 0x1.7f7d1cp-20f, __fmaf_rn(-n, 0x1.62e4p-1f, x));
+    const uint32_t e = __float_as_uint(z) << 23;
+    const float k = __uint_as_float(e + 0x3f800000u);
+    const float an = fabsf(n);
+    const float u = __fmul_rn(b, b);
+    const float j = __fmaf_rn(__fmaf_rn(__fmaf_rn(0x1.0e4020p-7f, b, 0x1.573e2ep-5f), u, __fmaf_rn(0x1.555e66p-3f, b, 0x1.fffdb6p-2f)), u,
+                              __fmul_rn(0x1.ffffecp-1f, b));
+    if (!(an > 126.0f)) return __fmaf_rn(j, k, k);
+    const uint32_t g = (n <= 0.0f) ? 0x82000000u : 0u;
+    const float s1 = __uint_as_float(g + 0x7f000000u);
+    const float s2 = __uint_as_float(e - g);
+    if (an > 192.0f) return __fmul_rn(s1, s1);
+    return __fmul_rn(__fmaf_rn(s2, j, s2), s1);
+}
+
+// glibc 2.39 expf (sysdeps/ieee754/flt-32/e_expf.c; table = 2^(i/32) with the exponent folded out),
+// used by the soft_max tail columns (ggml.c:2880-2884).  Verified against host expf over 3.2e8
+// inputs on the build host ("libm on the device").
+__device__ __constant__ uint64_t c_exp2f_tab[32] = {
+    0x3ff0000000000000ULL, 0x3fefd9b0d3158574ULL, 0x3fefb5586cf9890fULL, 0x3fef9301d0125b51ULL,
+    0x3fef72b83c7d517bULL, 0x3fef54873168b9aaULL, 0x3fef387a6e756238ULL, 0x3fef1e9df51fdee1ULL,
+    0x3fef06fe0a31b715ULL, 0x3feef1a7373aa9cbULL, 0x3feedea64c123422ULL, 0x3feece086061892dULL,
+    0x3feebfdad5362a27ULL, 0x3feeb42b569d4f82ULL, 0x3feeab07dd485429ULL, 0x3feea47eb03a5585ULL,
+    0x3feea09e667f3bcdULL, 0x3fee9f75e8ec5f74ULL, 0x3feea11473eb0187ULL, 0x3feea589994cce13ULL,
+    0x3feeace5422aa0dbULL, 0x3feeb737b0cdc5e5ULL, 0x3feec49182a3f090ULL, 0x3feed503b23e255dULL,
+    0x3feee89f995ad3adULL, 0x3feeff76f2fb5e47ULL, 0x3fef199bdd85529cULL, 0x3fef3720dcef9069ULL,
+    0x3fef5818dcfba487ULL, 0x3fef7c97337b9b5fULL, 0x3fefa4afa2a490daULL, 0x3fefd0765b6e4540ULL,
+};
+__device__ __forceinline__ float glibc_expf_dev(float x) {
+    const uint32_t ux = __float_as_uint(x);
+    const uint32_t abstop = (ux >> 20) & 0x7ffu;
+    if (abstop >= 0x42bu) {                        // |x| >= 88 or nan
+        if (ux == 0xff800000u) return 0.0f;
+        if (abstop >= 0x7f8u) return x + x;
+        if (x > 0x1.62e42ep6f) return __int_as_float(0x7f800000);
+        if (x < -0x1.9fe368p6f) return 0.0f;
+    }
+    const double xd = (double) x;
+    double z = __dmul_rn(0x1.71547652b82fep+0 * 32.0, xd);
+    double kd = __dadd_rn(z, 0x1.8p+52);
+    const uint64_t ki = (uint64_t) __double_as_longlong(kd);
+    kd = __dsub_rn(kd, 0x1.8p+52);
+    const double r = __dsub_rn(z, kd);
+    uint64_t t = c_exp2f_tab[ki & 31];
+    t += ki << 47;
+    const double s = __longlong_as_double((long long) t);
+    const double C0 = 0x1.c6af84b912394p-5 / 32 / 32 / 32, C1 = 0x1.ebfce50fac4f3p-3 / 32 / 32, C2 = 0x1.62e42ff0c52d6p-1 / 32;
+    z = __dadd_rn(__dmul_rn(C0, r), C1);
+    const double r2 = __dmul_rn(r, r);
+    double y = __dadd_rn(__dmul_rn(C2, r), 1.0);
+    y = __dadd_rn(__dmul_rn(z, r2), y);
+    y = __dmul_rn(y, s);
+    return __double2float_rn(y);
+}
+#endif  // __CUDACC__
+
+}  // namespace bark

@@ -1,0 +1,61 @@
+// bark_context: everything one generation needs, owned by bark_load_model / bark_free.
+// Host control plane in C++ (like the reference's bark.cpp:133-164), all tensors in HBM.
+#pragma once
+#include "../../include/bark.h"
+#include "model.h"
+
+#include <map>
+#include <random>
+#include <string>
+#include <vector>
+
+struct bark_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+
+    bark::GPTModel semantic, coarse, fine;
+    bark::CodecModel codec;
+    std::map<std::string, int32_t> token_to_id;      // WordPiece vocabulary (bark.cpp:664-690)
+
+    __half * d_gelu_tab = nullptr;                   // 65536-entry table, ggml.c:3795-3810
+    unsigned * d_ln_fallbacks = nullptr;             // rows whose LayerNorm sums had to be replayed sequentially
+
+    bark::Workspace ws;
+    float * h_logits = nullptr;                      // pinned, max(n_out) or 1024*fine_vocab
+    int32_t * h_tok = nullptr;                       // pinned, 8*1024 ids
+
+    // codec scratch
+    float * c_buf[3] = {nullptr, nullptr, nullptr}; size_t c_cap = 0;   // ping-pong activations (floats)
+    float * c_gi = nullptr;                                            // LSTM input projections
+    int32_t * d_codes = nullptr;
+
+    std::mt19937 rng;                                // seeded once at load (bark.cpp:1179)
+
+    std::vector<int32_t> tokens;                     // 513 prompt ids
+    std::vector<int32_t> semantic_tokens;
+    std::vector<int32_t> coarse_tokens;              // [T][2] flattened
+    std::vector<int32_t> fine_tokens;                // [T][8] flattened
+    std::vector<float> audio;
+
+    bark_context_params params;
+    bark_statistics stats{};
+
+    std::vector<void *> device_allocs;               // everything cudaMalloc'ed for this context
+};
+
+namespace bark {
+
+// loader.cu
+bool load_model_file(const std::string & path, bark_context * ctx);
+void * ctx_alloc(bark_context * ctx, size_t bytes);
+
+// gpt_forward.cu — one evaluation of a causal model; mirrors bark_eval_encoder_internal (bark.cpp:1586-1643)
+bool gpt_eval(bark_context * ctx, GPTModel & m, const int32_t * tokens, int n, int * n_past, bool merge_ctx, float * logits_host);
+// one non-causal pass of the fine model; mirrors bark_eval_fine_encoder_internal (bark.cpp:1907-1959)
+bool fine_eval(bark_context * ctx, const int32_t * in_buffer /*[8][1024]*/, int nn, float * logits_host /*[1024][n_out]*/);
+// EnCodec decode; codes [8][T] on the host; result in ctx->audio
+bool codec_decode(bark_context * ctx, const int32_t * codes, int T);
+
+int64_t now_us();
+
+}  // namespace bark

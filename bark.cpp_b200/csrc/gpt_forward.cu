@@ -1,0 +1,145 @@
+// Per-call orchestration of the GPT and EnCodec kernels: the device-side replacement of
+// bark_eval_encoder_internal (bark.cpp:1586-1643), bark_eval_fine_encoder_internal (bark.cpp:1907-1959)
+// and encodec_eval (encodec.cpp/encodec.cpp:819-847).  No graph is built or allocated per step: the
+// workspace is sized once at load for the worst case (block_size rows).
+#include "codec_kernels.h"
+#include "context.h"
+#include "gpt_kernels.h"
+
+#include <algorithm>
+#include <time.h>
+
+namespace bark {
+
+int64_t now_us() {
+    timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (int64_t) ts.tv_sec * 1000000 + ts.tv_nsec / 1000;
+}
+
+static int act_kp(const GPTModel & m, int K) { return li_padded_k(K, m.wtype == W_F16 ? 2 : 4); }
+static size_t act_elem(const GPTModel & m) { return m.wtype == W_F16 ? 2 : 4; }
+
+// transformer body shared by the causal and the fine model; x [N][E] is updated in place.
+// K/V rows of this call go to k_dst/v_dst (KV-cache slot of position n_past, or the fine model's scratch),
+// attention then reads n_kv rows starting at k_all/v_all.
+static void run_layers(bark_context * ctx, GPTModel & m, int N, int n_past, bool causal) {
+    Workspace & ws = ctx->ws;
+    cudaStream_t s = ctx->stream;
+    const int E = m.n_embd, H = m.n_head;
+    const int kpE = act_kp(m, E), kp4E = act_kp(m, 4 * E);
+    for (int il = 0; il < m.n_layer; il++) {
+        const GPTLayer & L = m.layers[(size_t) il];
+        layernorm_act(ws.x, N, E, L.ln_1_g, L.ln_1_b, ws.act, m.wtype, kpE, ctx->d_ln_fallbacks, s);
+        float * k_all, * v_all, * k_dst, * v_dst; int n_kv;
+        if (causal) {
+            k_all = m.mem_k + (size_t) il * m.block_size * E; v_all = m.mem_v + (size_t) il * m.block_size * E;
+            k_dst = k_all + (size_t) n_past * E; v_dst = v_all + (size_t) n_past * E; n_kv = n_past + N;      // bark.cpp:1294-1300
+        } else {
+            k_all = k_dst = ws.kbuf; v_all = v_dst = ws.vbuf; n_kv = N;
+        }
+        MatmulEpilogue qkv; qkv.mode = EPI_QKV; qkv.out = ws.q; qkv.ldo = E; qkv.k_out = k_dst; qkv.v_out = v_dst;
+        lane_matmul(L.c_attn, ws.act, N, qkv, s);
+        attention(ws.q, k_all, v_all, N, n_kv, n_past, E, H, causal, ws.scores, ws.act, m.wtype, kpE, s);
+        MatmulEpilogue res; res.mode = EPI_RESID; res.out = ws.x; res.ldo = E;
+        lane_matmul(L.c_proj, ws.act, N, res, s);                                                              // + inpL
+        layernorm_act(ws.x, N, E, L.ln_2_g, L.ln_2_b, ws.act, m.wtype, kpE, ctx->d_ln_fallbacks, s);
+        MatmulEpilogue ge; ge.mode = EPI_GELU_ACT; ge.act_out = ws.act2; ge.act_wt = (int) m.wtype; ge.act_Kp = kp4E; ge.gelu_tab = ctx->d_gelu_tab;
+        lane_matmul(L.fc, ws.act, N, ge, s);
+        lane_matmul(L.proj, ws.act2, N, res, s);                                                                // + inpFF
+    }
+}
+
+bool gpt_eval(bark_context * ctx, GPTModel & m, const int32_t * tokens, int n, int * n_past, bool merge_ctx, float * logits_host) {
+    if (!n_past) { fprintf(stderr, "%s: n_past is null\n", __func__); return false; }
+    const int64_t t0 = now_us();
+    Workspace & ws = ctx->ws;
+    cudaStream_t s = ctx->stream;
+    const int E = m.n_embd;
+    int N = n;
+    bool merge = false;
+    if (*n_past > 0) {
+        if (N != 1) { fprintf(stderr, "%s: decoding expects one token per step (got %d)\n", __func__, N); return false; }
+    } else if (merge_ctx) {
+        if (N != 513) { fprintf(stderr, "%s: merged prompt must hold 256+256+1 ids (got %d)\n", __func__, N); return false; }
+        N = 257; merge = true;                                                                                  // bark.cpp:1230-1233
+    }
+    if (N < 1 || *n_past + N > m.block_size) { fprintf(stderr, "%s: context overflow (n_past %d + %d > %d)\n", __func__, *n_past, N, m.block_size); return false; }
+    memcpy(ctx->h_tok, tokens, (size_t) n * sizeof(int32_t));
+    BARK_CUDA_CHECK(cudaMemcpyAsync(ws.tok, ctx->h_tok, (size_t) n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    gpt_embed_causal(m, ws.tok, N, *n_past, merge, ws.x, s);
+    run_layers(ctx, m, N, *n_past, true);
+    // final norm + lm_head on the last position only (bark.cpp:1391-1405)
+    const int kpE = act_kp(m, E);
+    layernorm_act(ws.x + (size_t)(N - 1) * E, 1, E, m.ln_f_g, m.ln_f_b, ws.act, m.wtype, kpE, ctx->d_ln_fallbacks, s);
+    MatmulEpilogue st; st.mode = EPI_STORE; st.out = ws.logits; st.ldo = m.n_out_vocab;
+    lane_matmul(m.lm_head[0], ws.act, 1, st, s);
+    BARK_CUDA_CHECK(cudaMemcpyAsync(ctx->h_logits, ws.logits, (size_t) m.n_out_vocab * sizeof(float), cudaMemcpyDeviceToHost, s));
+    BARK_CUDA_CHECK(cudaStreamSynchronize(s));
+    memcpy(logits_host, ctx->h_logits, (size_t) m.n_out_vocab * sizeof(float));
+    *n_past += N;
+    m.t_predict_us += now_us() - t0;
+    return true;
+}
+
+bool fine_eval(bark_context * ctx, const int32_t * in_buffer, int nn, float * logits_host) {
+    GPTModel & m = ctx->fine;
+    if (nn < 1 || nn > 7) { fprintf(stderr, "%s: codebook index %d out of range\n", __func__, nn); return false; }
+    const int64_t t0 = now_us();
+    Workspace & ws = ctx->ws;
+    cudaStream_t s = ctx->stream;
+    const int E = m.n_embd, N = 1024;
+    memcpy(ctx->h_tok, in_buffer, (size_t) 8 * 1024 * sizeof(int32_t));
+    BARK_CUDA_CHECK(cudaMemcpyAsync(ws.tok, ctx->h_tok, (size_t) 8 * 1024 * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    gpt_embed_fine(m, ws.tok, nn, ws.x, s);
+    run_layers(ctx, m, N, 0, false);
+    const int kpE = act_kp(m, E);
+    layernorm_act(ws.x, N, E, m.ln_f_g, m.ln_f_b, ws.act, m.wtype, kpE, ctx->d_ln_fallbacks, s);
+    MatmulEpilogue st; st.mode = EPI_STORE; st.out = ws.logits; st.ldo = m.n_out_vocab;
+    lane_matmul(m.lm_head[nn - 1], ws.act, N, st, s);                                                           // n_codes_given = 1 (bark.cpp:61,1573)
+    const size_t nb = (size_t) N * m.n_out_vocab * sizeof(float);
+    BARK_CUDA_CHECK(cudaMemcpyAsync(ctx->h_logits, ws.logits, nb, cudaMemcpyDeviceToHost, s));
+    BARK_CUDA_CHECK(cudaStreamSynchronize(s));
+    memcpy(logits_host, ctx->h_logits, nb);
+    m.t_predict_us += now_us() - t0;
+    return true;
+}
+
+bool codec_decode(bark_context * ctx, const int32_t * codes, int T) {
+    if (T < 7) { fprintf(stderr, "%s: need at least 7 frames (reflect padding of the k=7 convolutions), got %d\n", __func__, T); return false; }
+    CodecModel & cm = ctx->codec;
+    cudaStream_t s = ctx->stream;
+    static const int ratios[4] = {8, 5, 4, 2};
+    const size_t need = (size_t) 10240 * T + 1024;             // largest activation: [64][160T] = [32][320T] = 10240*T floats
+    if (need > ctx->c_cap) {
+        for (int i = 0; i < 3; i++) { if (ctx->c_buf[i]) BARK_CUDA_CHECK(cudaFree(ctx->c_buf[i])); BARK_CUDA_CHECK(cudaMalloc(&ctx->c_buf[i], need * sizeof(float))); }
+        if (ctx->c_gi) BARK_CUDA_CHECK(cudaFree(ctx->c_gi));
+        BARK_CUDA_CHECK(cudaMalloc(&ctx->c_gi, (size_t) T * 2048 * sizeof(float)));
+        if (ctx->d_codes) BARK_CUDA_CHECK(cudaFree(ctx->d_codes));
+        BARK_CUDA_CHECK(cudaMalloc(&ctx->d_codes, (size_t) 8 * T * sizeof(int32_t)));
+        ctx->c_cap = need;
+    }
+    float * a = ctx->c_buf[0], * b = ctx->c_buf[1], * c = ctx->c_buf[2];
+    BARK_CUDA_CHECK(cudaMemcpyAsync(ctx->d_codes, codes, (size_t) 8 * T * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    rvq_decode(cm, ctx->d_codes, T, a, s);                                                // [128][T]
+    conv1d(a, cm.hidden_dim, T, cm.init, false, nullptr, b, s);                          // [512][T]
+    int C = cm.init.cout;
+    lstm_layer(b, C, T, cm.lstm_ih_w[0], cm.lstm_hh_w[0], cm.lstm_ih_b[0], cm.lstm_hh_b[0], nullptr, ctx->c_gi, a, s);
+    lstm_layer(a, C, T, cm.lstm_ih_w[1], cm.lstm_hh_w[1], cm.lstm_ih_b[1], cm.lstm_hh_b[1], b /*skip (decoder.h:72)*/, ctx->c_gi, c, s);
+    float * cur = c, * t1 = a, * t2 = b;
+    int L = T;
+    for (int i = 0; i < 4; i++) {
+        convtr1d(cur, C, L, cm.blk[i].us, ratios[i], t1, s);          // ELU fused on the input; -> [C/2][L*r]
+        C /= 2; L *= ratios[i];
+        conv1d(t1, C, L, cm.blk[i].sc, false, nullptr, t2, s);        // shortcut on the raw up-sampled signal
+        conv1d(t1, C, L, cm.blk[i].c1, true, nullptr, cur, s);        // ELU -> k3 -> [C/2][L]
+        conv1d(cur, C / 2, L, cm.blk[i].c2, true, t2, t1, s);         // ELU -> k1, + shortcut
+        std::swap(cur, t1);
+    }
+    conv1d(cur, C, L, cm.final_conv, true, nullptr, t1, s);           // ELU -> k7 -> [1][320 T]
+    ctx->audio.resize((size_t) L);
+    BARK_CUDA_CHECK(cudaMemcpyAsync(ctx->audio.data(), t1, (size_t) L * sizeof(float), cudaMemcpyDeviceToHost, s));
+    BARK_CUDA_CHECK(cudaStreamSynchronize(s));
+    return true;
+}
+
+}  // namespace bark

@@ -1,0 +1,30 @@
+// Host-callable launchers of the GPT kernels (gpt_kernels.cu, decode_kernels.cu).
+#pragma once
+#include "model.h"
+
+namespace bark {
+
+enum EpiMode : int { EPI_STORE = 0, EPI_RESID = 1, EPI_GELU_ACT = 2, EPI_QKV = 3 };
+
+struct MatmulEpilogue {
+    int mode = EPI_STORE;
+    float * out = nullptr; int ldo = 0;              // STORE / RESID target ([m][ldo]); QKV: q rows with ldo = E
+    float * k_out = nullptr, * v_out = nullptr;      // QKV: K/V rows (KV cache slot of the first new position, or the fine model's buffers)
+    void * act_out = nullptr; int act_wt = 0, act_Kp = 0;   // GELU_ACT: operand for the following mul_mat
+    const __half * gelu_tab = nullptr;
+};
+
+void permute_to_li(const void * src_rowmajor, void * dst_li, int n_out, int K, WType t, cudaStream_t s);
+
+void gpt_embed_causal(const GPTModel & m, const int32_t * d_tok, int N, int n_past, bool merge, float * x, cudaStream_t s);
+void gpt_embed_fine(const GPTModel & m, const int32_t * d_ids, int nn, float * x, cudaStream_t s);
+
+void layernorm_act(const float * x, int rows, int E, const float * g, const float * b, void * act, WType wt, int Kp,
+                   unsigned * fallback_counter, cudaStream_t s);
+
+void lane_matmul(const DMat & W, const void * act, int rows, const MatmulEpilogue & ep, cudaStream_t s);
+
+void attention(const float * Q, const float * Kc, const float * Vc, int N, int n_kv, int n_past, int E, int H, bool causal,
+               float * scores, void * act, WType wt, int Kp, cudaStream_t s);
+
+}  // namespace bark
