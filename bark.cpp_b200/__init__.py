@@ -48,6 +48,7 @@ EXPORTS = [
     "bark_b200_sample", "bark_b200_reseed", "bark_b200_tokenize", "bark_b200_forward_text_encoder",
     "bark_b200_forward_coarse_encoder", "bark_b200_forward_fine_encoder", "bark_b200_get_tokens", "bark_b200_set_tokens",
     "bark_b200_get_stats", "bark_b200_get_hparams", "bark_b200_kernel_launches", "bark_b200_layernorm_fallbacks",
+    "bark_b200_profile_enable", "bark_b200_profile_report", "bark_b200_io_counters",
     "ggml_time_init", "ggml_time_us", "ggml_time_ms",
 ]
 
@@ -103,6 +104,10 @@ def lib() -> C.CDLL:
     L.bark_b200_kernel_launches.restype = C.c_ulonglong
     L.bark_b200_layernorm_fallbacks.restype = C.c_uint
     L.bark_b200_layernorm_fallbacks.argtypes = [vp]
+    L.bark_b200_profile_enable.argtypes = [C.c_int]
+    L.bark_b200_profile_report.restype = C.c_int
+    L.bark_b200_profile_report.argtypes = [C.c_char_p, C.c_int]
+    L.bark_b200_io_counters.argtypes = [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), C.c_int]
     L.ggml_time_us.restype = C.c_int64
     _lib = L
     return L
@@ -235,3 +240,21 @@ class Bark:
 
 def kernel_launches() -> int:
     return int(lib().bark_b200_kernel_launches())
+
+
+def profile_enable(on: bool):
+    lib().bark_b200_profile_enable(int(on))
+
+
+def profile_report() -> dict:
+    import json
+    n = lib().bark_b200_profile_report(None, 0)
+    buf = C.create_string_buffer(n + 16)
+    lib().bark_b200_profile_report(buf, n + 16)
+    return json.loads(buf.value.decode())
+
+
+def io_counters(reset: bool = False):
+    a, b = C.c_ulonglong(0), C.c_ulonglong(0)
+    lib().bark_b200_io_counters(C.byref(a), C.byref(b), int(reset))
+    return a.value, b.value

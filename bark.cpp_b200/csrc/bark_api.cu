@@ -358,9 +358,9 @@ extern "C" bool bark_b200_forward_text_encoder(struct bark_context * ctx, int) {
 extern "C" bool bark_b200_forward_coarse_encoder(struct bark_context * ctx, int) { return ctx && run_coarse(ctx); }
 extern "C" bool bark_b200_forward_fine_encoder(struct bark_context * ctx, int) { return ctx && run_fine(ctx); }
 // the reference also exports these three as C++ symbols without a header (bark.cpp:1703,1865,2061)
-bool bark_forward_text_encoder(struct bark_context * ctx, int n) { return bark_b200_forward_text_encoder(ctx, n); }
-bool bark_forward_coarse_encoder(struct bark_context * ctx, int n) { return bark_b200_forward_coarse_encoder(ctx, n); }
-bool bark_forward_fine_encoder(struct bark_context * ctx, int n) { return bark_b200_forward_fine_encoder(ctx, n); }
+BARK_API bool bark_forward_text_encoder(struct bark_context * ctx, int n) { return bark_b200_forward_text_encoder(ctx, n); }
+BARK_API bool bark_forward_coarse_encoder(struct bark_context * ctx, int n) { return bark_b200_forward_coarse_encoder(ctx, n); }
+BARK_API bool bark_forward_fine_encoder(struct bark_context * ctx, int n) { return bark_b200_forward_fine_encoder(ctx, n); }
 
 extern "C" bool bark_generate_audio(struct bark_context * ctx, const char * text, int n_threads) {
     (void) n_threads;                      // CPU thread count of the reference's backend; nothing to size here

@@ -28,9 +28,20 @@ namespace bark {
 
 // number of kernels this library launched (bench.py reports it as gpu_launches)
 extern unsigned long long g_kernel_launches;
+// host<->device traffic issued by the library (bench.py: e2e.h2d_bytes_per_step / d2h_bytes_per_step)
+extern unsigned long long g_h2d_bytes, g_d2h_bytes;
+// optional per-launch device timing (prof.cu): CUDA events on the launching stream around every kernel
+extern bool g_prof_on;
+void prof_begin(const char * name, cudaStream_t s, double work);
+void prof_end(cudaStream_t s);
+// `work` annotates the NEXT launch with its algorithmic bytes (or flops) for the roofline report
+extern double g_next_work;
 #define BARK_LAUNCH(kernel, grid, block, smem, stream, ...)                                           \
     do {                                                                                              \
+        if (::bark::g_prof_on) ::bark::prof_begin(#kernel, (stream), ::bark::g_next_work);            \
         kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                                   \
+        if (::bark::g_prof_on) ::bark::prof_end((stream));                                            \
+        ::bark::g_next_work = 0.0;                                                                    \
         ++::bark::g_kernel_launches;                                                                  \
     } while (0)
 

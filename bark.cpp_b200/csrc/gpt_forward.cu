@@ -65,7 +65,7 @@ bool gpt_eval(bark_context * ctx, GPTModel & m, const int32_t * tokens, int n, i
     }
     if (N < 1 || *n_past + N > m.block_size) { fprintf(stderr, "%s: context overflow (n_past %d + %d > %d)\n", __func__, *n_past, N, m.block_size); return false; }
     memcpy(ctx->h_tok, tokens, (size_t) n * sizeof(int32_t));
-    BARK_CUDA_CHECK(cudaMemcpyAsync(ws.tok, ctx->h_tok, (size_t) n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    BARK_CUDA_CHECK(cudaMemcpyAsync(ws.tok, ctx->h_tok, (size_t) n * sizeof(int32_t), cudaMemcpyHostToDevice, s)); g_h2d_bytes += (size_t) n * sizeof(int32_t);
     gpt_embed_causal(m, ws.tok, N, *n_past, merge, ws.x, s);
     run_layers(ctx, m, N, *n_past, true);
     // final norm + lm_head on the last position only (bark.cpp:1391-1405)
@@ -73,7 +73,7 @@ bool gpt_eval(bark_context * ctx, GPTModel & m, const int32_t * tokens, int n, i
     layernorm_act(ws.x + (size_t)(N - 1) * E, 1, E, m.ln_f_g, m.ln_f_b, ws.act, m.wtype, kpE, ctx->d_ln_fallbacks, s);
     MatmulEpilogue st; st.mode = EPI_STORE; st.out = ws.logits; st.ldo = m.n_out_vocab;
     lane_matmul(m.lm_head[0], ws.act, 1, st, s);
-    BARK_CUDA_CHECK(cudaMemcpyAsync(ctx->h_logits, ws.logits, (size_t) m.n_out_vocab * sizeof(float), cudaMemcpyDeviceToHost, s));
+    BARK_CUDA_CHECK(cudaMemcpyAsync(ctx->h_logits, ws.logits, (size_t) m.n_out_vocab * sizeof(float), cudaMemcpyDeviceToHost, s)); g_d2h_bytes += (size_t) m.n_out_vocab * sizeof(float);
     BARK_CUDA_CHECK(cudaStreamSynchronize(s));
     memcpy(logits_host, ctx->h_logits, (size_t) m.n_out_vocab * sizeof(float));
     *n_past += N;
@@ -89,7 +89,7 @@ bool fine_eval(bark_context * ctx, const int32_t * in_buffer, int nn, float * lo
     cudaStream_t s = ctx->stream;
     const int E = m.n_embd, N = 1024;
     memcpy(ctx->h_tok, in_buffer, (size_t) 8 * 1024 * sizeof(int32_t));
-    BARK_CUDA_CHECK(cudaMemcpyAsync(ws.tok, ctx->h_tok, (size_t) 8 * 1024 * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    BARK_CUDA_CHECK(cudaMemcpyAsync(ws.tok, ctx->h_tok, (size_t) 8 * 1024 * sizeof(int32_t), cudaMemcpyHostToDevice, s)); g_h2d_bytes += (size_t) 8 * 1024 * sizeof(int32_t);
     gpt_embed_fine(m, ws.tok, nn, ws.x, s);
     run_layers(ctx, m, N, 0, false);
     const int kpE = act_kp(m, E);
@@ -97,7 +97,7 @@ bool fine_eval(bark_context * ctx, const int32_t * in_buffer, int nn, float * lo
     MatmulEpilogue st; st.mode = EPI_STORE; st.out = ws.logits; st.ldo = m.n_out_vocab;
     lane_matmul(m.lm_head[nn - 1], ws.act, N, st, s);                                                           // n_codes_given = 1 (bark.cpp:61,1573)
     const size_t nb = (size_t) N * m.n_out_vocab * sizeof(float);
-    BARK_CUDA_CHECK(cudaMemcpyAsync(ctx->h_logits, ws.logits, nb, cudaMemcpyDeviceToHost, s));
+    BARK_CUDA_CHECK(cudaMemcpyAsync(ctx->h_logits, ws.logits, nb, cudaMemcpyDeviceToHost, s)); g_d2h_bytes += nb;
     BARK_CUDA_CHECK(cudaStreamSynchronize(s));
     memcpy(logits_host, ctx->h_logits, nb);
     m.t_predict_us += now_us() - t0;
@@ -119,7 +119,7 @@ bool codec_decode(bark_context * ctx, const int32_t * codes, int T) {
         ctx->c_cap = need;
     }
     float * a = ctx->c_buf[0], * b = ctx->c_buf[1], * c = ctx->c_buf[2];
-    BARK_CUDA_CHECK(cudaMemcpyAsync(ctx->d_codes, codes, (size_t) 8 * T * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    BARK_CUDA_CHECK(cudaMemcpyAsync(ctx->d_codes, codes, (size_t) 8 * T * sizeof(int32_t), cudaMemcpyHostToDevice, s)); g_h2d_bytes += (size_t) 8 * T * sizeof(int32_t);
     rvq_decode(cm, ctx->d_codes, T, a, s);                                                // [128][T]
     conv1d(a, cm.hidden_dim, T, cm.init, false, nullptr, b, s);                          // [512][T]
     int C = cm.init.cout;
@@ -137,7 +137,7 @@ bool codec_decode(bark_context * ctx, const int32_t * codes, int T) {
     }
     conv1d(cur, C, L, cm.final_conv, true, nullptr, t1, s);           // ELU -> k7 -> [1][320 T]
     ctx->audio.resize((size_t) L);
-    BARK_CUDA_CHECK(cudaMemcpyAsync(ctx->audio.data(), t1, (size_t) L * sizeof(float), cudaMemcpyDeviceToHost, s));
+    BARK_CUDA_CHECK(cudaMemcpyAsync(ctx->audio.data(), t1, (size_t) L * sizeof(float), cudaMemcpyDeviceToHost, s)); g_d2h_bytes += (size_t) L * sizeof(float);
     BARK_CUDA_CHECK(cudaStreamSynchronize(s));
     return true;
 }

@@ -233,6 +233,10 @@ __global__ void __launch_bounds__(256) lane_matmul_kernel(const T * __restrict__
 
 void lane_matmul(const DMat & W, const void * act, int rows, const MatmulEpilogue & ep, cudaStream_t s) {
     const int gx = (W.n_out + 7) / 8;
+    {   // roofline annotation: decode (1 row) streams the weights once -> bytes; multi-row passes are dense contractions -> flops
+        const double es = W.type == W_F16 ? 2.0 : 4.0;
+        g_next_work = rows == 1 ? (double) W.n_out * W.K * es + W.K * es + W.n_out * 4.0 : 2.0 * rows * (double) W.n_out * W.K;
+    }
     if (W.type == W_F16) {
         if (rows == 1) BARK_LAUNCH((lane_matmul_kernel<__half, 1>), dim3(gx, 1), 256, 0, s, (const __half *) W.p, W.K, W.Kp, W.n_out, (const __half *) act, rows, ep);
         else           BARK_LAUNCH((lane_matmul_kernel<__half, 8>), dim3(gx, (rows + 7) / 8), 256, 0, s, (const __half *) W.p, W.K, W.Kp, W.n_out, (const __half *) act, rows, ep);

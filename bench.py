@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the bark.cpp hot path on B200 (driver contract: one JSON line from rank 0).
+
+  python bench.py --gpus N --steps K --warmup W            our CUDA path through the C-ABI (libbark_b200.so)
+  python bench.py --impl reference --gpus N --steps K ...  the reference's own CPU path (oracle/_ref) on the host cores
+
+Workload (BASELINE.json configs[1]): bark-small dimensions, f16 GPT + f16 codec, batch 1 per GPU, full
+semantic -> coarse -> fine -> EnCodec, synthetic seeded weights (no checkpoint is reachable offline), prompt
+"hello world", seed 0, n_steps_text_encoder = 138 -> 138 semantic / 414 coarse / 6144 fine samples, 207 frames,
+66 240 samples = 2.76 s of 24 kHz audio (the README-sized clip of BASELINE.md).  One "step" = one
+bark_generate_audio call.  metric = audio seconds produced per wall second (inverse RTF); per-stage tokens/s
+ride along.  N > 1: one context per GPU, distinct prompt seeds, no collective on the data path (SURVEY §8e:
+prompts are independent units) -> weak scaling, value = N clips / max-over-ranks time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+os.environ.setdefault("BARK_B200_QUIET", "1")
+
+import numpy as np  # noqa: E402
+
+import __graft_entry__ as graft  # noqa: E402
+
+METRIC = "audio sec/sec (inverse RTF), bark-small f16, batch 1 per GPU, semantic->coarse->fine->encodec"
+UNIT = "audio_s/s"
+PROMPT = "hello world"
+N_STEPS_TEXT = 138
+SAMPLE_RATE = 24000
+FIXTURE_DIR = os.environ.get("BARK_B200_FIXTURES", "/tmp/bark_b200_fixtures")
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], tflops=d.get("bf16_tflops_sustained", d["bf16_tflops"]), tflops_burst=d["bf16_tflops"], source="measured")
+    return dict(hbm_gbs=6650.0, tflops=1400.0, tflops_burst=1590.0, source="fallback")
+
+
+def weights_path(config="small", ftype="f16", seed=1234):
+    import importlib
+    graft.load_package()
+    weights = importlib.import_module("bark_cpp_b200.weights")
+    os.makedirs(FIXTURE_DIR, exist_ok=True)
+    path = os.path.join(FIXTURE_DIR, f"{config}_{ftype}_{seed}.bin")
+    if not os.path.exists(path):
+        tmp = path + f".tmp{os.getpid()}"
+        weights.write_weights(tmp, weights.CONFIGS[config](weights.F16 if ftype == "f16" else weights.F32), seed)
+        os.replace(tmp, path)
+    return path
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device=0):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def dist_env():
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def algorithmic_work(pkg_bark):
+    """Per-clip algorithmic bytes / flops of the two roofline regimes (SURVEY §8d formulas), from the loaded header."""
+    out = {}
+    for which, name in ((0, "semantic"), (1, "coarse"), (2, "fine")):
+        L, H, E, ctx, bias, n_in, n_out, n_heads, n_wtes, ftype = [int(v) for v in pkg_bark.hparams(which)]
+        bpw = 2 if ftype == 1 else 4
+        out[name] = dict(L=L, E=E, n_out=n_out, bpw=bpw,
+                         decode_weight_bytes=(12 * L * E * E + n_out * E) * bpw,
+                         dense_flops=lambda N, rows_out, L=L, E=E, n_out=n_out: 2 * N * 12 * L * E * E + 4 * N * N * E * L + 2 * rows_out * E * n_out)
+    return out
+
+
+def run_ours(args):
+    rank, world, local = dist_env()
+    pkg = graft.load_package()
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        torch.cuda.set_device(local)
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist = dist_mod
+    path = weights_path()
+    if dist:
+        dist.barrier()
+    device = local if world > 1 else int(os.environ.get("BARK_B200_DEVICE", "0"))
+    b = pkg.Bark(path, seed=rank, n_steps_text_encoder=N_STEPS_TEXT, device=device)
+    prompt = PROMPT if rank == 0 else f"{PROMPT} {rank}"
+
+    def sync_all():
+        if dist:
+            dist.barrier()
+
+    for _ in range(args.warmup):
+        audio = b.generate(prompt)
+    n_audio = audio.size if args.warmup else None
+
+    # ---- timed region: EXACTLY K steps, barrier + sync on both sides, wall clock around the public C-ABI call with
+    # host buffers (prompt text in, waveform copied out) = the e2e figure; the device-event figure is taken per kernel below
+    sampler = ClockSampler(device)
+    pkg.io_counters(reset=True)
+    launches0 = pkg.kernel_launches()
+    sync_all()
+    sampler.start()
+    t0 = time.perf_counter()
+    stage_us = np.zeros(3); n_samples = np.zeros(3)
+    for _ in range(args.steps):
+        audio = b.generate(prompt)
+        s, pm = b.stats()
+        stage_us += [s.t_semantic_us, s.t_coarse_us, s.t_fine_us]
+    sync_all()
+    elapsed = time.perf_counter() - t0
+    clocks = sampler.stop()
+    launches = pkg.kernel_launches() - launches0
+    h2d, d2h = pkg.io_counters()
+    n_audio = audio.size
+    s, pm = b.stats()
+    n_samples = [pm[0][2], pm[1][2], pm[2][2]]        # cumulative since load (reference semantics, bark.cpp:1698)
+    n_calls = args.warmup + args.steps
+
+    if dist:
+        import torch
+        t = torch.tensor([elapsed], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_max = float(t.item())
+        tot = torch.tensor([float(n_audio)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        total_audio_samples = float(tot.item())
+    else:
+        elapsed_max, total_audio_samples = elapsed, float(n_audio)
+    audio_s_per_step = total_audio_samples / SAMPLE_RATE
+    e2e_value = audio_s_per_step * args.steps / elapsed_max
+
+    # ---- per-kernel device time (CUDA events on the launching stream) for the roofline: one extra profiled step on rank 0
+    roofline, kernels, value = None, None, e2e_value
+    if rank == 0:
+        pkg.profile_enable(True)
+        b.generate(prompt)
+        rep = pkg.profile_report()
+        pkg.profile_enable(False)
+        P = peaks()
+        tot_ms = sum(v["ms"] for v in rep.values()) or 1.0
+        kernels = {k: dict(launches=v["launches"], ms=round(v["ms"], 3), share=round(v["ms"] / tot_ms, 4)) for k, v in sorted(rep.items(), key=lambda kv: -kv[1]["ms"])}
+        top = max(rep.items(), key=lambda kv: kv[1]["ms"])
+        name, v = top
+        per_launch_work = v["work"] / max(v["launches"], 1)
+        per_launch_s = v["ms"] * 1e-3 / max(v["launches"], 1)
+        is_hbm = "1>" in name or "decode" in name      # single-row matmul / decode kernels stream weights; multi-row passes are dense contractions
+        if v["work"] > 0:
+            if is_hbm:
+                ach = per_launch_work / per_launch_s / 1e9
+                roofline = dict(kernel=name, bound="hbm", achieved=round(ach, 1), peak=P["hbm_gbs"], unit="GB/s", frac=round(ach / P["hbm_gbs"], 4), traffic=None,
+                                peak_source=P["source"], launches=v["launches"], avg_launch_us=round(per_launch_s * 1e6, 2))
+            else:
+                ach = per_launch_work / per_launch_s / 1e12
+                roofline = dict(kernel=name, bound="tensor", achieved=round(ach, 2), peak=P["tflops"], unit="TFLOP/s", frac=round(ach / P["tflops"], 4), traffic=None,
+                                peak_source=P["source"] + " (sustained bf16 cuBLAS)", launches=v["launches"], avg_launch_us=round(per_launch_s * 1e6, 2),
+                                note="bit-exact path: f16 operands, fp32 FMA chain in the reference's lane order on CUDA cores; tensor-core peak shown as the ceiling the contraction would have without the parity constraint")
+        # value = same metric with inputs resident: sum of device kernel time of the profiled step (no host sampling, no copies)
+        value = audio_s_per_step / world / (tot_ms * 1e-3) * world if tot_ms else e2e_value
+
+    if rank != 0:
+        b.close()
+        if dist:
+            dist.destroy_process_group()
+        return
+    result = {
+        "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(elapsed_max / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16 weights/operands, f32 accumulate (reference arithmetic)", "data": "synthetic (seeded random weights in ggml_weights.bin format, prompt 'hello world')",
+        "config": {"workload": "bark-small f16, batch=1 per GPU, n_steps_text_encoder=138 -> 2.76 s clip (BASELINE configs[1])", "parallelism": f"replica x{world} (one prompt per GPU, no collective)",
+                   "mode": "parity (token ids bit-identical to the CPU reference)", "l2": "inputs larger than L2: 0.84 GB of weights streamed per clip vs 126 MB L2; no flush needed"},
+        "e2e": {"value": round(e2e_value, 4), "unit": UNIT, "h2d_bytes_per_step": int(h2d / args.steps), "d2h_bytes_per_step": int(d2h / args.steps),
+                "note": "wall clock around bark_generate_audio (C-ABI, host text in / host waveform out), includes per-step logits D2H + host sampling"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "stages": {n: {"tokens_per_s": round(float(ns) / n_calls / (us / args.steps * 1e-6), 1) if us else None, "ms": round(us / args.steps / 1e3, 2)}
+                   for n, ns, us in zip(("semantic", "coarse", "fine"), n_samples, stage_us)},
+        "audio_seconds_per_step": round(audio_s_per_step, 4),
+        "roofline": roofline, "kernels": kernels,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        result["cpu_baseline"] = cpu_baseline(path, budget_s=args.cpu_budget)
+    b.close()
+    if dist:
+        dist.destroy_process_group()
+    print(json.dumps(result))
+
+
+def cpu_baseline(path, budget_s=30.0, steps=1):
+    """The reference's CPU path on this box's host cores: oracle/_ref (the unmodified reference) when it travelled with the
+    snapshot, else the C oracle port.  Bounded sample: the clip is shortened (n_steps_text_encoder) until one run fits the budget."""
+    orc = graft.load_oracle_bindings()
+    cores = os.cpu_count() or 1
+    if orc.have_ref():
+        # ggml's thread pool spins on a barrier per graph node, so "all cores" is not its fastest setting on a big host:
+        # try a few thread counts on a short clip and keep the best (reported as `cores`).
+        cands = sorted({c for c in (8, 16, 32, 64, cores) if c <= cores})
+        best = None
+        for c in cands:
+            r = orc.Ref(path, seed=0, n_steps=8)
+            t0 = time.perf_counter(); r.generate(PROMPT, n_threads=c); dt = time.perf_counter() - t0
+            st = r.stats()
+            if best is None or dt < best[1]:
+                best = (c, dt, st[4] * 1e-6)
+        threads, t_short, t_fine = best
+        # fine stage cost is fixed (6 passes over 1024 rows); semantic+coarse scale with the clip
+        per_tok = max((t_short - t_fine) / 8.0, 1e-4)
+        n = int(max(8, min(N_STEPS_TEXT, (budget_s - t_fine) / per_tok)))
+        r = orc.Ref(path, seed=0, n_steps=n)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            g = r.generate(PROMPT, n_threads=threads)
+        dt = (time.perf_counter() - t0) / steps
+        st = r.stats()
+        return {"value": round(g["audio"].size / SAMPLE_RATE / dt, 5), "unit": UNIT, "cores": threads, "host_cores": cores, "kind": "reference",
+                "sample": f"same weights/prompt/seed, n_steps_text_encoder={n} -> {g['audio'].size / SAMPLE_RATE:.2f} s clip, one bark_generate_audio at -t {threads} "
+                          f"(best of {cands} on a short clip): {dt:.2f} s (semantic {st[2] / 1e3:.0f} ms, coarse {st[3] / 1e3:.0f} ms, fine {st[4] / 1e3:.0f} ms)",
+                "build": r.build_info(), "seconds": round(dt, 3)}
+    o = orc.Oracle(path, seed=0, n_steps=4)
+    t0 = time.perf_counter(); g = o.generate(PROMPT); dt = time.perf_counter() - t0
+    return {"value": round(g["audio"].size / SAMPLE_RATE / dt, 5), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"C oracle (OpenMP), n_steps_text_encoder=4 -> {g['audio'].size / SAMPLE_RATE:.2f} s clip in {dt:.2f} s", "seconds": round(dt, 3)}
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    path = weights_path()
+    per_step_budget = max(6.0, 200.0 / max(args.steps + args.warmup, 1))
+    # one calibration inside the first warm-up, then identical steps
+    base = cpu_baseline(path, budget_s=per_step_budget, steps=1)
+    orc = graft.load_oracle_bindings()
+    cores = base.get("cores", os.cpu_count() or 1)
+    n = int(base["sample"].split("n_steps_text_encoder=")[1].split(" ")[0]) if "n_steps_text_encoder=" in base["sample"] else 8
+    times, audio_s = [], None
+    if orc.have_ref():
+        r = orc.Ref(path, seed=0, n_steps=n)
+        for i in range(max(args.warmup - 1, 0) + args.steps):
+            t0 = time.perf_counter(); g = r.generate(PROMPT, n_threads=cores); dt = time.perf_counter() - t0
+            if i >= max(args.warmup - 1, 0):
+                times.append(dt)
+            audio_s = g["audio"].size / SAMPLE_RATE
+    else:
+        o = orc.Oracle(path, seed=0, n_steps=n)
+        for i in range(max(args.warmup - 1, 0) + args.steps):
+            t0 = time.perf_counter(); g = o.generate(PROMPT); dt = time.perf_counter() - t0
+            if i >= max(args.warmup - 1, 0):
+                times.append(dt)
+            audio_s = g["audio"].size / SAMPLE_RATE
+    total = sum(times)
+    value = audio_s * len(times) / total
+    base.update(value=round(value, 5))
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": round(value, 5), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(total / len(times) * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16 weights/operands, f32 accumulate", "data": "synthetic (same file as the CUDA arm)",
+        "config": {"workload": f"bark-small f16, batch=1, bounded sample n_steps_text_encoder={n} ({audio_s:.2f} s clip) of BASELINE configs[1]", "parallelism": f"host CPU, {cores} threads"},
+        "cpu_baseline": base, "e2e": {"value": round(value, 5), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=30.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

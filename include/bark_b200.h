@@ -47,6 +47,11 @@ BARK_API void bark_b200_get_hparams(struct bark_context * ctx, int which, int32_
 BARK_API unsigned long long bark_b200_kernel_launches(void);               /* kernels launched by this library so far */
 BARK_API unsigned bark_b200_layernorm_fallbacks(struct bark_context * ctx); /* LayerNorm rows replayed sequentially */
 
+/* measurement hooks used by bench.py */
+BARK_API void bark_b200_profile_enable(int on);                            /* CUDA-event timing of every kernel launch; clears previous records */
+BARK_API int  bark_b200_profile_report(char * buf, int cap);               /* JSON {kernel: {launches, ms, work}}; returns bytes needed */
+BARK_API void bark_b200_io_counters(unsigned long long * h2d_bytes, unsigned long long * d2h_bytes, int reset);
+
 #ifdef __cplusplus
 }
 #endif
