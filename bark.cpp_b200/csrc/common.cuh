@@ -32,16 +32,16 @@ extern unsigned long long g_kernel_launches;
 extern unsigned long long g_h2d_bytes, g_d2h_bytes;
 // optional per-launch device timing (prof.cu): CUDA events on the launching stream around every kernel
 extern bool g_prof_on;
-void prof_begin(const char * name, cudaStream_t s, double work);
+void prof_begin(const char * name, cudaStream_t s, double bytes, double flops);
 void prof_end(cudaStream_t s);
-// `work` annotates the NEXT launch with its algorithmic bytes (or flops) for the roofline report
-extern double g_next_work;
+// annotate the NEXT launch with its algorithmic HBM bytes and/or flops for the roofline report
+extern double g_next_bytes, g_next_flops;
 #define BARK_LAUNCH(kernel, grid, block, smem, stream, ...)                                           \
     do {                                                                                              \
-        if (::bark::g_prof_on) ::bark::prof_begin(#kernel, (stream), ::bark::g_next_work);            \
+        if (::bark::g_prof_on) ::bark::prof_begin(#kernel, (stream), ::bark::g_next_bytes, ::bark::g_next_flops);            \
         kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                                   \
         if (::bark::g_prof_on) ::bark::prof_end((stream));                                            \
-        ::bark::g_next_work = 0.0;                                                                    \
+        ::bark::g_next_bytes = ::bark::g_next_flops = 0.0;                                                                    \
         ++::bark::g_kernel_launches;                                                                  \
     } while (0)
 
@@ -145,6 +145,90 @@ __device__ __forceinline__ float glibc_expf_dev(float x) {
     y = __dmul_rn(y, s);
     return __double2float_rn(y);
 }
+
+// glibc 2.39 expm1f / tanhf (sysdeps/ieee754/flt-32/s_expm1f.c, s_tanhf.c: the fdlibm float algorithms), restated with
+// explicit IEEE single-precision operations.  ELU uses expm1f (ggml.c:2533), the LSTM gates tanhf / expf (ggml.c:2532,2536).
+// The C restatement was checked against the host libm on 3.3e8 inputs spanning every float ("libm on the device").
+__device__ __forceinline__ float glibc_expm1f_dev(float x) {
+    const float one = 1.0f, huge = 1.0e+30f, tiny = 1.0e-30f, o_threshold = 8.8721679688e+01f, ln2_hi = 6.9313812256e-01f,
+                ln2_lo = 9.0580006145e-06f, invln2 = 1.4426950216e+00f, Q1 = -3.3333335072e-02f, Q2 = 1.5873016091e-03f,
+                Q3 = -7.9365076090e-05f, Q4 = 4.0082177293e-06f, Q5 = -2.0109921195e-07f;
+    float y, hi, lo, c = 0.0f, t, e, hxs, hfx, r1;
+    int k;
+    uint32_t hx = __float_as_uint(x);
+    const uint32_t xsb = hx & 0x80000000u;
+    hx &= 0x7fffffffu;
+    if (hx >= 0x4195b844u) {                       // |x| >= 27 ln2
+        if (hx >= 0x42b17218u) {
+            if (hx > 0x7f800000u) return __fadd_rn(x, x);
+            if (hx == 0x7f800000u) return xsb == 0 ? x : -1.0f;
+            if (x > o_threshold) return __fmul_rn(huge, huge);
+        }
+        if (xsb != 0) return __fsub_rn(tiny, one);
+    }
+    if (hx > 0x3eb17218u) {                        // |x| > 0.5 ln2
+        if (hx < 0x3F851592u) {
+            if (xsb == 0) { hi = __fsub_rn(x, ln2_hi); lo = ln2_lo; k = 1; }
+            else          { hi = __fadd_rn(x, ln2_hi); lo = -ln2_lo; k = -1; }
+        } else {
+            k = __float2int_rz(__fadd_rn(__fmul_rn(invln2, x), xsb == 0 ? 0.5f : -0.5f));
+            t = (float) k;
+            hi = __fsub_rn(x, __fmul_rn(t, ln2_hi));
+            lo = __fmul_rn(t, ln2_lo);
+        }
+        x = __fsub_rn(hi, lo);
+        c = __fsub_rn(__fsub_rn(hi, x), lo);
+    } else if (hx < 0x33000000u) {                 // |x| < 2^-25
+        t = __fadd_rn(huge, x);
+        return __fsub_rn(x, __fsub_rn(t, __fadd_rn(huge, x)));
+    } else k = 0;
+    hfx = __fmul_rn(0.5f, x);
+    hxs = __fmul_rn(x, hfx);
+    r1 = __fadd_rn(one, __fmul_rn(hxs, __fadd_rn(Q1, __fmul_rn(hxs, __fadd_rn(Q2, __fmul_rn(hxs, __fadd_rn(Q3, __fmul_rn(hxs, __fadd_rn(Q4, __fmul_rn(hxs, Q5)))))))))); 
+    t = __fsub_rn(3.0f, __fmul_rn(r1, hfx));
+    e = __fmul_rn(hxs, __fdiv_rn(__fsub_rn(r1, t), __fsub_rn(6.0f, __fmul_rn(x, t))));
+    if (k == 0) return __fsub_rn(x, __fsub_rn(__fmul_rn(x, e), hxs));
+    e = __fsub_rn(__fmul_rn(x, __fsub_rn(e, c)), c);
+    e = __fsub_rn(e, hxs);
+    if (k == -1) return __fsub_rn(__fmul_rn(0.5f, __fsub_rn(x, e)), 0.5f);
+    if (k == 1) {
+        if (x < -0.25f) return __fmul_rn(-2.0f, __fsub_rn(e, __fadd_rn(x, 0.5f)));
+        return __fadd_rn(one, __fmul_rn(2.0f, __fsub_rn(x, e)));
+    }
+    if (k <= -2 || k > 56) {
+        y = __fsub_rn(one, __fsub_rn(e, x));
+        y = __uint_as_float(__float_as_uint(y) + ((uint32_t) k << 23));
+        return __fsub_rn(y, one);
+    }
+    if (k < 23) {
+        t = __uint_as_float(0x3f800000u - (0x1000000u >> k));
+        y = __fsub_rn(t, __fsub_rn(e, x));
+        y = __uint_as_float(__float_as_uint(y) + ((uint32_t) k << 23));
+    } else {
+        t = __uint_as_float((uint32_t)(0x7f - k) << 23);
+        y = __fsub_rn(x, __fadd_rn(e, t));
+        y = __fadd_rn(y, one);
+        y = __uint_as_float(__float_as_uint(y) + ((uint32_t) k << 23));
+    }
+    return y;
+}
+
+__device__ __forceinline__ float glibc_tanhf_dev(float x) {
+    const float one = 1.0f, two = 2.0f, tiny = 1.0e-30f;
+    const uint32_t jx = __float_as_uint(x), ix = jx & 0x7fffffffu;
+    float t, z;
+    if (ix >= 0x7f800000u) return (jx & 0x80000000u) ? __fsub_rn(__fdiv_rn(one, x), one) : __fadd_rn(__fdiv_rn(one, x), one);
+    if (ix < 0x41b00000u) {                        // |x| < 22
+        if (ix == 0) return x;
+        if (ix < 0x24000000u) return __fmul_rn(x, __fadd_rn(one, x));
+        if (ix >= 0x3f800000u) { t = glibc_expm1f_dev(__fmul_rn(two, fabsf(x))); z = __fsub_rn(one, __fdiv_rn(two, __fadd_rn(t, two))); }
+        else                   { t = glibc_expm1f_dev(__fmul_rn(-two, fabsf(x))); z = __fdiv_rn(-t, __fadd_rn(t, two)); }
+    } else z = __fsub_rn(one, tiny);
+    return (jx & 0x80000000u) ? -z : z;
+}
+
+__device__ __forceinline__ float elu_exact(float x) { return x > 0.f ? x : glibc_expm1f_dev(x); }                       // ggml.c:2533
+__device__ __forceinline__ float sigmoid_exact(float x) { return __fdiv_rn(1.f, __fadd_rn(1.f, glibc_expf_dev(-x))); } // ggml.c:2536
 #endif  // __CUDACC__
 
 }  // namespace bark

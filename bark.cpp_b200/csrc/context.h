@@ -27,6 +27,7 @@ struct bark_context {
     // codec scratch
     float * c_buf[3] = {nullptr, nullptr, nullptr}; size_t c_cap = 0;   // ping-pong activations (floats)
     float * c_gi = nullptr;                                            // LSTM input projections
+    float * c_hbuf = nullptr; unsigned * c_counter = nullptr;          // LSTM hidden-state exchange + grid barrier counter
     int32_t * d_codes = nullptr;
 
     std::mt19937 rng;                                // seeded once at load (bark.cpp:1179)

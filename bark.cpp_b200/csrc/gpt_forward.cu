@@ -116,6 +116,7 @@ bool codec_decode(bark_context * ctx, const int32_t * codes, int T) {
         BARK_CUDA_CHECK(cudaMalloc(&ctx->c_gi, (size_t) T * 2048 * sizeof(float)));
         if (ctx->d_codes) BARK_CUDA_CHECK(cudaFree(ctx->d_codes));
         BARK_CUDA_CHECK(cudaMalloc(&ctx->d_codes, (size_t) 8 * T * sizeof(int32_t)));
+        if (!ctx->c_hbuf) { ctx->c_hbuf = (float *) ctx_alloc(ctx, 2 * 512 * sizeof(float)); ctx->c_counter = (unsigned *) ctx_alloc(ctx, sizeof(unsigned)); }
         ctx->c_cap = need;
     }
     float * a = ctx->c_buf[0], * b = ctx->c_buf[1], * c = ctx->c_buf[2];
@@ -123,8 +124,8 @@ bool codec_decode(bark_context * ctx, const int32_t * codes, int T) {
     rvq_decode(cm, ctx->d_codes, T, a, s);                                                // [128][T]
     conv1d(a, cm.hidden_dim, T, cm.init, false, nullptr, b, s);                          // [512][T]
     int C = cm.init.cout;
-    lstm_layer(b, C, T, cm.lstm_ih_w[0], cm.lstm_hh_w[0], cm.lstm_ih_b[0], cm.lstm_hh_b[0], nullptr, ctx->c_gi, a, s);
-    lstm_layer(a, C, T, cm.lstm_ih_w[1], cm.lstm_hh_w[1], cm.lstm_ih_b[1], cm.lstm_hh_b[1], b /*skip (decoder.h:72)*/, ctx->c_gi, c, s);
+    lstm_layer(b, C, T, cm.lstm_ih_w[0], cm.lstm_hh_w[0], cm.lstm_Kp, cm.lstm_ih_b[0], cm.lstm_hh_b[0], nullptr, ctx->c_gi, ctx->c_hbuf, ctx->c_counter, a, s);
+    lstm_layer(a, C, T, cm.lstm_ih_w[1], cm.lstm_hh_w[1], cm.lstm_Kp, cm.lstm_ih_b[1], cm.lstm_hh_b[1], b /*skip (decoder.h:72)*/, ctx->c_gi, ctx->c_hbuf, ctx->c_counter, c, s);
     float * cur = c, * t1 = a, * t2 = b;
     int L = T;
     for (int i = 0; i < 4; i++) {

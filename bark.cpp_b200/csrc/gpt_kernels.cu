@@ -233,9 +233,10 @@ __global__ void __launch_bounds__(256) lane_matmul_kernel(const T * __restrict__
 
 void lane_matmul(const DMat & W, const void * act, int rows, const MatmulEpilogue & ep, cudaStream_t s) {
     const int gx = (W.n_out + 7) / 8;
-    {   // roofline annotation: decode (1 row) streams the weights once -> bytes; multi-row passes are dense contractions -> flops
+    {   // roofline annotation: algorithmic HBM bytes (weights once + operands) and flops of this mat-mul
         const double es = W.type == W_F16 ? 2.0 : 4.0;
-        g_next_work = rows == 1 ? (double) W.n_out * W.K * es + W.K * es + W.n_out * 4.0 : 2.0 * rows * (double) W.n_out * W.K;
+        g_next_bytes = (double) W.n_out * W.K * es + (double) rows * (W.K * es + W.n_out * 4.0);
+        g_next_flops = 2.0 * rows * (double) W.n_out * W.K;
     }
     if (W.type == W_F16) {
         if (rows == 1) BARK_LAUNCH((lane_matmul_kernel<__half, 1>), dim3(gx, 1), 256, 0, s, (const __half *) W.p, W.K, W.Kp, W.n_out, (const __half *) act, rows, ep);
@@ -349,13 +350,16 @@ void attention(const float * Q, const float * Kc, const float * Vc, int N, int n
     const int D = E / H;
     const float scale = 1.0f / sqrtf((float) E / (float) H);                 // bark.cpp:1318
     const int rows = H * N;
+    g_next_bytes = 4.0 * ((double) n_kv * E + (double) N * E + (double) H * N * n_kv); g_next_flops = 2.0 * (double) N * n_kv * E;
     if (D == 64)       BARK_LAUNCH(attn_scores_kernel<2>, (rows + 7) / 8, 256, 0, s, Q, Kc, N, n_kv, n_past, E, H, scale, causal ? 1 : 0, scores);
     else if (D == 32)  BARK_LAUNCH(attn_scores_kernel<1>, (rows + 7) / 8, 256, 0, s, Q, Kc, N, n_kv, n_past, E, H, scale, causal ? 1 : 0, scores);
     else if (D == 96)  BARK_LAUNCH(attn_scores_kernel<3>, (rows + 7) / 8, 256, 0, s, Q, Kc, N, n_kv, n_past, E, H, scale, causal ? 1 : 0, scores);
     else if (D == 128) BARK_LAUNCH(attn_scores_kernel<4>, (rows + 7) / 8, 256, 0, s, Q, Kc, N, n_kv, n_past, E, H, scale, causal ? 1 : 0, scores);
     else { fprintf(stderr, "bark_b200: unsupported head size %d (need a multiple of 32, <= 128)\n", D); abort(); }
+    g_next_bytes = 8.0 * (double) rows * n_kv;
     BARK_LAUNCH(attn_softmax_kernel, (rows + 7) / 8, 256, 0, s, scores, rows, n_kv);
     const int qy = max(1, 256 / D);
+    g_next_bytes = 4.0 * ((double) n_kv * E + (double) H * N * n_kv + (double) N * E); g_next_flops = 2.0 * (double) N * n_kv * E;
     BARK_LAUNCH(attn_pv_kernel, dim3((N + qy - 1) / qy, H), dim3(D, qy), 0, s, scores, Vc, N, n_kv, E, H, D, act, (int) wt, Kp);
 }
 

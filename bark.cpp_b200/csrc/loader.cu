@@ -10,6 +10,7 @@
 //     (bark.cpp:976-991).
 // Error behaviour follows the reference: message on stderr, false/nullptr to the caller.
 #include "context.h"
+#include "codec_kernels.h"
 #include "gpt_kernels.h"
 
 #include <cmath>
@@ -174,13 +175,13 @@ bool load_codec(bark_context * ctx, std::ifstream & f, CodecModel & c) {
     if (ftype != W_F16) {   // an all-f32 codec cannot run in the reference either (ggml.c:14899 asserts an f16 kernel)
         fprintf(stderr, "%s: codec weights must be f16 (ftype %d)\n", __func__, ftype); return false;
     }
-    struct CSlot { ConvW * cv = nullptr; bool is_w = false; __half ** hw = nullptr; float ** fb = nullptr; int ne[3]; };
+    struct CSlot { ConvW * cv = nullptr; bool is_w = false, transposed = false; __half ** hw = nullptr; float ** fb = nullptr; int ne[3]; };
     std::map<std::string, CSlot> slots;
     const int nf = c.n_filters, ks = c.kernel_size, rk = c.res_kernel;
     static const int ratios[4] = {8, 5, 4, 2};
     auto conv = [&](const std::string & base, ConvW * cv, int k, int cin, int cout, bool transposed) {
         cv->k = k; cv->cin = cin; cv->cout = cout;
-        CSlot w; w.cv = cv; w.is_w = true; w.ne[0] = k; w.ne[1] = transposed ? cout : cin; w.ne[2] = transposed ? cin : cout; slots[base + ".weight"] = w;
+        CSlot w; w.cv = cv; w.is_w = true; w.transposed = transposed; w.ne[0] = k; w.ne[1] = transposed ? cout : cin; w.ne[2] = transposed ? cin : cout; slots[base + ".weight"] = w;
         CSlot b; b.cv = cv; b.is_w = false; b.ne[0] = cout; b.ne[1] = 1; b.ne[2] = 1; slots[base + ".bias"] = b;
     };
     int mult = 16;
@@ -231,9 +232,32 @@ bool load_codec(bark_context * ctx, std::ifstream & f, CodecModel & c) {
         }
         const bool is_weight = s.hw || (s.cv && s.is_w);
         if (h.ttype != (is_weight ? (int) W_F16 : (int) W_F32)) { fprintf(stderr, "%s: tensor '%s' has wrong type %d\n", __func__, h.name.c_str(), h.ttype); return false; }
-        void * d = upload_raw(ctx, f, bytes, host, true);
-        if (!d) return false;
-        if (s.hw) *s.hw = (__half *) d; else if (s.fb) *s.fb = (float *) d; else if (s.is_w) s.cv->w = (__half *) d; else s.cv->b = (float *) d;
+        if (!is_weight) {
+            void * d = upload_raw(ctx, f, bytes, host, true);
+            if (!d) return false;
+            if (s.fb) *s.fb = (float *) d; else s.cv->b = (float *) d;
+            continue;
+        }
+        // f16 weights -> lane-interleaved rows (common.cuh) so every codec dot product streams like the GPT mat-muls
+        __half * raw = (__half *) upload_raw(ctx, f, bytes, host, false);
+        if (!raw) return false;
+        int rows, K;
+        __half * tmp = nullptr;
+        const bool transposed = s.cv && s.transposed;
+        if (s.hw) { rows = s.ne[1]; K = s.ne[0]; }
+        else if (transposed) {                                               // stored [Cin][Cout][k] -> rows [Cout*k] x Cin
+            rows = s.cv->cout * s.cv->k; K = s.cv->cin;
+            BARK_CUDA_CHECK(cudaMalloc(&tmp, bytes));
+            convtr_rows(raw, tmp, s.cv->cin, s.cv->cout, s.cv->k, ctx->stream);
+        } else { rows = s.cv->cout; K = s.cv->cin * s.cv->k; }               // stored [Cout][Cin][k]: row o, column c*k + j (im2col order)
+        if (K % 32 != 0) { fprintf(stderr, "%s: tensor '%s': contraction length %d is not a multiple of 32\n", __func__, h.name.c_str(), K); return false; }
+        const int Kp = li_padded_k(K, 2);
+        __half * li = (__half *) ctx_alloc(ctx, (size_t) rows * Kp * sizeof(__half));
+        permute_to_li(tmp ? tmp : raw, li, rows, K, W_F16, ctx->stream);
+        BARK_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        BARK_CUDA_CHECK(cudaFree(raw));
+        if (tmp) BARK_CUDA_CHECK(cudaFree(tmp));
+        if (s.hw) { *s.hw = li; c.lstm_Kp = Kp; } else { s.cv->w = li; s.cv->Kp = Kp; }
     }
     for (auto & kv : slots) {
         const CSlot & s = kv.second;
@@ -241,7 +265,7 @@ bool load_codec(bark_context * ctx, std::ifstream & f, CodecModel & c) {
         if (!present) { fprintf(stderr, "%s: tensor '%s' missing from the codec section\n", __func__, kv.first.c_str()); return false; }
     }
     for (int q = 0; q < 8; q++) if (!c.embed[q]) { fprintf(stderr, "%s: codebook %d missing\n", __func__, q); return false; }
-    printf("%s: model size = %.2f MB\n", __func__, total / 1024.0 / 1024.0);
+    if (ctx->params.verbosity >= MEDIUM) printf("%s: codec model size = %.2f MB\n", __func__, total / 1024.0 / 1024.0);
     return true;
 }
 

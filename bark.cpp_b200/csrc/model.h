@@ -36,14 +36,15 @@ struct GPTModel {
     int64_t t_sample_us = 0, t_predict_us = 0, t_main_us = 0, n_sample = 0;
 };
 
-struct ConvW { __half * w = nullptr; float * b = nullptr; int k = 0, cin = 0, cout = 0; };
+struct ConvW { __half * w = nullptr; float * b = nullptr; int k = 0, cin = 0, cout = 0, Kp = 0; };   // w: LI16 rows (conv: [Cout] x Cin*k; transposed conv: [Cout*k] x Cin)
 
 struct CodecModel {
     int hidden_dim = 128, n_filters = 32, kernel_size = 7, res_kernel = 3, n_bins = 1024;
-    ConvW init, final_conv;                 // conv weights [Cout][Cin][k] f16 (ggml [k,Cin,Cout])
-    __half * lstm_ih_w[2] = {nullptr, nullptr}, * lstm_hh_w[2] = {nullptr, nullptr};   // [4H][H] f16
+    ConvW init, final_conv;
+    __half * lstm_ih_w[2] = {nullptr, nullptr}, * lstm_hh_w[2] = {nullptr, nullptr};   // [4H] x H, LI16 rows
+    int lstm_Kp = 0;
     float  * lstm_ih_b[2] = {nullptr, nullptr}, * lstm_hh_b[2] = {nullptr, nullptr};
-    struct Block { ConvW us, c1, c2, sc; } blk[4];   // us: transposed conv, weights [Cin][Cout][k] f16
+    struct Block { ConvW us, c1, c2, sc; } blk[4];   // us: transposed conv
     float * embed[8] = {nullptr};           // codebooks 0..7, [n_bins][hidden] f32
 };
 

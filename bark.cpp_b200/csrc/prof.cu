@@ -12,10 +12,10 @@ namespace bark {
 
 unsigned long long g_h2d_bytes = 0, g_d2h_bytes = 0;
 bool g_prof_on = false;
-double g_next_work = 0.0;
+double g_next_bytes = 0.0, g_next_flops = 0.0;
 
 namespace {
-struct Rec { const char * name; cudaEvent_t a, b; double work; };
+struct Rec { const char * name; cudaEvent_t a, b; double bytes, flops; };
 std::vector<Rec> g_recs;
 std::vector<cudaEvent_t> g_pool;
 cudaEvent_t get_event() {
@@ -24,8 +24,8 @@ cudaEvent_t get_event() {
 }
 }  // namespace
 
-void prof_begin(const char * name, cudaStream_t s, double work) {
-    Rec r{name, get_event(), get_event(), work};
+void prof_begin(const char * name, cudaStream_t s, double bytes, double flops) {
+    Rec r{name, get_event(), get_event(), bytes, flops};
     BARK_CUDA_CHECK(cudaEventRecord(r.a, s));
     g_recs.push_back(r);
 }
@@ -41,22 +41,22 @@ extern "C" void bark_b200_profile_enable(int on) {
     g_recs.clear();
 }
 
-// JSON: {"kernel": {"launches": n, "ms": t, "work": w}, ...}; returns the length needed
+// JSON: {"kernel": {"launches": n, "ms": t, "bytes": b, "flops": f}, ...}; returns the length needed
 extern "C" int bark_b200_profile_report(char * buf, int cap) {
     BARK_CUDA_CHECK(cudaDeviceSynchronize());
-    struct Agg { long n = 0; double ms = 0, work = 0; };
+    struct Agg { long n = 0; double ms = 0, bytes = 0, flops = 0; };
     std::map<std::string, Agg> agg;
     for (auto & r : g_recs) {
         float ms = 0; BARK_CUDA_CHECK(cudaEventElapsedTime(&ms, r.a, r.b));
         std::string n = r.name;
         if (!n.empty() && n.front() == '(') n = n.substr(1, n.size() - 2);
-        Agg & a = agg[n]; a.n++; a.ms += ms; a.work += r.work;
+        Agg & a = agg[n]; a.n++; a.ms += ms; a.bytes += r.bytes; a.flops += r.flops;
     }
     std::string out = "{";
     bool first = true;
     for (auto & kv : agg) {
         char tmp[512];
-        snprintf(tmp, sizeof tmp, "%s\"%s\": {\"launches\": %ld, \"ms\": %.6f, \"work\": %.6e}", first ? "" : ", ", kv.first.c_str(), kv.second.n, kv.second.ms, kv.second.work);
+        snprintf(tmp, sizeof tmp, "%s\"%s\": {\"launches\": %ld, \"ms\": %.6f, \"bytes\": %.6e, \"flops\": %.6e}", first ? "" : ", ", kv.first.c_str(), kv.second.n, kv.second.ms, kv.second.bytes, kv.second.flops);
         out += tmp; first = false;
     }
     out += "}";

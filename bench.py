@@ -176,7 +176,7 @@ def run_ours(args):
     e2e_value = audio_s_per_step * args.steps / elapsed_max
 
     # ---- per-kernel device time (CUDA events on the launching stream) for the roofline: one extra profiled step on rank 0
-    roofline, kernels, value = None, None, e2e_value
+    roofline, roofline_all, kernels, value = None, None, None, e2e_value
     if rank == 0:
         pkg.profile_enable(True)
         b.generate(prompt)
@@ -185,21 +185,21 @@ def run_ours(args):
         P = peaks()
         tot_ms = sum(v["ms"] for v in rep.values()) or 1.0
         kernels = {k: dict(launches=v["launches"], ms=round(v["ms"], 3), share=round(v["ms"] / tot_ms, 4)) for k, v in sorted(rep.items(), key=lambda kv: -kv[1]["ms"])}
-        top = max(rep.items(), key=lambda kv: kv[1]["ms"])
-        name, v = top
-        per_launch_work = v["work"] / max(v["launches"], 1)
-        per_launch_s = v["ms"] * 1e-3 / max(v["launches"], 1)
-        is_hbm = "1>" in name or "decode" in name      # single-row matmul / decode kernels stream weights; multi-row passes are dense contractions
-        if v["work"] > 0:
-            if is_hbm:
-                ach = per_launch_work / per_launch_s / 1e9
-                roofline = dict(kernel=name, bound="hbm", achieved=round(ach, 1), peak=P["hbm_gbs"], unit="GB/s", frac=round(ach / P["hbm_gbs"], 4), traffic=None,
-                                peak_source=P["source"], launches=v["launches"], avg_launch_us=round(per_launch_s * 1e6, 2))
-            else:
-                ach = per_launch_work / per_launch_s / 1e12
-                roofline = dict(kernel=name, bound="tensor", achieved=round(ach, 2), peak=P["tflops"], unit="TFLOP/s", frac=round(ach / P["tflops"], 4), traffic=None,
-                                peak_source=P["source"] + " (sustained bf16 cuBLAS)", launches=v["launches"], avg_launch_us=round(per_launch_s * 1e6, 2),
-                                note="bit-exact path: f16 operands, fp32 FMA chain in the reference's lane order on CUDA cores; tensor-core peak shown as the ceiling the contraction would have without the parity constraint")
+        def roof(name, v):
+            """achieved vs the measured peak of whichever roof is closer for this kernel (HBM bytes or dense flops)"""
+            sec = v["ms"] * 1e-3
+            gbs = v["bytes"] / sec / 1e9 if sec else 0.0
+            tfs = v["flops"] / sec / 1e12 if sec else 0.0
+            f_h, f_t = gbs / P["hbm_gbs"], tfs / P["tflops"]
+            common = dict(kernel=name, launches=v["launches"], avg_launch_us=round(sec * 1e6 / max(v["launches"], 1), 2), share=round(v["ms"] / tot_ms, 4), traffic=None,
+                          peak_source=P["source"])
+            if f_h >= f_t:
+                return dict(bound="hbm", achieved=round(gbs, 1), peak=P["hbm_gbs"], unit="GB/s", frac=round(f_h, 4), **common)
+            return dict(bound="tensor", achieved=round(tfs, 2), peak=P["tflops"], unit="TFLOP/s", frac=round(f_t, 4),
+                        note="parity path: f16 operands, fp32 FMA chains in the reference's lane order on CUDA cores; bf16 cuBLAS peak is the ceiling of the contraction without the bit-exactness constraint", **common)
+        ranked = sorted(rep.items(), key=lambda kv: -kv[1]["ms"])
+        roofline = roof(*ranked[0])
+        roofline_all = [roof(n, v) for n, v in ranked[:6]]
         # value = same metric with inputs resident: sum of device kernel time of the profiled step (no host sampling, no copies)
         value = audio_s_per_step / world / (tot_ms * 1e-3) * world if tot_ms else e2e_value
 
@@ -221,14 +221,14 @@ def run_ours(args):
         "stages": {n: {"tokens_per_s": round(float(ns) / n_calls / (us / args.steps * 1e-6), 1) if us else None, "ms": round(us / args.steps / 1e3, 2)}
                    for n, ns, us in zip(("semantic", "coarse", "fine"), n_samples, stage_us)},
         "audio_seconds_per_step": round(audio_s_per_step, 4),
-        "roofline": roofline, "kernels": kernels,
+        "roofline": roofline, "roofline_top6": roofline_all, "kernels": kernels,
     }
     if world == 1 and not args.no_cpu_baseline:
         result["cpu_baseline"] = cpu_baseline(path, budget_s=args.cpu_budget)
     b.close()
     if dist:
         dist.destroy_process_group()
-    print(json.dumps(result))
+    emit(result)
 
 
 def cpu_baseline(path, budget_s=30.0, steps=1):
@@ -296,16 +296,29 @@ def run_reference(args):
     total = sum(times)
     value = audio_s * len(times) / total
     base.update(value=round(value, 5))
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": round(value, 5), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(total / len(times) * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16 weights/operands, f32 accumulate", "data": "synthetic (same file as the CUDA arm)",
         "config": {"workload": f"bark-small f16, batch=1, bounded sample n_steps_text_encoder={n} ({audio_s:.2f} s clip) of BASELINE configs[1]", "parallelism": f"host CPU, {cores} threads"},
         "cpu_baseline": base, "e2e": {"value": round(value, 5), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
+
+
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """The one JSON line of the contract goes to the real stdout; everything else (C-level prints of the reference
+    harness, library banners) was redirected to stderr in main()."""
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)

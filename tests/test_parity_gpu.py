@@ -84,7 +84,8 @@ def test_generate_tokens_bit_exact_and_waveform(pkg, orc, weights_file, config, 
         assert np.array_equal(b.tokens(1), ref["coarse"])
         assert np.array_equal(b.tokens(2), ref["fine"])
         assert audio.shape == ref["audio"].shape
-        assert wav_rel(audio, ref["audio"]) < WAV_RTOL
+        assert wav_rel(audio, ref["audio"]) < WAV_RTOL             # the contract
+        assert np.array_equal(bits(audio), bits(ref["audio"]))      # what the lane-ordered codec actually delivers
         # second call on the same context: RNG is NOT reseeded (bark.cpp:1179), sample counters accumulate
         audio2 = b.generate("hello world")
         assert audio2.shape[0] % 320 == 0
@@ -99,7 +100,8 @@ def test_encodec_decode_within_tolerance(pkg, orc, weights_file):
             codes = rng.integers(0, 1024, (8, T)).astype(np.int32)
             a, r = b.encodec_decode(codes), o.encodec_decode(codes)
             assert a.shape == r.shape == (320 * T,)
-            assert wav_rel(a, r) < WAV_RTOL
+            assert wav_rel(a, r) < WAV_RTOL                      # the contract
+            assert np.array_equal(bits(a), bits(r)), f"T={T}: codec is expected to be bit-exact, rel err {wav_rel(a, r):.3e}"
 
 
 def test_full_size_against_the_reference_itself(pkg, orc, weights_file):
