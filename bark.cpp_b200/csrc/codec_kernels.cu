@@ -88,6 +88,13 @@ __global__ void __launch_bounds__(256) conv1d_lane_kernel(const float * __restri
             for (int c = 0; c < NG * 8; c++) if (c < nsteps) acc = __fmaf_rn(wch[c], xs[aoff[c] + tl], acc);
             float r = lane_tree_reduce(acc);
             if (lane == 0) {
+                if ((nsteps << 5) < K) {                                         // K % 32 leftovers: float products summed in double (ggml.c:2281-2283)
+                    double sd = (double) r;
+                    const __half * wrow = w_li + (size_t) o * Kp;
+                    for (int kk = nsteps << 5; kk < K; kk++)
+                        sd = __dadd_rn(sd, (double) __fmul_rn(__half2float(wrow[li_offset(kk, 8)]), xs[(kk / KW) * S + (kk % KW) + tl]));
+                    r = __double2float_rn(sd);
+                }
                 r = __fadd_rn(bo, r);                                            // ops.cpp:72 add(repeat(b), dst)
                 if (resid) r = __fadd_rn(r, resid[(size_t) o * T + t]);
                 y[(size_t) o * T + t] = r;
@@ -98,7 +105,7 @@ __global__ void __launch_bounds__(256) conv1d_lane_kernel(const float * __restri
 
 void conv1d(const float * x, int Cin, int T, const ConvW & cv, bool elu_in, const float * resid, float * y, cudaStream_t s) {
     const int K = Cin * cv.k, nsteps = K / 32, ngroups = (nsteps + 7) / 8;
-    if (K % 32 != 0 || ngroups > 4) { fprintf(stderr, "bark_b200: unsupported conv shape Cin=%d k=%d\n", Cin, cv.k); abort(); }
+    if (ngroups > 4) { fprintf(stderr, "bark_b200: unsupported conv shape Cin=%d k=%d\n", Cin, cv.k); abort(); }
     const int TT = 32;
     const int S = (TT + cv.k - 1) | 1;
     const size_t smem = (size_t) Cin * S * sizeof(float);

@@ -250,7 +250,7 @@ bool load_codec(bark_context * ctx, std::ifstream & f, CodecModel & c) {
             BARK_CUDA_CHECK(cudaMalloc(&tmp, bytes));
             convtr_rows(raw, tmp, s.cv->cin, s.cv->cout, s.cv->k, ctx->stream);
         } else { rows = s.cv->cout; K = s.cv->cin * s.cv->k; }               // stored [Cout][Cin][k]: row o, column c*k + j (im2col order)
-        if (K % 32 != 0) { fprintf(stderr, "%s: tensor '%s': contraction length %d is not a multiple of 32\n", __func__, h.name.c_str(), K); return false; }
+        if (K % 32 != 0 && (s.hw || transposed)) { fprintf(stderr, "%s: tensor '%s': contraction length %d is not a multiple of 32\n", __func__, h.name.c_str(), K); return false; }
         const int Kp = li_padded_k(K, 2);
         __half * li = (__half *) ctx_alloc(ctx, (size_t) rows * Kp * sizeof(__half));
         permute_to_li(tmp ? tmp : raw, li, rows, K, W_F16, ctx->stream);
