@@ -14,6 +14,12 @@ import subprocess
 
 import numpy as np
 
+# The C oracle uses OpenMP.  On big shared hosts (the GPU box reports 128 logical CPUs but the container gets far fewer
+# cycles) a 128-thread team that spin-waits between the hundreds of tiny parallel regions of the LSTM loop can stall
+# for minutes, so cap the team and make idle threads sleep.  Must be set before libgomp initialises.
+os.environ.setdefault("OMP_NUM_THREADS", str(min(16, os.cpu_count() or 1)))
+os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+
 HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "libbark_oracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libbark_ref.so")
