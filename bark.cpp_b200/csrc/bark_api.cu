@@ -199,9 +199,10 @@ bool run_coarse(bark_context * ctx) {
         int n_past = 0;
         for (int j = 0; j < P.sliding_window_size && step < n_steps; j++) {
             if (P.progress_callback) P.progress_callback(ctx, COARSE, 100 * (step + 1) / n_steps, P.progress_callback_user_data);
-            if (!gpt_eval(ctx, m, in.data(), (int) in.size(), &n_past, false, logits.data())) { fprintf(stderr, "%s: Could not generate token\n", __func__); return false; }
             const bool major = step % P.n_coarse_codebooks == 0;
             const int lo = P.semantic_vocab_size + (major ? 0 : 1) * P.codebook_size;
+            // only logits [lo, lo + codebook_size) are ever looked at in this stage (bark.cpp:1829-1833): decode steps compute just that window of lm_head
+            if (!gpt_eval(ctx, m, in.data(), (int) in.size(), &n_past, false, logits.data(), lo, lo + P.codebook_size)) { fprintf(stderr, "%s: Could not generate token\n", __func__); return false; }
             const int32_t next = lo + sample_token(ctx, m, logits.data() + lo, P.codebook_size, P.temp, nullptr);
             in.assign(1, next);
             out.push_back(next);
@@ -332,6 +333,8 @@ extern "C" struct bark_context * bark_load_model(const char * model_path, struct
     }
     bark_context * ctx = new bark_context();
     ctx->device = dev;
+    ctx->n_sm = prop.multiProcessorCount;
+    { const char * e = getenv("BARK_B200_DECODE"); ctx->use_decode_kernel = !(e && !strcmp(e, "multi")); }   // "multi": one kernel per op (debug / A-B)
     ctx->params = params;
     BARK_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     if (!load_model_file(model_path, ctx)) {

@@ -18,7 +18,9 @@ struct bark_context {
     std::map<std::string, int32_t> token_to_id;      // WordPiece vocabulary (bark.cpp:664-690)
 
     __half * d_gelu_tab = nullptr;                   // 65536-entry table, ggml.c:3795-3810
-    unsigned * d_ln_fallbacks = nullptr;             // rows whose LayerNorm sums had to be replayed sequentially
+    unsigned * d_ln_fallbacks = nullptr;             // [0] LayerNorm rows, [1] soft_max rows replayed sequentially
+    unsigned * d_barrier = nullptr; unsigned barrier_base = 0;   // grid barrier counter of the persistent decode kernel
+    int n_sm = 0; bool use_decode_kernel = true;
 
     bark::Workspace ws;
     float * h_logits = nullptr;                      // pinned, max(n_out) or 1024*fine_vocab
@@ -51,7 +53,9 @@ bool load_model_file(const std::string & path, bark_context * ctx);
 void * ctx_alloc(bark_context * ctx, size_t bytes);
 
 // gpt_forward.cu — one evaluation of a causal model; mirrors bark_eval_encoder_internal (bark.cpp:1586-1643)
-bool gpt_eval(bark_context * ctx, GPTModel & m, const int32_t * tokens, int n, int * n_past, bool merge_ctx, float * logits_host);
+// logits [lm_lo, lm_hi) are computed and copied to logits_host + lm_lo (lm_hi <= 0: all of them)
+bool gpt_eval(bark_context * ctx, GPTModel & m, const int32_t * tokens, int n, int * n_past, bool merge_ctx, float * logits_host, int lm_lo = 0, int lm_hi = 0);
+void build_decode_tables(bark_context * ctx, GPTModel & m);
 // one non-causal pass of the fine model; mirrors bark_eval_fine_encoder_internal (bark.cpp:1907-1959)
 bool fine_eval(bark_context * ctx, const int32_t * in_buffer /*[8][1024]*/, int nn, float * logits_host /*[1024][n_out]*/);
 // EnCodec decode; codes [8][T] on the host; result in ctx->audio

@@ -1,0 +1,450 @@
+// Persistent decode step: ONE cooperative launch evaluates a whole causal-GPT token (N = 1, n_past > 0), i.e. everything
+// bark_build_gpt_graph (bark.cpp:1186-1414) emits for a single position — ~35 ggml nodes and ~400 thread barriers per
+// layer on the CPU, ~10 kernel launches per layer in the multi-kernel path (gpt_forward.cu) — with the same bit-exact
+// arithmetic (common.cuh "Lane order").
+//
+// One CTA per SM, 512 threads.  Weight rows (lane-interleaved layout) are a pure stream: each CTA owns a contiguous row
+// range of every matrix and pulls it with TMA bulk copies (cp.async.bulk + mbarrier complete_tx) into a shared-memory
+// ring several phases ahead of use, so HBM traffic never waits on the dependent math.  Phases of a layer
+//   P1  LN1 -> QKV rows (q to global, K/V appended to the f32 KV cache)        | grid barrier
+//   P2  scores[h][k] = <K[k][h], q[h]> * scale, (h,k) pairs spread over all warps | grid barrier
+//   P3  per (head, 16-wide slice of the head dim): soft_max + P.V              | grid barrier
+//   P4  c_proj rows + residual                                                  | grid barrier
+//   P5  LN2 -> c_fc rows -> GELU table                                         | grid barrier
+//   P6  mlp/c_proj rows + residual                                              | grid barrier
+// then LN_f -> lm_head rows [row_lo, row_hi).  Barriers are a monotonic counter in global memory
+// (red.release / ld.acquire), cross-CTA vectors travel through L2 (ld.global.cg).
+#include "gpt_kernels.h"
+
+namespace bark {
+
+namespace {
+
+constexpr int kThreads = 512;
+constexpr int kWarps = kThreads / 32;
+constexpr int kSlots = 5;
+constexpr int kSlotBytes = 32 * 1024;
+
+struct __align__(8) SmemLayout {
+    // dynamic shared memory carve-up (byte offsets); ring first (16-byte aligned for bulk copies)
+    static constexpr int ring = 0;
+    static constexpr int act = ring + kSlots * kSlotBytes;          // two-plane LI activation operand, up to 4096 floats
+    static constexpr int x = act + 4096 * 4;                        // residual stream, up to 1024 floats
+    static constexpr int q = x + 1024 * 4;                          // q vector / scores row, up to 1024 floats
+    static constexpr int part = q + 1024 * 4;                       // P.V lane partials [32][16] + chunk sums [128] + scratch
+    static constexpr int red = part + (32 * 16 + 128) * 4;          // block reduction scratch: 16 doubles x 2
+    static constexpr int bar = red + 2 * kWarps * 8;                // kSlots mbarriers
+    static constexpr int total = bar + kSlots * 8;
+};
+
+// ---- PTX helpers -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void * p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void * src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void grid_barrier(unsigned * counter, unsigned target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+        unsigned v;
+        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory"); } while ((int) (v - target) < 0);
+    }
+    __syncthreads();
+}
+
+// two-plane LI index of column k in the shared activation operand: LDS.128 of one plane is contiguous across lanes
+__device__ __forceinline__ int act_index(int k) {
+    const int v = k & 31, c = k >> 5, g = c >> 3, e = c & 7;
+    return (((g << 1) + (e >> 2)) * 32 + v) * 4 + (e & 3);
+}
+
+// sum of one double per thread over the block; every thread returns the same value (fixed order)
+__device__ __forceinline__ double block_sum_d(double v, double * scratch) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < kWarps; w++) s += scratch[w];
+    return s;
+}
+
+// LayerNorm of xs[0..E) (ggml.c:11964-12013, see layernorm_act_kernel for the order-independence argument) ->
+// activation operand (optionally f16-rounded) in two-plane LI order
+template <bool ROUND16>
+__device__ void block_layernorm(const float * xs, int E, const float * __restrict__ g, const float * __restrict__ b, float * act, double * scratch,
+                                unsigned * fallback_counter) {
+    const double slack = 2.0 * (double) E * 0x1p-53 * (1.0 + 1e-6);
+    double s = 0.0, a = 0.0;
+    for (int i = threadIdx.x; i < E; i += kThreads) { const double v = (double) xs[i]; s += v; a += fabs(v); }
+    s = block_sum_d(s, scratch); a = block_sum_d(a, scratch + kWarps);
+    double d = slack * a;
+    float mean = __double2float_rn(__ddiv_rn(s, (double) E));
+    if (__double2float_rn(__ddiv_rn(s - d, (double) E)) != __double2float_rn(__ddiv_rn(s + d, (double) E))) {
+        double ss = 0.0;                                            // every thread replays the sequential sum (rare; keeps control flow uniform)
+        for (int i = 0; i < E; i++) ss = __dadd_rn(ss, (double) xs[i]);
+        mean = __double2float_rn(__ddiv_rn(ss, (double) E));
+        if (threadIdx.x == 0 && fallback_counter) atomicAdd(fallback_counter, 1u);
+    }
+    double s2 = 0.0;
+    for (int i = threadIdx.x; i < E; i += kThreads) { const float v = __fsub_rn(xs[i], mean); s2 += (double) __fmul_rn(v, v); }
+    s2 = block_sum_d(s2, scratch);
+    d = slack * s2;
+    float variance = __double2float_rn(__ddiv_rn(s2, (double) E));
+    if (__double2float_rn(__ddiv_rn(s2 - d, (double) E)) != __double2float_rn(__ddiv_rn(s2 + d, (double) E))) {
+        double ss = 0.0;
+        for (int i = 0; i < E; i++) { const float v = __fsub_rn(xs[i], mean); ss = __dadd_rn(ss, (double) __fmul_rn(v, v)); }
+        variance = __double2float_rn(__ddiv_rn(ss, (double) E));
+        if (threadIdx.x == 0 && fallback_counter) atomicAdd(fallback_counter, 1u);
+    }
+    const float scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(variance, 1e-5f)));
+    for (int i = threadIdx.x; i < E; i += kThreads) {
+        float y = __fmul_rn(__fsub_rn(xs[i], mean), scale);
+        y = __fmul_rn(y, g[i]);
+        if (b) y = __fadd_rn(y, b[i]);
+        act[act_index(i)] = ROUND16 ? round_f16(y) : y;
+    }
+    __syncthreads();
+}
+
+// ---- weight stream --------------------------------------------------------------------------------------------------
+struct Cursor {                 // position in this CTA's chunk sequence: (phase, sub-chunk)
+    int phase, sub;
+};
+
+struct StreamCtx {
+    const DecodePhase * phases; int n_phases;
+    int lm_lo, lm_hi;           // row window of the last phase (lm_head)
+    int cta, n_cta;
+};
+
+// rows [r0, r1) of `phase` owned by this CTA
+__device__ __forceinline__ void cta_rows(const StreamCtx & sc, int phase, int & r0, int & r1) {
+    const DecodePhase & p = sc.phases[phase];
+    int lo = 0, hi = p.n_out;
+    if (phase == sc.n_phases - 1) { lo = sc.lm_lo; hi = sc.lm_hi; }
+    const int n = hi - lo, per = (n + sc.n_cta - 1) / sc.n_cta;
+    r0 = min(hi, lo + sc.cta * per); r1 = min(hi, r0 + per);
+}
+__device__ __forceinline__ int rows_per_chunk(const DecodePhase & p) { return kSlotBytes / p.row_bytes; }
+__device__ __forceinline__ int phase_chunks(const StreamCtx & sc, int phase) {
+    int r0, r1; cta_rows(sc, phase, r0, r1);
+    const int rpc = rows_per_chunk(sc.phases[phase]);
+    return (r1 - r0 + rpc - 1) / rpc;
+}
+// advance to the next existing chunk at or after (phase, sub); returns false past the end
+__device__ __forceinline__ bool cursor_valid(const StreamCtx & sc, Cursor & c) {
+    while (c.phase < sc.n_phases && c.sub >= phase_chunks(sc, c.phase)) { c.phase++; c.sub = 0; }
+    return c.phase < sc.n_phases;
+}
+__device__ __forceinline__ void issue_chunk(const StreamCtx & sc, const Cursor & c, unsigned char * ring, uint32_t bars, int slot) {
+    const DecodePhase & p = sc.phases[c.phase];
+    int r0, r1; cta_rows(sc, c.phase, r0, r1);
+    const int rpc = rows_per_chunk(p);
+    const int a = r0 + c.sub * rpc, b = min(r1, a + rpc);
+    const uint32_t bytes = (uint32_t)(b - a) * (uint32_t) p.row_bytes;
+    const uint32_t bar = bars + slot * 8;
+    mbar_expect_tx(bar, bytes);
+    tma_bulk_g2s(smem_u32(ring + (size_t) slot * kSlotBytes), (const unsigned char *) p.w + (size_t) a * p.row_bytes, bytes, bar);
+}
+
+enum { EP_QKV = 0, EP_RESID = 1, EP_GELU = 2, EP_LOGITS = 3 };
+
+template <typename WT> struct Unpack;
+template <> struct Unpack<__half> {
+    static constexpr int G = 8;
+    __device__ static void w(const uint4 & u, float (&f)[8]) {
+        const __half2 * h = reinterpret_cast<const __half2 *>(&u);
+#pragma unroll
+        for (int i = 0; i < 4; i++) { const float2 t = __half22float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+    }
+};
+template <> struct Unpack<float> {
+    static constexpr int G = 4;
+    __device__ static void w(const uint4 & u, float (&f)[4]) { f[0] = __uint_as_float(u.x); f[1] = __uint_as_float(u.y); f[2] = __uint_as_float(u.z); f[3] = __uint_as_float(u.w); }
+};
+
+// one weight row (in the ring) against the shared activation operand, lane order
+template <typename WT>
+__device__ __forceinline__ float row_dot(const unsigned char * row, const float * act, int K, int lane) {
+    constexpr int G = Unpack<WT>::G;
+    const int nsteps = K >> 5;
+    const uint4 * wv = reinterpret_cast<const uint4 *>(row) + lane;
+    float acc = 0.0f;
+    if constexpr (G == 8) {
+        const int ng = nsteps >> 3, tail = nsteps & 7;
+        for (int g = 0; g < ng; g++) {
+            float w[8]; Unpack<WT>::w(wv[g * 32], w);
+            const float4 a0 = *reinterpret_cast<const float4 *>(act + ((g * 2) * 32 + lane) * 4);
+            const float4 a1 = *reinterpret_cast<const float4 *>(act + ((g * 2 + 1) * 32 + lane) * 4);
+            acc = __fmaf_rn(w[0], a0.x, acc); acc = __fmaf_rn(w[1], a0.y, acc); acc = __fmaf_rn(w[2], a0.z, acc); acc = __fmaf_rn(w[3], a0.w, acc);
+            acc = __fmaf_rn(w[4], a1.x, acc); acc = __fmaf_rn(w[5], a1.y, acc); acc = __fmaf_rn(w[6], a1.z, acc); acc = __fmaf_rn(w[7], a1.w, acc);
+        }
+        if (tail) {
+            float w[8]; Unpack<WT>::w(wv[ng * 32], w);
+            const float * a0 = act + ((ng * 2) * 32 + lane) * 4, * a1 = act + ((ng * 2 + 1) * 32 + lane) * 4;
+#pragma unroll
+            for (int e = 0; e < 8; e++) if (e < tail) acc = __fmaf_rn(w[e], e < 4 ? a0[e] : a1[e - 4], acc);
+        }
+    } else {
+        // f32 rows: 4 chain steps per 16 bytes = one quad of the two-plane operand (quad index = chain step / 4)
+        const int nq = nsteps >> 2, tail = nsteps & 3;
+        for (int qd = 0; qd < nq; qd++) {
+            float w[4]; Unpack<WT>::w(wv[qd * 32], w);
+            const float4 a = *reinterpret_cast<const float4 *>(act + (qd * 32 + lane) * 4);
+            acc = __fmaf_rn(w[0], a.x, acc); acc = __fmaf_rn(w[1], a.y, acc); acc = __fmaf_rn(w[2], a.z, acc); acc = __fmaf_rn(w[3], a.w, acc);
+        }
+        if (tail) {
+            float w[4]; Unpack<WT>::w(wv[nq * 32], w);
+            const float * a = act + (nq * 32 + lane) * 4;
+#pragma unroll
+            for (int e = 0; e < 4; e++) if (e < tail) acc = __fmaf_rn(w[e], a[e], acc);
+        }
+    }
+    return lane_tree_reduce(acc);
+}
+
+}  // namespace
+
+template <typename WT>
+__global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs A) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char * ring = smem + SmemLayout::ring;
+    float * act = reinterpret_cast<float *>(smem + SmemLayout::act);
+    float * xs = reinterpret_cast<float *>(smem + SmemLayout::x);
+    float * qs = reinterpret_cast<float *>(smem + SmemLayout::q);
+    float * part = reinterpret_cast<float *>(smem + SmemLayout::part);
+    double * red = reinterpret_cast<double *>(smem + SmemLayout::red);
+    const uint32_t bars = smem_u32(smem + SmemLayout::bar);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int E = A.E, H = A.H, D = E / H, L = A.L, ctx = A.block_size, n_past = A.n_past, n_kv = n_past + 1;
+    constexpr bool kRound = sizeof(WT) == 2;
+
+    StreamCtx sc{A.phases, 4 * L + 1, A.lm_lo, A.lm_hi, (int) blockIdx.x, (int) gridDim.x};
+    if (tid == 0) {
+        for (int s = 0; s < kSlots; s++) mbar_init(bars + s * 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    Cursor prod{0, 0}, cons{0, 0};
+    int prod_n = 0, cons_n = 0;                              // chunks issued / consumed so far
+    if (tid == 0) {
+        for (int s = 0; s < kSlots && cursor_valid(sc, prod); s++) { issue_chunk(sc, prod, ring, bars, s); prod.sub++; prod_n++; }
+    }
+
+    // embedding of the one new token (bark.cpp:1226-1228, 1259): every CTA keeps its own copy of the residual stream
+    for (int i = tid; i < E; i += kThreads) {
+        const float t = kRound ? __half2float(((const __half *) A.wte)[(size_t) A.token * E + i]) : ((const float *) A.wte)[(size_t) A.token * E + i];
+        xs[i] = __fadd_rn(t, A.wpe[(size_t) n_past * E + i]);
+    }
+    __syncthreads();
+
+    unsigned bar_target = A.barrier_base;
+    const float scale = 1.0f / sqrtf((float) E / (float) H);
+
+    // consume every chunk of `phase` that belongs to this CTA
+    auto run_phase = [&](int phase, int ep, int layer) {
+        const DecodePhase & p = sc.phases[phase];
+        int r0, r1; cta_rows(sc, phase, r0, r1);
+        const int rpc = rows_per_chunk(p);
+        const int nch = (r1 - r0 + rpc - 1) / rpc;
+        for (int sub = 0; sub < nch; sub++) {
+            const int slot = cons_n % kSlots;
+            mbar_wait(bars + slot * 8, (uint32_t)((cons_n / kSlots) & 1));
+            const int a = r0 + sub * rpc, b = min(r1, a + rpc);
+            const unsigned char * base = ring + (size_t) slot * kSlotBytes;
+            for (int r = a + warp; r < b; r += kWarps) {
+                const float v = row_dot<WT>(base + (size_t)(r - a) * p.row_bytes, act, p.K, lane);
+                if (lane == 0) {
+                    if (ep == EP_QKV) {
+                        if (r < E) __stcg(A.gq + r, v);
+                        else if (r < 2 * E) __stcg(A.mem_k + ((size_t) layer * ctx + n_past) * E + (r - E), v);
+                        else __stcg(A.mem_v + ((size_t) layer * ctx + n_past) * E + (r - 2 * E), v);
+                    } else if (ep == EP_RESID) {
+                        __stcg(A.gx + r, __fadd_rn(v, xs[r]));
+                    } else if (ep == EP_GELU) {
+                        float gl;
+                        if (v <= -10.0f) gl = 0.0f; else if (v >= 10.0f) gl = v; else gl = __half2float(A.gelu_tab[__half_as_ushort(__float2half_rn(v))]);
+                        __stcg(A.gff + r, gl);
+                    } else {
+                        A.logits[r] = v;
+                    }
+                }
+            }
+            cons_n++;
+            __syncthreads();                                  // everyone is done reading this slot
+            if (tid == 0 && cursor_valid(sc, prod)) { issue_chunk(sc, prod, ring, bars, slot); prod.sub++; prod_n++; }
+        }
+    };
+
+    for (int il = 0; il < L; il++) {
+        const DecodeLayerVec & lv = A.layer_vecs[il];
+        // ---- P1: LN1 -> QKV ----
+        block_layernorm<kRound>(xs, E, lv.ln_1_g, lv.ln_1_b, act, red, A.ln_fallbacks);
+        run_phase(4 * il + 0, EP_QKV, il);
+        bar_target += gridDim.x; grid_barrier(A.barrier, bar_target);
+
+        // ---- P2: scores ----
+        for (int i = tid; i < E; i += kThreads) qs[i] = __ldcg(A.gq + i);
+        __syncthreads();
+        {
+            const float * Kc = A.mem_k + (size_t) il * ctx * E;
+            const int total = H * n_kv, gw = blockIdx.x * kWarps + warp, nw = gridDim.x * kWarps;
+            for (int t = gw; t < total; t += nw) {
+                const int h = t / n_kv, k = t % n_kv;
+                const float * kr = Kc + (size_t) k * E + h * D;
+                float acc = 0.0f;
+                for (int c = 0; c < (D >> 5); c++) acc = __fmaf_rn(__ldcg(kr + c * 32 + lane), qs[h * D + c * 32 + lane], acc);
+                float r = lane_tree_reduce(acc);
+                if (lane == 0) __stcg(A.gscores + (size_t) h * ctx + k, __fmul_rn(r, scale));
+            }
+        }
+        bar_target += gridDim.x; grid_barrier(A.barrier, bar_target);
+
+        // ---- P3: soft_max + P.V, one CTA per (head, 16 columns of the head) ----
+        {
+            const int parts = D >> 4;
+            if ((int) blockIdx.x < H * parts) {
+                const int h = blockIdx.x / parts, pc = blockIdx.x % parts;
+                float * p = qs;                                  // scores row -> probabilities
+                float * csum = part + 32 * 16;                   // chunk sums
+                float mx = __int_as_float(0xff800000);
+                for (int i = tid; i < n_kv; i += kThreads) { const float v = __ldcg(A.gscores + (size_t) h * ctx + i); p[i] = v; mx = fmaxf(mx, v); }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                float * fred = reinterpret_cast<float *>(red);
+                __syncthreads();
+                if (lane == 0) fred[warp] = mx;
+                __syncthreads();
+                mx = fred[0];
+#pragma unroll
+                for (int w = 1; w < kWarps; w++) mx = fmaxf(mx, fred[w]);
+                const int nchunks = n_kv >> 3;
+                if (tid < nchunks) {
+                    float v[8];
+#pragma unroll
+                    for (int l = 0; l < 8; l++) { v[l] = ggml_v_expf_dev(__fsub_rn(p[tid * 8 + l], mx)); }
+#pragma unroll
+                    for (int l = 0; l < 8; l++) p[tid * 8 + l] = v[l];
+                    const float t0 = __fadd_rn(v[4], v[0]), t1 = __fadd_rn(v[5], v[1]), t2 = __fadd_rn(v[6], v[2]), t3 = __fadd_rn(v[7], v[3]);
+                    csum[tid] = __fadd_rn(__fadd_rn(t0, t2), __fadd_rn(t1, t3));
+                }
+                __syncthreads();
+                // sum = sequential double accumulation of the chunk sums, then the libm-expf tail (ggml.c:2845-2888).  All terms
+                // are positive, so a tree sum S brackets the sequential one within +-2n*2^-53*S; if 1/sum rounds to the same float at
+                // both ends the order cannot matter, else replay sequentially.
+                float sc_f;
+                {
+                    double s = 0.0;
+                    for (int c = lane; c < nchunks; c += 32) s += (double) csum[c];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                    const double dl = 2.0 * (double)(nchunks + 8) * 0x1p-53 * s * (1.0 + 1e-6);
+                    double lo = s - dl, hi = s + dl;
+                    float tails[7]; int nt = 0;
+                    for (int i = nchunks * 8; i < n_kv; i++) { tails[nt] = glibc_expf_dev(__fsub_rn(p[i], mx)); lo = __dadd_rn(lo, (double) tails[nt]); hi = __dadd_rn(hi, (double) tails[nt]); nt++; }
+                    float f_lo = __double2float_rn(__ddiv_rn(1.0, lo)), f_hi = __double2float_rn(__ddiv_rn(1.0, hi));
+                    if (f_lo != f_hi) {
+                        double q2 = 0.0;
+                        for (int c = 0; c < nchunks; c++) q2 = __dadd_rn(q2, (double) csum[c]);
+                        for (int i = 0; i < nt; i++) q2 = __dadd_rn(q2, (double) tails[i]);
+                        f_lo = __double2float_rn(__ddiv_rn(1.0, q2));
+                        if (tid == 0 && A.ln_fallbacks) atomicAdd(A.ln_fallbacks + 1, 1u);
+                    }
+                    sc_f = f_lo;
+                    __syncthreads();
+                    if (tid < nt) p[nchunks * 8 + tid] = tails[tid];
+                }
+                __syncthreads();
+                for (int i = tid; i < n_kv; i += kThreads) p[i] = __fmul_rn(p[i], sc_f);
+                __syncthreads();
+                // P.V in lane order: thread (v, d) walks virtual lane v of output column d
+                const int v = tid >> 4, dd = tid & 15;
+                const float * Vc = A.mem_v + (size_t) il * ctx * E + h * D + pc * 16 + dd;
+                const int np = n_kv & ~31;
+                float acc = 0.0f;
+#pragma unroll 8
+                for (int k = v; k < np; k += 32) acc = __fmaf_rn(__ldcg(Vc + (size_t) k * E), p[k], acc);
+                part[v * 16 + dd] = acc;
+                __syncthreads();
+                if (tid < 16) {
+                    float a32[32];
+#pragma unroll
+                    for (int l = 0; l < 32; l++) a32[l] = part[l * 16 + tid];
+                    float sum = lane_tree_reduce_local(a32);
+                    const float * Vd = A.mem_v + (size_t) il * ctx * E + h * D + pc * 16 + tid;
+                    int i = np, r = n_kv - np;                   // leftovers as the pinned build compiles them (oracle orc_vec_dot_f32)
+                    while (r >= 8) { for (int l = 0; l < 8; l++) sum = __fadd_rn(sum, __fmul_rn(__ldcg(Vd + (size_t)(i + l) * E), p[i + l])); i += 8; r -= 8; }
+                    if (r >= 4)    { for (int l = 0; l < 4; l++) sum = __fadd_rn(sum, __fmul_rn(__ldcg(Vd + (size_t)(i + l) * E), p[i + l])); i += 4; r -= 4; }
+                    for (; r > 0; r--, i++) sum = __fmaf_rn(__ldcg(Vd + (size_t) i * E), p[i], sum);
+                    __stcg(A.gatt + h * D + pc * 16 + tid, sum);
+                }
+            }
+        }
+        bar_target += gridDim.x; grid_barrier(A.barrier, bar_target);
+
+        // ---- P4: c_proj + residual ----
+        for (int i = tid; i < E; i += kThreads) { const float t = __ldcg(A.gatt + i); act[act_index(i)] = kRound ? round_f16(t) : t; }
+        __syncthreads();
+        run_phase(4 * il + 1, EP_RESID, il);
+        bar_target += gridDim.x; grid_barrier(A.barrier, bar_target);
+
+        // ---- P5: LN2 -> c_fc -> GELU ----
+        for (int i = tid; i < E; i += kThreads) xs[i] = __ldcg(A.gx + i);
+        __syncthreads();
+        block_layernorm<kRound>(xs, E, lv.ln_2_g, lv.ln_2_b, act, red, A.ln_fallbacks);
+        run_phase(4 * il + 2, EP_GELU, il);
+        bar_target += gridDim.x; grid_barrier(A.barrier, bar_target);
+
+        // ---- P6: mlp/c_proj + residual ----
+        for (int i = tid; i < 4 * E; i += kThreads) { const float t = __ldcg(A.gff + i); act[act_index(i)] = kRound ? round_f16(t) : t; }
+        __syncthreads();
+        run_phase(4 * il + 3, EP_RESID, il);
+        bar_target += gridDim.x; grid_barrier(A.barrier, bar_target);
+
+        for (int i = tid; i < E; i += kThreads) xs[i] = __ldcg(A.gx + i);
+        __syncthreads();
+    }
+    // ---- final norm + lm_head window ----
+    block_layernorm<kRound>(xs, E, A.ln_f_g, A.ln_f_b, act, red, A.ln_fallbacks);
+    run_phase(4 * L, EP_LOGITS, 0);
+}
+
+static size_t decode_smem_bytes() { return (size_t) SmemLayout::total + 128; }
+
+int decode_barriers_per_step(int n_layer) { return 6 * n_layer; }
+
+void launch_decode_step(const DecodeArgs & args, WType wt, int n_sm, cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        BARK_CUDA_CHECK(cudaFuncSetAttribute(gpt_decode_step_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) decode_smem_bytes()));
+        BARK_CUDA_CHECK(cudaFuncSetAttribute(gpt_decode_step_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) decode_smem_bytes()));
+        configured = true;
+    }
+    DecodeArgs a = args;
+    void * kargs[] = {(void *) &a};
+    const void * fn = wt == W_F16 ? (const void *) gpt_decode_step_kernel<__half> : (const void *) gpt_decode_step_kernel<float>;
+    if (g_prof_on) prof_begin("gpt_decode_step_kernel", s, g_next_bytes, g_next_flops);
+    BARK_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(n_sm), dim3(kThreads), kargs, decode_smem_bytes(), s));
+    if (g_prof_on) prof_end(s);
+    g_next_bytes = g_next_flops = 0.0;
+    ++g_kernel_launches;
+}
+
+}  // namespace bark

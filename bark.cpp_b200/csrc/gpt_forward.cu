@@ -7,6 +7,7 @@
 #include "gpt_kernels.h"
 
 #include <algorithm>
+#include <vector>
 #include <time.h>
 
 namespace bark {
@@ -49,7 +50,47 @@ static void run_layers(bark_context * ctx, GPTModel & m, int N, int n_past, bool
     }
 }
 
-bool gpt_eval(bark_context * ctx, GPTModel & m, const int32_t * tokens, int n, int * n_past, bool merge_ctx, float * logits_host) {
+// Phase table + exchange buffers of the persistent decode kernel (decode_kernels.cu), once per causal model.
+void build_decode_tables(bark_context * ctx, GPTModel & m) {
+    const int L = m.n_layer, E = m.n_embd;
+    const size_t es = m.wtype == W_F16 ? 2 : 4;
+    std::vector<DecodePhase> ph((size_t) 4 * L + 1);
+    std::vector<DecodeLayerVec> lv((size_t) L);
+    auto set = [&](DecodePhase & p, const DMat & d) { p.w = d.p; p.n_out = d.n_out; p.K = d.K; p.row_bytes = (int)(d.Kp * es); p.pad = 0; };
+    for (int l = 0; l < L; l++) {
+        const GPTLayer & G = m.layers[(size_t) l];
+        set(ph[(size_t) 4 * l], G.c_attn); set(ph[(size_t) 4 * l + 1], G.c_proj); set(ph[(size_t) 4 * l + 2], G.fc); set(ph[(size_t) 4 * l + 3], G.proj);
+        lv[(size_t) l] = DecodeLayerVec{G.ln_1_g, G.ln_1_b, G.ln_2_g, G.ln_2_b};
+    }
+    set(ph[(size_t) 4 * L], m.lm_head[0]);
+    m.d_phases = ctx_alloc(ctx, ph.size() * sizeof(DecodePhase));
+    m.d_layer_vecs = ctx_alloc(ctx, lv.size() * sizeof(DecodeLayerVec));
+    BARK_CUDA_CHECK(cudaMemcpy(m.d_phases, ph.data(), ph.size() * sizeof(DecodePhase), cudaMemcpyHostToDevice));
+    BARK_CUDA_CHECK(cudaMemcpy(m.d_layer_vecs, lv.data(), lv.size() * sizeof(DecodeLayerVec), cudaMemcpyHostToDevice));
+    m.gx = (float *) ctx_alloc(ctx, (size_t) E * 4);  m.gq = (float *) ctx_alloc(ctx, (size_t) E * 4);
+    m.gatt = (float *) ctx_alloc(ctx, (size_t) E * 4); m.gff = (float *) ctx_alloc(ctx, (size_t) 4 * E * 4);
+    m.gscores = (float *) ctx_alloc(ctx, (size_t) m.n_head * m.block_size * 4);
+    m.glogits = (float *) ctx_alloc(ctx, (size_t) m.n_out_vocab * 4);
+}
+
+// one decode token through the persistent kernel
+static void decode_step(bark_context * ctx, GPTModel & m, int token, int n_past, int lm_lo, int lm_hi) {
+    DecodeArgs a{};
+    a.phases = (const DecodePhase *) m.d_phases; a.layer_vecs = (const DecodeLayerVec *) m.d_layer_vecs;
+    a.wte = m.wte[0]; a.wpe = m.wpe; a.ln_f_g = m.ln_f_g; a.ln_f_b = m.ln_f_b; a.gelu_tab = ctx->d_gelu_tab;
+    a.mem_k = m.mem_k; a.mem_v = m.mem_v;
+    a.gx = m.gx; a.gq = m.gq; a.gatt = m.gatt; a.gff = m.gff; a.gscores = m.gscores; a.logits = m.glogits;
+    a.barrier = ctx->d_barrier; a.barrier_base = ctx->barrier_base; a.ln_fallbacks = ctx->d_ln_fallbacks;
+    a.E = m.n_embd; a.H = m.n_head; a.L = m.n_layer; a.block_size = m.block_size; a.n_past = n_past; a.token = token; a.lm_lo = lm_lo; a.lm_hi = lm_hi;
+    const double es = m.wtype == W_F16 ? 2.0 : 4.0;
+    const double E = m.n_embd, L = m.n_layer;
+    g_next_bytes = (12.0 * L * E * E + (double)(lm_hi - lm_lo) * E) * es + 2.0 * L * (double)(n_past + 1) * E * 4.0 + 2.0 * L * E * 4.0 + (double)(lm_hi - lm_lo) * 4.0;   // SURVEY §8d B_tok
+    g_next_flops = 2.0 * (12.0 * L * E * E + (double)(lm_hi - lm_lo) * E) + 4.0 * L * (double)(n_past + 1) * E;
+    launch_decode_step(a, m.wtype, ctx->n_sm, ctx->stream);
+    ctx->barrier_base += (unsigned) decode_barriers_per_step(m.n_layer) * (unsigned) ctx->n_sm;
+}
+
+bool gpt_eval(bark_context * ctx, GPTModel & m, const int32_t * tokens, int n, int * n_past, bool merge_ctx, float * logits_host, int lm_lo, int lm_hi) {
     if (!n_past) { fprintf(stderr, "%s: n_past is null\n", __func__); return false; }
     const int64_t t0 = now_us();
     Workspace & ws = ctx->ws;
@@ -57,8 +98,19 @@ bool gpt_eval(bark_context * ctx, GPTModel & m, const int32_t * tokens, int n, i
     const int E = m.n_embd;
     int N = n;
     bool merge = false;
+    if (lm_hi <= 0 || lm_hi > m.n_out_vocab || lm_lo < 0 || lm_lo >= lm_hi) { lm_lo = 0; lm_hi = m.n_out_vocab; }
     if (*n_past > 0) {
         if (N != 1) { fprintf(stderr, "%s: decoding expects one token per step (got %d)\n", __func__, N); return false; }
+        if (ctx->use_decode_kernel && *n_past + 1 <= m.block_size && tokens[0] >= 0 && tokens[0] < m.n_in_vocab) {
+            decode_step(ctx, m, tokens[0], *n_past, lm_lo, lm_hi);
+            const size_t nb = (size_t)(lm_hi - lm_lo) * sizeof(float);
+            BARK_CUDA_CHECK(cudaMemcpyAsync(ctx->h_logits, m.glogits + lm_lo, nb, cudaMemcpyDeviceToHost, s)); g_d2h_bytes += nb;
+            BARK_CUDA_CHECK(cudaStreamSynchronize(s));
+            memcpy(logits_host + lm_lo, ctx->h_logits, nb);
+            *n_past += 1;
+            m.t_predict_us += now_us() - t0;
+            return true;
+        }
     } else if (merge_ctx) {
         if (N != 513) { fprintf(stderr, "%s: merged prompt must hold 256+256+1 ids (got %d)\n", __func__, N); return false; }
         N = 257; merge = true;                                                                                  // bark.cpp:1230-1233

@@ -27,4 +27,19 @@ void lane_matmul(const DMat & W, const void * act, int rows, const MatmulEpilogu
 void attention(const float * Q, const float * Kc, const float * Vc, int N, int n_kv, int n_past, int E, int H, bool causal,
                float * scores, void * act, WType wt, int Kp, cudaStream_t s);
 
+// ---- persistent decode step (decode_kernels.cu) -----------------------------------------------------------------
+struct DecodePhase { const void * w; int n_out, row_bytes, K, pad; };            // one streamed matrix: LI rows
+struct DecodeLayerVec { const float * ln_1_g, * ln_1_b, * ln_2_g, * ln_2_b; };
+struct DecodeArgs {
+    const DecodePhase * phases;          // [4L + 1]: per layer c_attn, c_proj, c_fc, mlp/c_proj; then lm_head
+    const DecodeLayerVec * layer_vecs;   // [L]
+    const void * wte; const float * wpe; const float * ln_f_g, * ln_f_b; const __half * gelu_tab;
+    float * mem_k, * mem_v;              // f32 KV cache [L][block_size][E]
+    float * gx, * gq, * gatt, * gff, * gscores, * logits;   // cross-CTA exchange vectors (L2)
+    unsigned * barrier; unsigned barrier_base; unsigned * ln_fallbacks;
+    int E, H, L, block_size, n_past, token, lm_lo, lm_hi;
+};
+int  decode_barriers_per_step(int n_layer);
+void launch_decode_step(const DecodeArgs & args, WType wt, int n_sm, cudaStream_t s);
+
 }  // namespace bark

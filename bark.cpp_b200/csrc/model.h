@@ -32,6 +32,9 @@ struct GPTModel {
     DMat lm_head[8];
     std::vector<GPTLayer> layers;
     float * mem_k = nullptr, * mem_v = nullptr;   // [L][block_size][E] f32 (bark.cpp:980-981); null for the fine model
+    // persistent decode step (decode_kernels.cu): phase table + cross-CTA exchange buffers, built once at load
+    void * d_phases = nullptr, * d_layer_vecs = nullptr;
+    float * gx = nullptr, * gq = nullptr, * gatt = nullptr, * gff = nullptr, * gscores = nullptr, * glogits = nullptr;
     // per-model statistics, same meaning as gpt_model::t_* (bark.cpp:114-118)
     int64_t t_sample_us = 0, t_predict_us = 0, t_main_us = 0, n_sample = 0;
 };
