@@ -231,6 +231,18 @@ def run_ours(args):
     emit(result)
 
 
+def usable_cpus():
+    """CPUs this container may really use: affinity mask capped by the cgroup CPU quota (nproc alone over-reports on shared hosts)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = max(1, min(n, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return n
+
+
 def cpu_baseline(path, budget_s=30.0, steps=1):
     """The reference's CPU path on this box's host cores: oracle/_ref (the unmodified reference) when it travelled with the
     snapshot, else the C oracle port.  Bounded sample: the clip is shortened (n_steps_text_encoder) until one run fits the budget."""
@@ -239,14 +251,16 @@ def cpu_baseline(path, budget_s=30.0, steps=1):
     if orc.have_ref():
         # ggml's thread pool spins on a barrier per graph node, so "all cores" is not its fastest setting on a big host:
         # try a few thread counts on a short clip and keep the best (reported as `cores`).
-        cands = sorted({c for c in (8, 16, 32, 64, cores) if c <= cores})
+        usable = usable_cpus()
+        cands = sorted({c for c in (4, 8, 16, 32, usable) if c <= usable})
         best = None
-        for c in cands:
+        for c in cands:                                      # ascending; stop as soon as more threads stop helping
             r = orc.Ref(path, seed=0, n_steps=8)
             t0 = time.perf_counter(); r.generate(PROMPT, n_threads=c); dt = time.perf_counter() - t0
             st = r.stats()
-            if best is None or dt < best[1]:
-                best = (c, dt, st[4] * 1e-6)
+            if best is not None and dt > best[1]:
+                break
+            best = (c, dt, st[4] * 1e-6)
         threads, t_short, t_fine = best
         # fine stage cost is fixed (6 passes over 1024 rows); semantic+coarse scale with the clip
         per_tok = max((t_short - t_fine) / 8.0, 1e-4)
