@@ -21,6 +21,7 @@ struct bark_context {
     unsigned * d_ln_fallbacks = nullptr;             // [0] LayerNorm rows, [1] soft_max rows replayed sequentially
     unsigned * d_barrier = nullptr; unsigned barrier_base = 0;   // grid barrier counter of the persistent decode kernel
     int n_sm = 0; bool use_decode_kernel = true;
+    unsigned long long * d_timing = nullptr;         // optional phase timestamps of the decode kernel (BARK_B200_DECODE_TIMING=1)
 
     bark::Workspace ws;
     float * h_logits = nullptr;                      // pinned, max(n_out) or 1024*fine_vocab

@@ -256,6 +256,10 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
     __syncthreads();
 
     unsigned bar_target = A.barrier_base;
+    // optional phase timestamps (CTA 0, thread 0): timing[layer*16 + i], i = before/after each of the 6 barriers
+    auto stamp = [&](int layer, int i) {
+        if (A.timing && blockIdx.x == 0 && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); A.timing[layer * 16 + i] = t; }
+    };
     const float scale = 1.0f / sqrtf((float) E / (float) H);
 
     // consume every chunk of `phase` that belongs to this CTA
@@ -295,10 +299,13 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
 
     for (int il = 0; il < L; il++) {
         const DecodeLayerVec & lv = A.layer_vecs[il];
+        stamp(il, 12);
         // ---- P1: LN1 -> QKV ----
         block_layernorm<kRound>(xs, E, lv.ln_1_g, lv.ln_1_b, act, red, A.ln_fallbacks);
         run_phase(4 * il + 0, EP_QKV, il);
+        stamp(il, 0);
         bar_target += gridDim.x; grid_barrier(A.barrier, bar_target);
+        stamp(il, 1);
 
         // ---- P2: scores ----
         for (int i = tid; i < E; i += kThreads) qs[i] = __ldcg(A.gq + i);
@@ -315,7 +322,9 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
                 if (lane == 0) __stcg(A.gscores + (size_t) h * ctx + k, __fmul_rn(r, scale));
             }
         }
+        stamp(il, 2);
         bar_target += gridDim.x; grid_barrier(A.barrier, bar_target);
+        stamp(il, 3);
 
         // ---- P3: soft_max + P.V, one CTA per (head, 16 columns of the head) ----
         {
@@ -397,26 +406,34 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
                 }
             }
         }
+        stamp(il, 4);
         bar_target += gridDim.x; grid_barrier(A.barrier, bar_target);
+        stamp(il, 5);
 
         // ---- P4: c_proj + residual ----
         for (int i = tid; i < E; i += kThreads) { const float t = __ldcg(A.gatt + i); act[act_index(i)] = kRound ? round_f16(t) : t; }
         __syncthreads();
         run_phase(4 * il + 1, EP_RESID, il);
+        stamp(il, 6);
         bar_target += gridDim.x; grid_barrier(A.barrier, bar_target);
+        stamp(il, 7);
 
         // ---- P5: LN2 -> c_fc -> GELU ----
         for (int i = tid; i < E; i += kThreads) xs[i] = __ldcg(A.gx + i);
         __syncthreads();
         block_layernorm<kRound>(xs, E, lv.ln_2_g, lv.ln_2_b, act, red, A.ln_fallbacks);
         run_phase(4 * il + 2, EP_GELU, il);
+        stamp(il, 8);
         bar_target += gridDim.x; grid_barrier(A.barrier, bar_target);
+        stamp(il, 9);
 
         // ---- P6: mlp/c_proj + residual ----
         for (int i = tid; i < 4 * E; i += kThreads) { const float t = __ldcg(A.gff + i); act[act_index(i)] = kRound ? round_f16(t) : t; }
         __syncthreads();
         run_phase(4 * il + 3, EP_RESID, il);
+        stamp(il, 10);
         bar_target += gridDim.x; grid_barrier(A.barrier, bar_target);
+        stamp(il, 11);
 
         for (int i = tid; i < E; i += kThreads) xs[i] = __ldcg(A.gx + i);
         __syncthreads();

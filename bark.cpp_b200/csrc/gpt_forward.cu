@@ -80,7 +80,7 @@ static void decode_step(bark_context * ctx, GPTModel & m, int token, int n_past,
     a.wte = m.wte[0]; a.wpe = m.wpe; a.ln_f_g = m.ln_f_g; a.ln_f_b = m.ln_f_b; a.gelu_tab = ctx->d_gelu_tab;
     a.mem_k = m.mem_k; a.mem_v = m.mem_v;
     a.gx = m.gx; a.gq = m.gq; a.gatt = m.gatt; a.gff = m.gff; a.gscores = m.gscores; a.logits = m.glogits;
-    a.barrier = ctx->d_barrier; a.barrier_base = ctx->barrier_base; a.ln_fallbacks = ctx->d_ln_fallbacks;
+    a.barrier = ctx->d_barrier; a.barrier_base = ctx->barrier_base; a.ln_fallbacks = ctx->d_ln_fallbacks; a.timing = ctx->d_timing;
     a.E = m.n_embd; a.H = m.n_head; a.L = m.n_layer; a.block_size = m.block_size; a.n_past = n_past; a.token = token; a.lm_lo = lm_lo; a.lm_hi = lm_hi;
     const double es = m.wtype == W_F16 ? 2.0 : 4.0;
     const double E = m.n_embd, L = m.n_layer;

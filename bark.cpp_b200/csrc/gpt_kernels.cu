@@ -7,29 +7,13 @@
 // intrinsics (__fmaf_rn, __fadd_rn, ...) so nvcc can neither contract nor reassociate it; the
 // accumulation order is the reference's (see common.cuh "Lane order").
 #include "gpt_kernels.h"
+#include "epilogue.cuh"
+
+#include <cstring>
 
 namespace bark {
 
 unsigned long long g_kernel_launches = 0;
-
-// ------------------------------------------------------------------------------------------------
-// activation operand writers: an activation value for column k of row m, in the format the next
-// mul_mat consumes (the reference converts src1 to the weight's vec_dot_type, ggml.c:12530-12558)
-// ------------------------------------------------------------------------------------------------
-template <typename T> struct ActIO;
-template <> struct ActIO<__half> {
-    static constexpr int G = 8;
-    __device__ static void store(void * act, size_t row_off, int k, float v) { ((__half *) act)[row_off + li_offset(k, 8)] = __float2half_rn(v); }
-};
-template <> struct ActIO<float> {
-    static constexpr int G = 4;
-    __device__ static void store(void * act, size_t row_off, int k, float v) { ((float *) act)[row_off + li_offset(k, 4)] = v; }
-};
-
-__device__ __forceinline__ void store_act(void * act, int wt, int Kp, int m, int k, float v) {
-    if (wt == W_F16) ActIO<__half>::store(act, (size_t) m * Kp, k, v);
-    else             ActIO<float>::store(act, (size_t) m * Kp, k, v);
-}
 
 // ------------------------------------------------------------------------------------------------
 // weight re-layout: row-major [n_out][K] -> lane-interleaved [n_out][Kp]
@@ -159,36 +143,6 @@ void layernorm_act(const float * x, int rows, int E, const float * g, const floa
 // chain with fused multiply-adds, then the fixed tree.  Weights and activations are both in LI
 // layout, so each chain group is one coalesced 16-byte load per lane.
 // ------------------------------------------------------------------------------------------------
-template <typename T> __device__ __forceinline__ void unpack16(const uint4 & u, float (&f)[16 / sizeof(T)]);
-template <> __device__ __forceinline__ void unpack16<__half>(const uint4 & u, float (&f)[8]) {
-    const __half2 * h = reinterpret_cast<const __half2 *>(&u);
-#pragma unroll
-    for (int i = 0; i < 4; i++) { const float2 t = __half22float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
-}
-template <> __device__ __forceinline__ void unpack16<float>(const uint4 & u, float (&f)[4]) {
-    f[0] = __uint_as_float(u.x); f[1] = __uint_as_float(u.y); f[2] = __uint_as_float(u.z); f[3] = __uint_as_float(u.w);
-}
-
-__device__ __forceinline__ float gelu_lookup(const __half * __restrict__ tab, float x) {   // ggml_vec_gelu_f32, ggml.c:2557-2571
-    if (x <= -10.0f) return 0.0f;
-    if (x >= 10.0f) return x;
-    return __half2float(tab[__half_as_ushort(__float2half_rn(x))]);
-}
-
-__device__ __forceinline__ void matmul_epilogue(const MatmulEpilogue & ep, int m, int o, float r) {
-    switch (ep.mode) {
-        case EPI_STORE: ep.out[(size_t) m * ep.ldo + o] = r; break;
-        case EPI_RESID: { float * p = ep.out + (size_t) m * ep.ldo + o; *p = __fadd_rn(r, *p); } break;
-        case EPI_GELU_ACT: store_act(ep.act_out, ep.act_wt, ep.act_Kp, m, o, gelu_lookup(ep.gelu_tab, r)); break;
-        case EPI_QKV: {
-            const int E = ep.ldo;
-            if (o < E)          ep.out[(size_t) m * E + o] = r;
-            else if (o < 2 * E) ep.k_out[(size_t) m * E + (o - E)] = r;
-            else                ep.v_out[(size_t) m * E + (o - 2 * E)] = r;
-        } break;
-    }
-}
-
 template <typename T, int MT>
 __global__ void __launch_bounds__(256) lane_matmul_kernel(const T * __restrict__ W, int K, int Kp, int O, const T * __restrict__ act, int M, MatmulEpilogue ep) {
     constexpr int G = 16 / sizeof(T);
@@ -231,6 +185,8 @@ __global__ void __launch_bounds__(256) lane_matmul_kernel(const T * __restrict__
     }
 }
 
+static bool use_tiled() { static const bool t = [] { const char * e = getenv("BARK_B200_GEMM"); return !(e && !strcmp(e, "simple")); }(); return t; }
+
 void lane_matmul(const DMat & W, const void * act, int rows, const MatmulEpilogue & ep, cudaStream_t s) {
     const int gx = (W.n_out + 7) / 8;
     {   // roofline annotation: algorithmic HBM bytes (weights once + operands) and flops of this mat-mul
@@ -238,6 +194,7 @@ void lane_matmul(const DMat & W, const void * act, int rows, const MatmulEpilogu
         g_next_bytes = (double) W.n_out * W.K * es + (double) rows * (W.K * es + W.n_out * 4.0);
         g_next_flops = 2.0 * rows * (double) W.n_out * W.K;
     }
+    if (rows >= 16 && use_tiled() && (W.type == W_F16 || W.type == W_F32)) { lane_gemm_tiled(W, act, rows, ep, s); return; }
     if (W.type == W_F16) {
         if (rows == 1) BARK_LAUNCH((lane_matmul_kernel<__half, 1>), dim3(gx, 1), 256, 0, s, (const __half *) W.p, W.K, W.Kp, W.n_out, (const __half *) act, rows, ep);
         else           BARK_LAUNCH((lane_matmul_kernel<__half, 8>), dim3(gx, (rows + 7) / 8), 256, 0, s, (const __half *) W.p, W.K, W.Kp, W.n_out, (const __half *) act, rows, ep);
@@ -350,6 +307,15 @@ void attention(const float * Q, const float * Kc, const float * Vc, int N, int n
     const int D = E / H;
     const float scale = 1.0f / sqrtf((float) E / (float) H);                 // bark.cpp:1318
     const int rows = H * N;
+    if (N >= 8 && use_tiled() && D % 32 == 0 && D <= 128) {
+        g_next_bytes = 4.0 * ((double) n_kv * E + (double) N * E + (double) H * N * n_kv); g_next_flops = 2.0 * (double) N * n_kv * E;
+        attention_tiled_scores(Q, Kc, N, n_kv, n_past, E, H, scale, causal, scores, s);
+        g_next_bytes = 8.0 * (double) rows * n_kv;
+        BARK_LAUNCH(attn_softmax_kernel, (rows + 7) / 8, 256, 0, s, scores, rows, n_kv);
+        g_next_bytes = 4.0 * ((double) n_kv * E + (double) H * N * n_kv + (double) N * E); g_next_flops = 2.0 * (double) N * n_kv * E;
+        attention_tiled_pv(scores, Vc, N, n_kv, E, H, act, wt, Kp, s);
+        return;
+    }
     g_next_bytes = 4.0 * ((double) n_kv * E + (double) N * E + (double) H * N * n_kv); g_next_flops = 2.0 * (double) N * n_kv * E;
     if (D == 64)       BARK_LAUNCH(attn_scores_kernel<2>, (rows + 7) / 8, 256, 0, s, Q, Kc, N, n_kv, n_past, E, H, scale, causal ? 1 : 0, scores);
     else if (D == 32)  BARK_LAUNCH(attn_scores_kernel<1>, (rows + 7) / 8, 256, 0, s, Q, Kc, N, n_kv, n_past, E, H, scale, causal ? 1 : 0, scores);

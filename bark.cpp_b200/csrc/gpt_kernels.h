@@ -27,6 +27,11 @@ void lane_matmul(const DMat & W, const void * act, int rows, const MatmulEpilogu
 void attention(const float * Q, const float * Kc, const float * Vc, int N, int n_kv, int n_past, int E, int H, bool causal,
                float * scores, void * act, WType wt, int Kp, cudaStream_t s);
 
+// ---- register-tiled multi-row kernels (gemm_kernels.cu) ------------------------------------------------------------
+void lane_gemm_tiled(const DMat & W, const void * act, int rows, const MatmulEpilogue & ep, cudaStream_t s);
+void attention_tiled_scores(const float * Q, const float * Kc, int N, int n_kv, int n_past, int E, int H, float scale, bool causal, float * scores, cudaStream_t s);
+void attention_tiled_pv(const float * scores, const float * Vc, int N, int n_kv, int E, int H, void * act, WType wt, int Kp, cudaStream_t s);
+
 // ---- persistent decode step (decode_kernels.cu) -----------------------------------------------------------------
 struct DecodePhase { const void * w; int n_out, row_bytes, K, pad; };            // one streamed matrix: LI rows
 struct DecodeLayerVec { const float * ln_1_g, * ln_1_b, * ln_2_g, * ln_2_b; };
@@ -37,6 +42,7 @@ struct DecodeArgs {
     float * mem_k, * mem_v;              // f32 KV cache [L][block_size][E]
     float * gx, * gq, * gatt, * gff, * gscores, * logits;   // cross-CTA exchange vectors (L2)
     unsigned * barrier; unsigned barrier_base; unsigned * ln_fallbacks;
+    unsigned long long * timing;         // optional [L][16] globaltimer stamps of CTA 0 (debug)
     int E, H, L, block_size, n_past, token, lm_lo, lm_hi;
 };
 int  decode_barriers_per_step(int n_layer);
