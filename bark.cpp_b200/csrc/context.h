@@ -19,7 +19,7 @@ struct bark_context {
 
     __half * d_gelu_tab = nullptr;                   // 65536-entry table, ggml.c:3795-3810
     unsigned * d_ln_fallbacks = nullptr;             // [0] LayerNorm rows, [1] soft_max rows replayed sequentially
-    unsigned * d_barrier = nullptr; unsigned barrier_base = 0;   // grid barrier counter of the persistent decode kernel
+    unsigned tag_base = 0;                           // epoch counter of the decode kernel's tagged exchanges (advances 6*L per token)
     int n_sm = 0; bool use_decode_kernel = true;
     unsigned long long * d_timing = nullptr;         // optional phase timestamps of the decode kernel (BARK_B200_DECODE_TIMING=1)
 

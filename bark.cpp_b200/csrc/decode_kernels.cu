@@ -3,17 +3,24 @@
 // layer on the CPU, ~10 kernel launches per layer in the multi-kernel path (gpt_forward.cu) — with the same bit-exact
 // arithmetic (common.cuh "Lane order").
 //
-// One CTA per SM, 512 threads.  Weight rows (lane-interleaved layout) are a pure stream: each CTA owns a contiguous row
-// range of every matrix and pulls it with TMA bulk copies (cp.async.bulk + mbarrier complete_tx) into a shared-memory
-// ring several phases ahead of use, so HBM traffic never waits on the dependent math.  Phases of a layer
-//   P1  LN1 -> QKV rows (q to global, K/V appended to the f32 KV cache)        | grid barrier
-//   P2  scores[h][k] = <K[k][h], q[h]> * scale, (h,k) pairs spread over all warps | grid barrier
-//   P3  per (head, 16-wide slice of the head dim): soft_max + P.V              | grid barrier
-//   P4  c_proj rows + residual                                                  | grid barrier
-//   P5  LN2 -> c_fc rows -> GELU table                                         | grid barrier
-//   P6  mlp/c_proj rows + residual                                              | grid barrier
-// then LN_f -> lm_head rows [row_lo, row_hi).  Barriers are a monotonic counter in global memory
-// (red.release / ld.acquire), cross-CTA vectors travel through L2 (ld.global.cg).
+// One CTA per SM, 512 threads.
+//  * Weights are a pure stream: each CTA owns a contiguous row range of every matrix (lane-interleaved rows) and pulls it
+//    with TMA bulk copies (cp.async.bulk + mbarrier complete_tx) into a shared-memory ring several phases ahead of use,
+//    so HBM traffic never waits on the dependent math.
+//  * Activations cross CTAs as TAGGED words: every exchanged float travels in one 8-byte {value, epoch} store; consumers
+//    spin on the words they need until the epoch matches.  Data and "ready" flag arrive in the same L2 transaction, so a
+//    grid-wide dependency costs one store->load latency instead of store + fence + atomic + poll + load (a classic
+//    barrier measured 1.5-2 us here; 6 per layer).  Epochs are unique per use and never reset.
+//  * KV rows of older positions are prefetched into registers BEFORE waiting for q / the probabilities.
+//
+// Phases of a layer (each ends by publishing tagged outputs, the next begins by consuming them):
+//   P1  LN1 -> QKV rows          -> q, k_new, v_new (+ K/V appended to the f32 KV cache for later tokens)
+//   P2  scores[h][k] = <K[k][h], q[h]> * scale, (h,k) pairs spread over all warps     -> scores
+//   P3  per (head, 16 columns of the head): soft_max + P.V                             -> att
+//   P4  c_proj rows + residual                                                         -> x
+//   P5  LN2 -> c_fc rows -> GELU table                                                 -> ff
+//   P6  mlp/c_proj rows + residual                                                     -> x
+// then LN_f -> lm_head rows [lm_lo, lm_hi) -> logits (plain stores; the kernel ends).
 #include "gpt_kernels.h"
 
 namespace bark {
@@ -25,15 +32,14 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kSlots = 5;
 constexpr int kSlotBytes = 32 * 1024;
 
-struct __align__(8) SmemLayout {
-    // dynamic shared memory carve-up (byte offsets); ring first (16-byte aligned for bulk copies)
-    static constexpr int ring = 0;
+struct SmemLayout {
+    static constexpr int ring = 0;                                  // kSlots x 32 KB weight ring (bulk-copy destination)
     static constexpr int act = ring + kSlots * kSlotBytes;          // two-plane LI activation operand, up to 4096 floats
     static constexpr int x = act + 4096 * 4;                        // residual stream, up to 1024 floats
-    static constexpr int q = x + 1024 * 4;                          // q vector / scores row, up to 1024 floats
-    static constexpr int part = q + 1024 * 4;                       // P.V lane partials [32][16] + chunk sums [128] + scratch
-    static constexpr int red = part + (32 * 16 + 128) * 4;          // block reduction scratch: 16 doubles x 2
-    static constexpr int bar = red + 2 * kWarps * 8;                // kSlots mbarriers
+    static constexpr int q = x + 1024 * 4;                          // q vector / probabilities row, up to 1024 floats
+    static constexpr int part = q + 1024 * 4;                       // P.V lane partials [32][16] + chunk sums [128]
+    static constexpr int red = part + (32 * 16 + 128) * 4;          // reduction scratch: 2 x 16 doubles + 4 broadcast slots
+    static constexpr int bar = red + (2 * kWarps + 4) * 8;          // kSlots mbarriers
     static constexpr int total = bar + kSlots * 8;
 };
 
@@ -56,14 +62,36 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void * src, uin
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-__device__ __forceinline__ void grid_barrier(unsigned * counter, unsigned target) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
-        unsigned v;
-        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory"); } while ((int) (v - target) < 0);
+// ---- tagged exchange -------------------------------------------------------------------------------------------------
+typedef unsigned long long tagged_t;                                // low 32 bits: float payload, high 32 bits: epoch
+__device__ __forceinline__ void publish(tagged_t * p, float v, uint32_t tag) {
+    const tagged_t w = ((tagged_t) tag << 32) | (tagged_t) __float_as_uint(v);
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+__device__ __forceinline__ tagged_t peek(const tagged_t * p) {
+    tagged_t w;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+    return w;
+}
+__device__ __forceinline__ float consume1(const tagged_t * p, uint32_t tag) {
+    tagged_t w = peek(p);
+    while ((uint32_t)(w >> 32) != tag) w = peek(p);
+    return __uint_as_float((uint32_t) w);
+}
+// every thread fetches entries tid, tid + 512, ... (< n <= 8 * 512): all loads go out together, stragglers are re-polled
+template <typename F>
+__device__ __forceinline__ void consume_vec(const tagged_t * g, int n, uint32_t tag, F && sink) {
+    tagged_t w[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) { const int i = threadIdx.x + j * kThreads; if (i < n) w[j] = peek(g + i); }
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int i = threadIdx.x + j * kThreads;
+        if (i < n) {
+            while ((uint32_t)(w[j] >> 32) != tag) w[j] = peek(g + i);
+            sink(i, __uint_as_float((uint32_t) w[j]));
+        }
     }
-    __syncthreads();
 }
 
 // two-plane LI index of column k in the shared activation operand: LDS.128 of one plane is contiguous across lanes
@@ -72,48 +100,62 @@ __device__ __forceinline__ int act_index(int k) {
     return (((g << 1) + (e >> 2)) * 32 + v) * 4 + (e & 3);
 }
 
-// sum of one double per thread over the block; every thread returns the same value (fixed order)
-__device__ __forceinline__ double block_sum_d(double v, double * scratch) {
+// Block-wide sum of doubles with few FP64 instructions: warp shuffles, one partial per warp, warp 0 folds them.
+// Returns the total in warp 0 (all its lanes); other warps get 0.  Contains one __syncthreads.
+__device__ __forceinline__ double block_sum_to_warp0(double v, double * scratch) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    __syncthreads();
     if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
     __syncthreads();
     double s = 0.0;
+    if (threadIdx.x < 32) {
+        s = threadIdx.x < kWarps ? scratch[threadIdx.x] : 0.0;
 #pragma unroll
-    for (int w = 0; w < kWarps; w++) s += scratch[w];
+        for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        s = __shfl_sync(0xffffffffu, s, 0);
+    }
     return s;
 }
 
-// LayerNorm of xs[0..E) (ggml.c:11964-12013, see layernorm_act_kernel for the order-independence argument) ->
-// activation operand (optionally f16-rounded) in two-plane LI order
+// LayerNorm of xs[0..E) (ggml.c:11964-12013; order-independence argument in layernorm_act_kernel, gpt_kernels.cu) ->
+// activation operand (optionally f16-rounded) in two-plane LI order.  `bc` = broadcast slots in shared memory.
 template <bool ROUND16>
 __device__ void block_layernorm(const float * xs, int E, const float * __restrict__ g, const float * __restrict__ b, float * act, double * scratch,
-                                unsigned * fallback_counter) {
+                                float * bc, unsigned * fallback_counter) {
     const double slack = 2.0 * (double) E * 0x1p-53 * (1.0 + 1e-6);
     double s = 0.0, a = 0.0;
     for (int i = threadIdx.x; i < E; i += kThreads) { const double v = (double) xs[i]; s += v; a += fabs(v); }
-    s = block_sum_d(s, scratch); a = block_sum_d(a, scratch + kWarps);
-    double d = slack * a;
-    float mean = __double2float_rn(__ddiv_rn(s, (double) E));
-    if (__double2float_rn(__ddiv_rn(s - d, (double) E)) != __double2float_rn(__ddiv_rn(s + d, (double) E))) {
-        double ss = 0.0;                                            // every thread replays the sequential sum (rare; keeps control flow uniform)
-        for (int i = 0; i < E; i++) ss = __dadd_rn(ss, (double) xs[i]);
-        mean = __double2float_rn(__ddiv_rn(ss, (double) E));
-        if (threadIdx.x == 0 && fallback_counter) atomicAdd(fallback_counter, 1u);
+    s = block_sum_to_warp0(s, scratch);
+    a = block_sum_to_warp0(a, scratch + kWarps);
+    if (threadIdx.x == 0) {
+        const double d = slack * a;
+        float mean = __double2float_rn(__ddiv_rn(s, (double) E));
+        if (__double2float_rn(__ddiv_rn(s - d, (double) E)) != __double2float_rn(__ddiv_rn(s + d, (double) E))) {
+            double ss = 0.0;                                        // rare: replay the reference's sequential sum
+            for (int i = 0; i < E; i++) ss = __dadd_rn(ss, (double) xs[i]);
+            mean = __double2float_rn(__ddiv_rn(ss, (double) E));
+            if (fallback_counter) atomicAdd(fallback_counter, 1u);
+        }
+        bc[0] = mean;
     }
+    __syncthreads();
+    const float mean = bc[0];
     double s2 = 0.0;
     for (int i = threadIdx.x; i < E; i += kThreads) { const float v = __fsub_rn(xs[i], mean); s2 += (double) __fmul_rn(v, v); }
-    s2 = block_sum_d(s2, scratch);
-    d = slack * s2;
-    float variance = __double2float_rn(__ddiv_rn(s2, (double) E));
-    if (__double2float_rn(__ddiv_rn(s2 - d, (double) E)) != __double2float_rn(__ddiv_rn(s2 + d, (double) E))) {
-        double ss = 0.0;
-        for (int i = 0; i < E; i++) { const float v = __fsub_rn(xs[i], mean); ss = __dadd_rn(ss, (double) __fmul_rn(v, v)); }
-        variance = __double2float_rn(__ddiv_rn(ss, (double) E));
-        if (threadIdx.x == 0 && fallback_counter) atomicAdd(fallback_counter, 1u);
+    s2 = block_sum_to_warp0(s2, scratch);
+    if (threadIdx.x == 0) {
+        const double d = slack * s2;
+        float variance = __double2float_rn(__ddiv_rn(s2, (double) E));
+        if (__double2float_rn(__ddiv_rn(s2 - d, (double) E)) != __double2float_rn(__ddiv_rn(s2 + d, (double) E))) {
+            double ss = 0.0;
+            for (int i = 0; i < E; i++) { const float v = __fsub_rn(xs[i], mean); ss = __dadd_rn(ss, (double) __fmul_rn(v, v)); }
+            variance = __double2float_rn(__ddiv_rn(ss, (double) E));
+            if (fallback_counter) atomicAdd(fallback_counter, 1u);
+        }
+        bc[1] = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(variance, 1e-5f)));
     }
-    const float scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(variance, 1e-5f)));
+    __syncthreads();
+    const float scale = bc[1];
     for (int i = threadIdx.x; i < E; i += kThreads) {
         float y = __fmul_rn(__fsub_rn(xs[i], mean), scale);
         y = __fmul_rn(y, g[i]);
@@ -124,23 +166,22 @@ __device__ void block_layernorm(const float * xs, int E, const float * __restric
 }
 
 // ---- weight stream --------------------------------------------------------------------------------------------------
-struct Cursor {                 // position in this CTA's chunk sequence: (phase, sub-chunk)
-    int phase, sub;
-};
+struct Cursor { int phase, sub; };                                  // position in this CTA's chunk sequence
 
 struct StreamCtx {
     const DecodePhase * phases; int n_phases;
-    int lm_lo, lm_hi;           // row window of the last phase (lm_head)
+    int lm_lo, lm_hi;                                               // row window of the last phase (lm_head)
     int cta, n_cta;
 };
 
-// rows [r0, r1) of `phase` owned by this CTA
+// rows [r0, r1) of `phase` owned by this CTA: balanced split, every CTA gets floor or ceil of n / n_cta rows
 __device__ __forceinline__ void cta_rows(const StreamCtx & sc, int phase, int & r0, int & r1) {
     const DecodePhase & p = sc.phases[phase];
     int lo = 0, hi = p.n_out;
     if (phase == sc.n_phases - 1) { lo = sc.lm_lo; hi = sc.lm_hi; }
-    const int n = hi - lo, per = (n + sc.n_cta - 1) / sc.n_cta;
-    r0 = min(hi, lo + sc.cta * per); r1 = min(hi, r0 + per);
+    const int n = hi - lo, base = n / sc.n_cta, rem = n % sc.n_cta;
+    r0 = lo + sc.cta * base + min(sc.cta, rem);
+    r1 = r0 + base + (sc.cta < rem ? 1 : 0);
 }
 __device__ __forceinline__ int rows_per_chunk(const DecodePhase & p) { return kSlotBytes / p.row_bytes; }
 __device__ __forceinline__ int phase_chunks(const StreamCtx & sc, int phase) {
@@ -148,7 +189,6 @@ __device__ __forceinline__ int phase_chunks(const StreamCtx & sc, int phase) {
     const int rpc = rows_per_chunk(sc.phases[phase]);
     return (r1 - r0 + rpc - 1) / rpc;
 }
-// advance to the next existing chunk at or after (phase, sub); returns false past the end
 __device__ __forceinline__ bool cursor_valid(const StreamCtx & sc, Cursor & c) {
     while (c.phase < sc.n_phases && c.sub >= phase_chunks(sc, c.phase)) { c.phase++; c.sub = 0; }
     return c.phase < sc.n_phases;
@@ -220,9 +260,11 @@ __device__ __forceinline__ float row_dot(const unsigned char * row, const float 
     return lane_tree_reduce(acc);
 }
 
+constexpr int kMaxTasks = 6;        // (h, k) score tasks per warp: H * block_size / (n_cta * kWarps) <= 16 * 1024 / (132 * 16) < 8
+
 }  // namespace
 
-template <typename WT>
+template <typename WT, int DSTEPS>
 __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs A) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char * ring = smem + SmemLayout::ring;
@@ -231,10 +273,14 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
     float * qs = reinterpret_cast<float *>(smem + SmemLayout::q);
     float * part = reinterpret_cast<float *>(smem + SmemLayout::part);
     double * red = reinterpret_cast<double *>(smem + SmemLayout::red);
+    float * bc = reinterpret_cast<float *>(red + 2 * kWarps);
     const uint32_t bars = smem_u32(smem + SmemLayout::bar);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int E = A.E, H = A.H, D = E / H, L = A.L, ctx = A.block_size, n_past = A.n_past, n_kv = n_past + 1;
+    constexpr int D = DSTEPS * 32;
+    const int E = A.E, H = A.H, L = A.L, ctx = A.block_size, n_past = A.n_past, n_kv = n_past + 1;
     constexpr bool kRound = sizeof(WT) == 2;
+    tagged_t * const gq = (tagged_t *) A.gq, * const gk = (tagged_t *) A.gk, * const gv = (tagged_t *) A.gv, * const gatt = (tagged_t *) A.gatt,
+             * const gx = (tagged_t *) A.gx, * const gff = (tagged_t *) A.gff, * const gscores = (tagged_t *) A.gscores;
 
     StreamCtx sc{A.phases, 4 * L + 1, A.lm_lo, A.lm_hi, (int) blockIdx.x, (int) gridDim.x};
     if (tid == 0) {
@@ -242,10 +288,10 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    Cursor prod{0, 0}, cons{0, 0};
-    int prod_n = 0, cons_n = 0;                              // chunks issued / consumed so far
+    Cursor prod{0, 0};
+    int cons_n = 0;                                          // chunks consumed so far
     if (tid == 0) {
-        for (int s = 0; s < kSlots && cursor_valid(sc, prod); s++) { issue_chunk(sc, prod, ring, bars, s); prod.sub++; prod_n++; }
+        for (int s = 0; s < kSlots && cursor_valid(sc, prod); s++) { issue_chunk(sc, prod, ring, bars, s); prod.sub++; }
     }
 
     // embedding of the one new token (bark.cpp:1226-1228, 1259): every CTA keeps its own copy of the residual stream
@@ -255,15 +301,14 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
     }
     __syncthreads();
 
-    unsigned bar_target = A.barrier_base;
-    // optional phase timestamps (CTA 0, thread 0): timing[layer*16 + i], i = before/after each of the 6 barriers
+    uint32_t tag = A.tag_base;                               // unique epoch per exchange; the host advances the base by 6 * L per launch
+    const float scale = 1.0f / sqrtf((float) E / (float) H);
     auto stamp = [&](int layer, int i) {
         if (A.timing && blockIdx.x == 0 && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); A.timing[layer * 16 + i] = t; }
     };
-    const float scale = 1.0f / sqrtf((float) E / (float) H);
 
-    // consume every chunk of `phase` that belongs to this CTA
-    auto run_phase = [&](int phase, int ep, int layer) {
+    // consume every weight chunk of `phase` that belongs to this CTA; outputs are published with epoch `otag`
+    auto run_phase = [&](int phase, int ep, int layer, uint32_t otag) {
         const DecodePhase & p = sc.phases[phase];
         int r0, r1; cta_rows(sc, phase, r0, r1);
         const int rpc = rows_per_chunk(p);
@@ -277,15 +322,15 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
                 const float v = row_dot<WT>(base + (size_t)(r - a) * p.row_bytes, act, p.K, lane);
                 if (lane == 0) {
                     if (ep == EP_QKV) {
-                        if (r < E) __stcg(A.gq + r, v);
-                        else if (r < 2 * E) __stcg(A.mem_k + ((size_t) layer * ctx + n_past) * E + (r - E), v);
-                        else __stcg(A.mem_v + ((size_t) layer * ctx + n_past) * E + (r - 2 * E), v);
+                        if (r < E) publish(gq + r, v, otag);
+                        else if (r < 2 * E) { publish(gk + (r - E), v, otag); A.mem_k[((size_t) layer * ctx + n_past) * E + (r - E)] = v; }
+                        else                { publish(gv + (r - 2 * E), v, otag); A.mem_v[((size_t) layer * ctx + n_past) * E + (r - 2 * E)] = v; }
                     } else if (ep == EP_RESID) {
-                        __stcg(A.gx + r, __fadd_rn(v, xs[r]));
+                        publish(gx + r, __fadd_rn(v, xs[r]), otag);
                     } else if (ep == EP_GELU) {
                         float gl;
                         if (v <= -10.0f) gl = 0.0f; else if (v >= 10.0f) gl = v; else gl = __half2float(A.gelu_tab[__half_as_ushort(__float2half_rn(v))]);
-                        __stcg(A.gff + r, gl);
+                        publish(gff + r, gl, otag);
                     } else {
                         A.logits[r] = v;
                     }
@@ -293,172 +338,223 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
             }
             cons_n++;
             __syncthreads();                                  // everyone is done reading this slot
-            if (tid == 0 && cursor_valid(sc, prod)) { issue_chunk(sc, prod, ring, bars, slot); prod.sub++; prod_n++; }
+            if (tid == 0 && cursor_valid(sc, prod)) { issue_chunk(sc, prod, ring, bars, slot); prod.sub++; }
         }
     };
 
+    const int parts = D >> 4;                                // P3: CTAs per head
+    const bool pv_cta = (int) blockIdx.x < H * parts;
+    const int pv_h = blockIdx.x / parts, pv_c = blockIdx.x % parts;
+    const int np = n_kv & ~31;
+
     for (int il = 0; il < L; il++) {
         const DecodeLayerVec & lv = A.layer_vecs[il];
+        const uint32_t t_qkv = tag + 1, t_sc = tag + 2, t_att = tag + 3, t_x1 = tag + 4, t_ff = tag + 5, t_x2 = tag + 6;
+        tag += 6;
         stamp(il, 12);
         // ---- P1: LN1 -> QKV ----
-        block_layernorm<kRound>(xs, E, lv.ln_1_g, lv.ln_1_b, act, red, A.ln_fallbacks);
-        run_phase(4 * il + 0, EP_QKV, il);
+        block_layernorm<kRound>(xs, E, lv.ln_1_g, lv.ln_1_b, act, red, bc, A.ln_fallbacks);
+        run_phase(4 * il + 0, EP_QKV, il, t_qkv);
         stamp(il, 0);
-        bar_target += gridDim.x; grid_barrier(A.barrier, bar_target);
-        stamp(il, 1);
 
-        // ---- P2: scores ----
-        for (int i = tid; i < E; i += kThreads) qs[i] = __ldcg(A.gq + i);
-        __syncthreads();
+        // ---- P2: scores.  K rows of older positions are fetched before q arrives. ----
         {
             const float * Kc = A.mem_k + (size_t) il * ctx * E;
             const int total = H * n_kv, gw = blockIdx.x * kWarps + warp, nw = gridDim.x * kWarps;
-            for (int t = gw; t < total; t += nw) {
+            float kf[kMaxTasks][DSTEPS];
+#pragma unroll
+            for (int i = 0; i < kMaxTasks; i++) {
+                const int t = gw + i * nw;
+                if (t < total) {
+                    const int h = t / n_kv, k = t % n_kv;
+                    if (k < n_past) {
+#pragma unroll
+                        for (int c = 0; c < DSTEPS; c++) kf[i][c] = __ldcg(Kc + (size_t) k * E + h * D + c * 32 + lane);
+                    }
+                }
+            }
+            consume_vec(gq, E, t_qkv, [&](int i, float v) { qs[i] = v; });
+            __syncthreads();
+            stamp(il, 1);
+#pragma unroll
+            for (int i = 0; i < kMaxTasks; i++) {
+                const int t = gw + i * nw;
+                if (t < total) {
+                    const int h = t / n_kv, k = t % n_kv;
+                    float acc = 0.0f;
+#pragma unroll
+                    for (int c = 0; c < DSTEPS; c++) {
+                        const float kv = (k < n_past) ? kf[i][c] : consume1(gk + h * D + c * 32 + lane, t_qkv);   // the new position's key comes through the exchange
+                        acc = __fmaf_rn(kv, qs[h * D + c * 32 + lane], acc);
+                    }
+                    const float r = lane_tree_reduce(acc);
+                    if (lane == 0) publish(gscores + (size_t) h * ctx + k, __fmul_rn(r, scale), t_sc);
+                }
+            }
+            for (int t = gw + kMaxTasks * nw; t < total; t += nw) {   // (not reached for the supported shapes; keeps the kernel total)
                 const int h = t / n_kv, k = t % n_kv;
-                const float * kr = Kc + (size_t) k * E + h * D;
                 float acc = 0.0f;
-                for (int c = 0; c < (D >> 5); c++) acc = __fmaf_rn(__ldcg(kr + c * 32 + lane), qs[h * D + c * 32 + lane], acc);
-                float r = lane_tree_reduce(acc);
-                if (lane == 0) __stcg(A.gscores + (size_t) h * ctx + k, __fmul_rn(r, scale));
+                for (int c = 0; c < DSTEPS; c++) {
+                    const float kv = (k < n_past) ? __ldcg(Kc + (size_t) k * E + h * D + c * 32 + lane) : consume1(gk + h * D + c * 32 + lane, t_qkv);
+                    acc = __fmaf_rn(kv, qs[h * D + c * 32 + lane], acc);
+                }
+                const float r = lane_tree_reduce(acc);
+                if (lane == 0) publish(gscores + (size_t) h * ctx + k, __fmul_rn(r, scale), t_sc);
             }
         }
         stamp(il, 2);
-        bar_target += gridDim.x; grid_barrier(A.barrier, bar_target);
-        stamp(il, 3);
 
         // ---- P3: soft_max + P.V, one CTA per (head, 16 columns of the head) ----
-        {
-            const int parts = D >> 4;
-            if ((int) blockIdx.x < H * parts) {
-                const int h = blockIdx.x / parts, pc = blockIdx.x % parts;
-                float * p = qs;                                  // scores row -> probabilities
-                float * csum = part + 32 * 16;                   // chunk sums
-                float mx = __int_as_float(0xff800000);
-                for (int i = tid; i < n_kv; i += kThreads) { const float v = __ldcg(A.gscores + (size_t) h * ctx + i); p[i] = v; mx = fmaxf(mx, v); }
+        if (pv_cta) {
+            const int h = pv_h, col0 = h * D + pv_c * 16;
+            const int v = tid >> 4, dd = tid & 15;              // thread (v, dd): virtual lane v of output column dd
+            const float * Vc = A.mem_v + (size_t) il * ctx * E + col0;
+            // prefetch this thread's chain of V values (older positions)
+            float vreg[32];
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-                float * fred = reinterpret_cast<float *>(red);
-                __syncthreads();
-                if (lane == 0) fred[warp] = mx;
-                __syncthreads();
-                mx = fred[0];
+            for (int c = 0; c < 32; c++) { const int k = v + 32 * c; if (k < np && k < n_past) vreg[c] = __ldcg(Vc + (size_t) k * E + dd); }
+            // leftover rows k = np + v (< 31 of them): one element per thread, parked in shared memory (`act` is idle in this phase)
+            const float vl = (np + v < n_past) ? __ldcg(Vc + (size_t)(np + v) * E + dd) : 0.0f;
+            const float v_new = consume1(gv + col0 + dd, t_qkv);     // value row of the new position
+            float * p = qs;                                          // scores row -> probabilities
+            float * csum = part + 32 * 16;
+            float mx = __int_as_float(0xff800000);
+            consume_vec(gscores + (size_t) h * ctx, n_kv, t_sc, [&](int i, float s) { p[i] = s; mx = fmaxf(mx, s); });
 #pragma unroll
-                for (int w = 1; w < kWarps; w++) mx = fmaxf(mx, fred[w]);
-                const int nchunks = n_kv >> 3;
-                if (tid < nchunks) {
-                    float v[8];
+            for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            float * fred = reinterpret_cast<float *>(red);
+            if (lane == 0) fred[warp] = mx;
+            __syncthreads();
+            mx = fred[0];
 #pragma unroll
-                    for (int l = 0; l < 8; l++) { v[l] = ggml_v_expf_dev(__fsub_rn(p[tid * 8 + l], mx)); }
+            for (int w = 1; w < kWarps; w++) mx = fmaxf(mx, fred[w]);
+            const int nchunks = n_kv >> 3;
+            if (tid < nchunks) {
+                float e8[8];
 #pragma unroll
-                    for (int l = 0; l < 8; l++) p[tid * 8 + l] = v[l];
-                    const float t0 = __fadd_rn(v[4], v[0]), t1 = __fadd_rn(v[5], v[1]), t2 = __fadd_rn(v[6], v[2]), t3 = __fadd_rn(v[7], v[3]);
-                    csum[tid] = __fadd_rn(__fadd_rn(t0, t2), __fadd_rn(t1, t3));
-                }
-                __syncthreads();
-                // sum = sequential double accumulation of the chunk sums, then the libm-expf tail (ggml.c:2845-2888).  All terms
-                // are positive, so a tree sum S brackets the sequential one within +-2n*2^-53*S; if 1/sum rounds to the same float at
-                // both ends the order cannot matter, else replay sequentially.
-                float sc_f;
-                {
-                    double s = 0.0;
-                    for (int c = lane; c < nchunks; c += 32) s += (double) csum[c];
+                for (int l = 0; l < 8; l++) e8[l] = ggml_v_expf_dev(__fsub_rn(p[tid * 8 + l], mx));
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                for (int l = 0; l < 8; l++) p[tid * 8 + l] = e8[l];
+                const float t0 = __fadd_rn(e8[4], e8[0]), t1 = __fadd_rn(e8[5], e8[1]), t2 = __fadd_rn(e8[6], e8[2]), t3 = __fadd_rn(e8[7], e8[3]);
+                csum[tid] = __fadd_rn(__fadd_rn(t0, t2), __fadd_rn(t1, t3));
+            }
+            __syncthreads();
+            // sum = sequential double accumulation of the chunk sums, then the libm-expf tail (ggml.c:2845-2888).  All terms are
+            // positive, so a tree sum S brackets the sequential one within +-2n*2^-53*S; if 1/sum rounds to the same float at both
+            // ends of the bracket the order cannot matter, else replay sequentially.  Done by warp 0, broadcast through bc[2].
+            if (warp == 0) {
+                double s = 0.0;
+                for (int c = lane; c < nchunks; c += 32) s += (double) csum[c];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                if (lane == 0) {
                     const double dl = 2.0 * (double)(nchunks + 8) * 0x1p-53 * s * (1.0 + 1e-6);
                     double lo = s - dl, hi = s + dl;
                     float tails[7]; int nt = 0;
                     for (int i = nchunks * 8; i < n_kv; i++) { tails[nt] = glibc_expf_dev(__fsub_rn(p[i], mx)); lo = __dadd_rn(lo, (double) tails[nt]); hi = __dadd_rn(hi, (double) tails[nt]); nt++; }
-                    float f_lo = __double2float_rn(__ddiv_rn(1.0, lo)), f_hi = __double2float_rn(__ddiv_rn(1.0, hi));
+                    float f_lo = __double2float_rn(__ddiv_rn(1.0, lo));
+                    const float f_hi = __double2float_rn(__ddiv_rn(1.0, hi));
                     if (f_lo != f_hi) {
                         double q2 = 0.0;
                         for (int c = 0; c < nchunks; c++) q2 = __dadd_rn(q2, (double) csum[c]);
                         for (int i = 0; i < nt; i++) q2 = __dadd_rn(q2, (double) tails[i]);
                         f_lo = __double2float_rn(__ddiv_rn(1.0, q2));
-                        if (tid == 0 && A.ln_fallbacks) atomicAdd(A.ln_fallbacks + 1, 1u);
+                        if (A.ln_fallbacks) atomicAdd(A.ln_fallbacks + 1, 1u);
                     }
-                    sc_f = f_lo;
-                    __syncthreads();
-                    if (tid < nt) p[nchunks * 8 + tid] = tails[tid];
+                    for (int i = 0; i < nt; i++) p[nchunks * 8 + i] = tails[i];
+                    bc[2] = f_lo;
                 }
-                __syncthreads();
-                for (int i = tid; i < n_kv; i += kThreads) p[i] = __fmul_rn(p[i], sc_f);
-                __syncthreads();
-                // P.V in lane order: thread (v, d) walks virtual lane v of output column d
-                const int v = tid >> 4, dd = tid & 15;
-                const float * Vc = A.mem_v + (size_t) il * ctx * E + h * D + pc * 16 + dd;
-                const int np = n_kv & ~31;
-                float acc = 0.0f;
-#pragma unroll 8
-                for (int k = v; k < np; k += 32) acc = __fmaf_rn(__ldcg(Vc + (size_t) k * E), p[k], acc);
-                part[v * 16 + dd] = acc;
-                __syncthreads();
-                if (tid < 16) {
-                    float a32[32];
+            }
+            __syncthreads();
+            const float sc_f = bc[2];
+            for (int i = tid; i < n_kv; i += kThreads) p[i] = __fmul_rn(p[i], sc_f);
+            __syncthreads();
+            float acc = 0.0f;
 #pragma unroll
-                    for (int l = 0; l < 32; l++) a32[l] = part[l * 16 + tid];
-                    float sum = lane_tree_reduce_local(a32);
-                    const float * Vd = A.mem_v + (size_t) il * ctx * E + h * D + pc * 16 + tid;
-                    int i = np, r = n_kv - np;                   // leftovers as the pinned build compiles them (oracle orc_vec_dot_f32)
-                    while (r >= 8) { for (int l = 0; l < 8; l++) sum = __fadd_rn(sum, __fmul_rn(__ldcg(Vd + (size_t)(i + l) * E), p[i + l])); i += 8; r -= 8; }
-                    if (r >= 4)    { for (int l = 0; l < 4; l++) sum = __fadd_rn(sum, __fmul_rn(__ldcg(Vd + (size_t)(i + l) * E), p[i + l])); i += 4; r -= 4; }
-                    for (; r > 0; r--, i++) sum = __fmaf_rn(__ldcg(Vd + (size_t) i * E), p[i], sum);
-                    __stcg(A.gatt + h * D + pc * 16 + tid, sum);
+            for (int c = 0; c < 32; c++) {
+                const int k = v + 32 * c;
+                if (k < np) acc = __fmaf_rn(k < n_past ? vreg[c] : v_new, p[k], acc);
+            }
+            part[v * 16 + dd] = acc;
+            act[v * 16 + dd] = vl;
+            __syncthreads();
+            if (tid < 16) {
+                float a32[32];
+#pragma unroll
+                for (int l = 0; l < 32; l++) a32[l] = part[l * 16 + tid];
+                float sum = lane_tree_reduce_local(a32);
+                // leftovers k = np .. n_kv-1 as the pinned build compiles them (oracle orc_vec_dot_f32): 8-groups and a 4-group of
+                // rounded multiply + add, then <= 3 fused multiply-adds
+                const int r = n_kv - np;
+                const int n8 = r & ~7, n4 = n8 + ((r - n8) >= 4 ? 4 : 0);
+#pragma unroll
+                for (int j = 0; j < 31; j++) {
+                    if (j < r) {
+                        const float vv = (np + j < n_past) ? act[j * 16 + tid] : v_new;
+                        if (j < n4) sum = __fadd_rn(sum, __fmul_rn(vv, p[np + j])); else sum = __fmaf_rn(vv, p[np + j], sum);
+                    }
                 }
+                publish(gatt + col0 + tid, sum, t_att);
             }
         }
         stamp(il, 4);
-        bar_target += gridDim.x; grid_barrier(A.barrier, bar_target);
-        stamp(il, 5);
 
         // ---- P4: c_proj + residual ----
-        for (int i = tid; i < E; i += kThreads) { const float t = __ldcg(A.gatt + i); act[act_index(i)] = kRound ? round_f16(t) : t; }
+        consume_vec(gatt, E, t_att, [&](int i, float t) { act[act_index(i)] = kRound ? round_f16(t) : t; });
         __syncthreads();
-        run_phase(4 * il + 1, EP_RESID, il);
+        stamp(il, 5);
+        run_phase(4 * il + 1, EP_RESID, il, t_x1);
         stamp(il, 6);
-        bar_target += gridDim.x; grid_barrier(A.barrier, bar_target);
-        stamp(il, 7);
 
         // ---- P5: LN2 -> c_fc -> GELU ----
-        for (int i = tid; i < E; i += kThreads) xs[i] = __ldcg(A.gx + i);
+        consume_vec(gx, E, t_x1, [&](int i, float t) { xs[i] = t; });
         __syncthreads();
-        block_layernorm<kRound>(xs, E, lv.ln_2_g, lv.ln_2_b, act, red, A.ln_fallbacks);
-        run_phase(4 * il + 2, EP_GELU, il);
+        stamp(il, 7);
+        block_layernorm<kRound>(xs, E, lv.ln_2_g, lv.ln_2_b, act, red, bc, A.ln_fallbacks);
+        run_phase(4 * il + 2, EP_GELU, il, t_ff);
         stamp(il, 8);
-        bar_target += gridDim.x; grid_barrier(A.barrier, bar_target);
-        stamp(il, 9);
 
         // ---- P6: mlp/c_proj + residual ----
-        for (int i = tid; i < 4 * E; i += kThreads) { const float t = __ldcg(A.gff + i); act[act_index(i)] = kRound ? round_f16(t) : t; }
+        consume_vec(gff, 4 * E, t_ff, [&](int i, float t) { act[act_index(i)] = kRound ? round_f16(t) : t; });
         __syncthreads();
-        run_phase(4 * il + 3, EP_RESID, il);
+        stamp(il, 9);
+        run_phase(4 * il + 3, EP_RESID, il, t_x2);
         stamp(il, 10);
-        bar_target += gridDim.x; grid_barrier(A.barrier, bar_target);
-        stamp(il, 11);
 
-        for (int i = tid; i < E; i += kThreads) xs[i] = __ldcg(A.gx + i);
+        consume_vec(gx, E, t_x2, [&](int i, float t) { xs[i] = t; });
         __syncthreads();
+        stamp(il, 11);
     }
     // ---- final norm + lm_head window ----
-    block_layernorm<kRound>(xs, E, A.ln_f_g, A.ln_f_b, act, red, A.ln_fallbacks);
-    run_phase(4 * L, EP_LOGITS, 0);
+    block_layernorm<kRound>(xs, E, A.ln_f_g, A.ln_f_b, act, red, bc, A.ln_fallbacks);
+    run_phase(4 * L, EP_LOGITS, 0, 0);
 }
 
 static size_t decode_smem_bytes() { return (size_t) SmemLayout::total + 128; }
 
-int decode_barriers_per_step(int n_layer) { return 6 * n_layer; }
+int decode_tags_per_step(int n_layer) { return 6 * n_layer; }
 
-void launch_decode_step(const DecodeArgs & args, WType wt, int n_sm, cudaStream_t s) {
+template <typename WT, int DSTEPS>
+static void launch_one(DecodeArgs a, int n_sm, cudaStream_t s) {
     static bool configured = false;
     if (!configured) {
-        BARK_CUDA_CHECK(cudaFuncSetAttribute(gpt_decode_step_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) decode_smem_bytes()));
-        BARK_CUDA_CHECK(cudaFuncSetAttribute(gpt_decode_step_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) decode_smem_bytes()));
+        BARK_CUDA_CHECK(cudaFuncSetAttribute(gpt_decode_step_kernel<WT, DSTEPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) decode_smem_bytes()));
         configured = true;
     }
-    DecodeArgs a = args;
     void * kargs[] = {(void *) &a};
-    const void * fn = wt == W_F16 ? (const void *) gpt_decode_step_kernel<__half> : (const void *) gpt_decode_step_kernel<float>;
+    BARK_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *) gpt_decode_step_kernel<WT, DSTEPS>, dim3(n_sm), dim3(kThreads), kargs, decode_smem_bytes(), s));
+}
+
+void launch_decode_step(const DecodeArgs & args, WType wt, int n_sm, cudaStream_t s) {
+    const int dsteps = args.E / args.H / 32;
     if (g_prof_on) prof_begin("gpt_decode_step_kernel", s, g_next_bytes, g_next_flops);
-    BARK_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(n_sm), dim3(kThreads), kargs, decode_smem_bytes(), s));
+    if (wt == W_F16) {
+        switch (dsteps) { case 1: launch_one<__half, 1>(args, n_sm, s); break; case 2: launch_one<__half, 2>(args, n_sm, s); break;
+                          case 3: launch_one<__half, 3>(args, n_sm, s); break; default: launch_one<__half, 4>(args, n_sm, s); }
+    } else {
+        switch (dsteps) { case 1: launch_one<float, 1>(args, n_sm, s); break; case 2: launch_one<float, 2>(args, n_sm, s); break;
+                          case 3: launch_one<float, 3>(args, n_sm, s); break; default: launch_one<float, 4>(args, n_sm, s); }
+    }
     if (g_prof_on) prof_end(s);
     g_next_bytes = g_next_flops = 0.0;
     ++g_kernel_launches;

@@ -67,9 +67,9 @@ void build_decode_tables(bark_context * ctx, GPTModel & m) {
     m.d_layer_vecs = ctx_alloc(ctx, lv.size() * sizeof(DecodeLayerVec));
     BARK_CUDA_CHECK(cudaMemcpy(m.d_phases, ph.data(), ph.size() * sizeof(DecodePhase), cudaMemcpyHostToDevice));
     BARK_CUDA_CHECK(cudaMemcpy(m.d_layer_vecs, lv.data(), lv.size() * sizeof(DecodeLayerVec), cudaMemcpyHostToDevice));
-    m.gx = (float *) ctx_alloc(ctx, (size_t) E * 4);  m.gq = (float *) ctx_alloc(ctx, (size_t) E * 4);
-    m.gatt = (float *) ctx_alloc(ctx, (size_t) E * 4); m.gff = (float *) ctx_alloc(ctx, (size_t) 4 * E * 4);
-    m.gscores = (float *) ctx_alloc(ctx, (size_t) m.n_head * m.block_size * 4);
+    auto tagged = [&](size_t n) { void * p = ctx_alloc(ctx, n * 8); BARK_CUDA_CHECK(cudaMemset(p, 0, n * 8)); return (unsigned long long *) p; };   // epoch 0 = never published
+    m.gx = tagged((size_t) E); m.gq = tagged((size_t) E); m.gk = tagged((size_t) E); m.gv = tagged((size_t) E); m.gatt = tagged((size_t) E);
+    m.gff = tagged((size_t) 4 * E); m.gscores = tagged((size_t) m.n_head * m.block_size);
     m.glogits = (float *) ctx_alloc(ctx, (size_t) m.n_out_vocab * 4);
 }
 
@@ -79,15 +79,15 @@ static void decode_step(bark_context * ctx, GPTModel & m, int token, int n_past,
     a.phases = (const DecodePhase *) m.d_phases; a.layer_vecs = (const DecodeLayerVec *) m.d_layer_vecs;
     a.wte = m.wte[0]; a.wpe = m.wpe; a.ln_f_g = m.ln_f_g; a.ln_f_b = m.ln_f_b; a.gelu_tab = ctx->d_gelu_tab;
     a.mem_k = m.mem_k; a.mem_v = m.mem_v;
-    a.gx = m.gx; a.gq = m.gq; a.gatt = m.gatt; a.gff = m.gff; a.gscores = m.gscores; a.logits = m.glogits;
-    a.barrier = ctx->d_barrier; a.barrier_base = ctx->barrier_base; a.ln_fallbacks = ctx->d_ln_fallbacks; a.timing = ctx->d_timing;
+    a.gx = m.gx; a.gq = m.gq; a.gk = m.gk; a.gv = m.gv; a.gatt = m.gatt; a.gff = m.gff; a.gscores = m.gscores; a.logits = m.glogits;
+    a.tag_base = ctx->tag_base; a.ln_fallbacks = ctx->d_ln_fallbacks; a.timing = ctx->d_timing;
     a.E = m.n_embd; a.H = m.n_head; a.L = m.n_layer; a.block_size = m.block_size; a.n_past = n_past; a.token = token; a.lm_lo = lm_lo; a.lm_hi = lm_hi;
     const double es = m.wtype == W_F16 ? 2.0 : 4.0;
     const double E = m.n_embd, L = m.n_layer;
     g_next_bytes = (12.0 * L * E * E + (double)(lm_hi - lm_lo) * E) * es + 2.0 * L * (double)(n_past + 1) * E * 4.0 + 2.0 * L * E * 4.0 + (double)(lm_hi - lm_lo) * 4.0;   // SURVEY §8d B_tok
     g_next_flops = 2.0 * (12.0 * L * E * E + (double)(lm_hi - lm_lo) * E) + 4.0 * L * (double)(n_past + 1) * E;
     launch_decode_step(a, m.wtype, ctx->n_sm, ctx->stream);
-    ctx->barrier_base += (unsigned) decode_barriers_per_step(m.n_layer) * (unsigned) ctx->n_sm;
+    ctx->tag_base += (unsigned) decode_tags_per_step(m.n_layer);
 }
 
 bool gpt_eval(bark_context * ctx, GPTModel & m, const int32_t * tokens, int n, int * n_past, bool merge_ctx, float * logits_host, int lm_lo, int lm_hi) {

@@ -40,12 +40,14 @@ struct DecodeArgs {
     const DecodeLayerVec * layer_vecs;   // [L]
     const void * wte; const float * wpe; const float * ln_f_g, * ln_f_b; const __half * gelu_tab;
     float * mem_k, * mem_v;              // f32 KV cache [L][block_size][E]
-    float * gx, * gq, * gatt, * gff, * gscores, * logits;   // cross-CTA exchange vectors (L2)
-    unsigned * barrier; unsigned barrier_base; unsigned * ln_fallbacks;
+    // cross-CTA exchange vectors in L2: 8-byte {float value, u32 epoch} words
+    unsigned long long * gx, * gq, * gk, * gv, * gatt, * gff, * gscores;
+    float * logits;
+    unsigned tag_base; unsigned * ln_fallbacks;
     unsigned long long * timing;         // optional [L][16] globaltimer stamps of CTA 0 (debug)
     int E, H, L, block_size, n_past, token, lm_lo, lm_hi;
 };
-int  decode_barriers_per_step(int n_layer);
+int  decode_tags_per_step(int n_layer);
 void launch_decode_step(const DecodeArgs & args, WType wt, int n_sm, cudaStream_t s);
 
 }  // namespace bark

@@ -312,8 +312,6 @@ bool load_model_file(const std::string & path, bark_context * ctx) {
     }
     ctx->d_ln_fallbacks = (unsigned *) ctx_alloc(ctx, 4 * sizeof(unsigned));
     BARK_CUDA_CHECK(cudaMemset(ctx->d_ln_fallbacks, 0, 4 * sizeof(unsigned)));
-    ctx->d_barrier = (unsigned *) ctx_alloc(ctx, sizeof(unsigned));
-    BARK_CUDA_CHECK(cudaMemset(ctx->d_barrier, 0, sizeof(unsigned)));
     build_decode_tables(ctx, ctx->semantic);
     build_decode_tables(ctx, ctx->coarse);
     return true;

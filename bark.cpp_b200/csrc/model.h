@@ -34,7 +34,8 @@ struct GPTModel {
     float * mem_k = nullptr, * mem_v = nullptr;   // [L][block_size][E] f32 (bark.cpp:980-981); null for the fine model
     // persistent decode step (decode_kernels.cu): phase table + cross-CTA exchange buffers, built once at load
     void * d_phases = nullptr, * d_layer_vecs = nullptr;
-    float * gx = nullptr, * gq = nullptr, * gatt = nullptr, * gff = nullptr, * gscores = nullptr, * glogits = nullptr;
+    unsigned long long * gx = nullptr, * gq = nullptr, * gk = nullptr, * gv = nullptr, * gatt = nullptr, * gff = nullptr, * gscores = nullptr;
+    float * glogits = nullptr;
     // per-model statistics, same meaning as gpt_model::t_* (bark.cpp:114-118)
     int64_t t_sample_us = 0, t_predict_us = 0, t_main_us = 0, n_sample = 0;
 };
