@@ -78,26 +78,31 @@ __device__ __forceinline__ float consume1(const tagged_t * p, uint32_t tag) {
     while ((uint32_t)(w >> 32) != tag) w = peek(p);
     return __uint_as_float((uint32_t) w);
 }
-// every thread fetches entries tid, tid + 512, ... (< n <= 8 * 512): all loads go out together, stragglers are re-polled
-template <typename F>
-__device__ __forceinline__ void consume_vec(const tagged_t * g, int n, uint32_t tag, F && sink) {
-    tagged_t w[8];
-#pragma unroll
-    for (int j = 0; j < 8; j++) { const int i = threadIdx.x + j * kThreads; if (i < n) w[j] = peek(g + i); }
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-        const int i = threadIdx.x + j * kThreads;
-        if (i < n) {
-            while ((uint32_t)(w[j] >> 32) != tag) w[j] = peek(g + i);
-            sink(i, __uint_as_float((uint32_t) w[j]));
-        }
-    }
-}
-
 // two-plane LI index of column k in the shared activation operand: LDS.128 of one plane is contiguous across lanes
 __device__ __forceinline__ int act_index(int k) {
     const int v = k & 31, c = k >> 5, g = c >> 3, e = c & 7;
     return (((g << 1) + (e >> 2)) * 32 + v) * 4 + (e & 3);
+}
+
+// Fetch a published vector into shared memory.  Every thread takes entries tid, tid + 512, ... (n <= MAXJ * 512): all loads
+// go out together, stragglers are re-polled.  Deliberately NOT inlined: the kernel lives or dies by its instruction-cache
+// footprint (a 100 KB body re-fetched from L2 every layer cost 5-10x), so shared pieces are real calls.
+enum { SINK_PLAIN = 0, SINK_ACT = 1, SINK_ACT_R16 = 2 };
+template <int MAXJ>
+__device__ __noinline__ void consume_to_smem(const tagged_t * g, int n, uint32_t tag, float * dst, int mode) {
+    tagged_t w[MAXJ];
+#pragma unroll
+    for (int j = 0; j < MAXJ; j++) { const int i = threadIdx.x + j * kThreads; if (i < n) w[j] = peek(g + i); }
+#pragma unroll
+    for (int j = 0; j < MAXJ; j++) {
+        const int i = threadIdx.x + j * kThreads;
+        if (i < n) {
+            while ((uint32_t)(w[j] >> 32) != tag) w[j] = peek(g + i);
+            const float v = __uint_as_float((uint32_t) w[j]);
+            if (mode == SINK_PLAIN) dst[i] = v; else dst[act_index(i)] = mode == SINK_ACT_R16 ? round_f16(v) : v;
+        }
+    }
+    __syncthreads();
 }
 
 // Block-wide sum of doubles with few FP64 instructions: warp shuffles, one partial per warp, warp 0 folds them.
@@ -120,7 +125,7 @@ __device__ __forceinline__ double block_sum_to_warp0(double v, double * scratch)
 // LayerNorm of xs[0..E) (ggml.c:11964-12013; order-independence argument in layernorm_act_kernel, gpt_kernels.cu) ->
 // activation operand (optionally f16-rounded) in two-plane LI order.  `bc` = broadcast slots in shared memory.
 template <bool ROUND16>
-__device__ void block_layernorm(const float * xs, int E, const float * __restrict__ g, const float * __restrict__ b, float * act, double * scratch,
+__device__ __noinline__ void block_layernorm(const float * xs, int E, const float * __restrict__ g, const float * __restrict__ b, float * act, double * scratch,
                                 float * bc, unsigned * fallback_counter) {
     const double slack = 2.0 * (double) E * 0x1p-53 * (1.0 + 1e-6);
     double s = 0.0, a = 0.0;
@@ -262,36 +267,94 @@ __device__ __forceinline__ float row_dot(const unsigned char * row, const float 
 
 constexpr int kMaxTasks = 6;        // (h, k) score tasks per warp: H * block_size / (n_cta * kWarps) <= 16 * 1024 / (132 * 16) < 8
 
+// everything run_phase needs; lives in registers/local memory of the kernel and is passed by reference
+struct PhaseCtx {
+    StreamCtx sc;
+    Cursor prod;                     // next chunk to request (thread 0)
+    int cons_n;                      // chunks consumed so far
+    unsigned char * ring; uint32_t bars;
+    const float * act; const float * xs;
+    tagged_t * gq, * gk, * gv, * gx, * gff;
+    float * mem_k, * mem_v, * logits;
+    const __half * gelu_tab;
+    int E, ctx, n_past;
+};
+
+// consume every weight chunk of `phase` that belongs to this CTA: one warp per row, lane-order dot against the shared
+// activation operand; outputs are published with epoch `otag` (or stored, for the logits)
+template <typename WT>
+__device__ __noinline__ void run_phase(PhaseCtx & pc, int phase, int ep, int layer, uint32_t otag) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const DecodePhase & p = pc.sc.phases[phase];
+    int r0, r1; cta_rows(pc.sc, phase, r0, r1);
+    const int rpc = rows_per_chunk(p);
+    const int nch = (r1 - r0 + rpc - 1) / rpc;
+    const int E = pc.E;
+    for (int sub = 0; sub < nch; sub++) {
+        const int slot = pc.cons_n % kSlots;
+        mbar_wait(pc.bars + slot * 8, (uint32_t)((pc.cons_n / kSlots) & 1));
+        const int a = r0 + sub * rpc, b = min(r1, a + rpc);
+        const unsigned char * base = pc.ring + (size_t) slot * kSlotBytes;
+        for (int r = a + warp; r < b; r += kWarps) {
+            const float v = row_dot<WT>(base + (size_t)(r - a) * p.row_bytes, pc.act, p.K, lane);
+            if (lane == 0) {
+                if (ep == EP_QKV) {
+                    const size_t slot_off = ((size_t) layer * pc.ctx + pc.n_past) * E;
+                    if (r < E) publish(pc.gq + r, v, otag);
+                    else if (r < 2 * E) { publish(pc.gk + (r - E), v, otag); pc.mem_k[slot_off + (r - E)] = v; }
+                    else                { publish(pc.gv + (r - 2 * E), v, otag); pc.mem_v[slot_off + (r - 2 * E)] = v; }
+                } else if (ep == EP_RESID) {
+                    publish(pc.gx + r, __fadd_rn(v, pc.xs[r]), otag);
+                } else if (ep == EP_GELU) {
+                    float gl;
+                    if (v <= -10.0f) gl = 0.0f; else if (v >= 10.0f) gl = v; else gl = __half2float(pc.gelu_tab[__half_as_ushort(__float2half_rn(v))]);
+                    publish(pc.gff + r, gl, otag);
+                } else {
+                    pc.logits[r] = v;
+                }
+            }
+        }
+        pc.cons_n++;
+        __syncthreads();                                  // everyone is done reading this slot
+        if (tid == 0 && cursor_valid(pc.sc, pc.prod)) { issue_chunk(pc.sc, pc.prod, pc.ring, pc.bars, slot); pc.prod.sub++; }
+    }
+}
+
 }  // namespace
 
 template <typename WT, int DSTEPS>
 __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs A) {
     extern __shared__ __align__(128) unsigned char smem[];
-    unsigned char * ring = smem + SmemLayout::ring;
     float * act = reinterpret_cast<float *>(smem + SmemLayout::act);
     float * xs = reinterpret_cast<float *>(smem + SmemLayout::x);
     float * qs = reinterpret_cast<float *>(smem + SmemLayout::q);
     float * part = reinterpret_cast<float *>(smem + SmemLayout::part);
     double * red = reinterpret_cast<double *>(smem + SmemLayout::red);
     float * bc = reinterpret_cast<float *>(red + 2 * kWarps);
-    const uint32_t bars = smem_u32(smem + SmemLayout::bar);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int D = DSTEPS * 32;
     const int E = A.E, H = A.H, L = A.L, ctx = A.block_size, n_past = A.n_past, n_kv = n_past + 1;
     constexpr bool kRound = sizeof(WT) == 2;
+    constexpr int kSinkAct = kRound ? SINK_ACT_R16 : SINK_ACT;
     tagged_t * const gq = (tagged_t *) A.gq, * const gk = (tagged_t *) A.gk, * const gv = (tagged_t *) A.gv, * const gatt = (tagged_t *) A.gatt,
              * const gx = (tagged_t *) A.gx, * const gff = (tagged_t *) A.gff, * const gscores = (tagged_t *) A.gscores;
 
-    StreamCtx sc{A.phases, 4 * L + 1, A.lm_lo, A.lm_hi, (int) blockIdx.x, (int) gridDim.x};
+    PhaseCtx pc;
+    pc.sc = StreamCtx{A.phases, 4 * L + 1, A.lm_lo, A.lm_hi, (int) blockIdx.x, (int) gridDim.x};
+    pc.prod = Cursor{0, 0}; pc.cons_n = 0;
+    pc.ring = smem + SmemLayout::ring; pc.bars = smem_u32(smem + SmemLayout::bar);
+    pc.act = act; pc.xs = xs;
+    pc.gq = gq; pc.gk = gk; pc.gv = gv; pc.gx = gx; pc.gff = gff;
+    pc.mem_k = A.mem_k; pc.mem_v = A.mem_v; pc.logits = A.logits; pc.gelu_tab = A.gelu_tab;
+    pc.E = E; pc.ctx = ctx; pc.n_past = n_past;
+
     if (tid == 0) {
-        for (int s = 0; s < kSlots; s++) mbar_init(bars + s * 8, 1);
+        for (int s = 0; s < kSlots; s++) mbar_init(pc.bars + s * 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    Cursor prod{0, 0};
-    int cons_n = 0;                                          // chunks consumed so far
     if (tid == 0) {
-        for (int s = 0; s < kSlots && cursor_valid(sc, prod); s++) { issue_chunk(sc, prod, ring, bars, s); prod.sub++; }
+        for (int s = 0; s < kSlots && cursor_valid(pc.sc, pc.prod); s++) { issue_chunk(pc.sc, pc.prod, pc.ring, pc.bars, s); pc.prod.sub++; }
     }
 
     // embedding of the one new token (bark.cpp:1226-1228, 1259): every CTA keeps its own copy of the residual stream
@@ -307,54 +370,20 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
         if (A.timing && blockIdx.x == 0 && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); A.timing[layer * 16 + i] = t; }
     };
 
-    // consume every weight chunk of `phase` that belongs to this CTA; outputs are published with epoch `otag`
-    auto run_phase = [&](int phase, int ep, int layer, uint32_t otag) {
-        const DecodePhase & p = sc.phases[phase];
-        int r0, r1; cta_rows(sc, phase, r0, r1);
-        const int rpc = rows_per_chunk(p);
-        const int nch = (r1 - r0 + rpc - 1) / rpc;
-        for (int sub = 0; sub < nch; sub++) {
-            const int slot = cons_n % kSlots;
-            mbar_wait(bars + slot * 8, (uint32_t)((cons_n / kSlots) & 1));
-            const int a = r0 + sub * rpc, b = min(r1, a + rpc);
-            const unsigned char * base = ring + (size_t) slot * kSlotBytes;
-            for (int r = a + warp; r < b; r += kWarps) {
-                const float v = row_dot<WT>(base + (size_t)(r - a) * p.row_bytes, act, p.K, lane);
-                if (lane == 0) {
-                    if (ep == EP_QKV) {
-                        if (r < E) publish(gq + r, v, otag);
-                        else if (r < 2 * E) { publish(gk + (r - E), v, otag); A.mem_k[((size_t) layer * ctx + n_past) * E + (r - E)] = v; }
-                        else                { publish(gv + (r - 2 * E), v, otag); A.mem_v[((size_t) layer * ctx + n_past) * E + (r - 2 * E)] = v; }
-                    } else if (ep == EP_RESID) {
-                        publish(gx + r, __fadd_rn(v, xs[r]), otag);
-                    } else if (ep == EP_GELU) {
-                        float gl;
-                        if (v <= -10.0f) gl = 0.0f; else if (v >= 10.0f) gl = v; else gl = __half2float(A.gelu_tab[__half_as_ushort(__float2half_rn(v))]);
-                        publish(gff + r, gl, otag);
-                    } else {
-                        A.logits[r] = v;
-                    }
-                }
-            }
-            cons_n++;
-            __syncthreads();                                  // everyone is done reading this slot
-            if (tid == 0 && cursor_valid(sc, prod)) { issue_chunk(sc, prod, ring, bars, slot); prod.sub++; }
-        }
-    };
-
     const int parts = D >> 4;                                // P3: CTAs per head
     const bool pv_cta = (int) blockIdx.x < H * parts;
     const int pv_h = blockIdx.x / parts, pv_c = blockIdx.x % parts;
     const int np = n_kv & ~31;
 
+#pragma unroll 1
     for (int il = 0; il < L; il++) {
-        const DecodeLayerVec & lv = A.layer_vecs[il];
+        const DecodeLayerVec lv = A.layer_vecs[il];
         const uint32_t t_qkv = tag + 1, t_sc = tag + 2, t_att = tag + 3, t_x1 = tag + 4, t_ff = tag + 5, t_x2 = tag + 6;
         tag += 6;
         stamp(il, 12);
         // ---- P1: LN1 -> QKV ----
         block_layernorm<kRound>(xs, E, lv.ln_1_g, lv.ln_1_b, act, red, bc, A.ln_fallbacks);
-        run_phase(4 * il + 0, EP_QKV, il, t_qkv);
+        run_phase<WT>(pc, 4 * il + 0, EP_QKV, il, t_qkv);
         stamp(il, 0);
 
         // ---- P2: scores.  K rows of older positions are fetched before q arrives. ----
@@ -366,21 +395,20 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
             for (int i = 0; i < kMaxTasks; i++) {
                 const int t = gw + i * nw;
                 if (t < total) {
-                    const int h = t / n_kv, k = t % n_kv;
+                    const int h = t / n_kv, k = t - h * n_kv;
                     if (k < n_past) {
 #pragma unroll
                         for (int c = 0; c < DSTEPS; c++) kf[i][c] = __ldcg(Kc + (size_t) k * E + h * D + c * 32 + lane);
                     }
                 }
             }
-            consume_vec(gq, E, t_qkv, [&](int i, float v) { qs[i] = v; });
-            __syncthreads();
+            consume_to_smem<2>(gq, E, t_qkv, qs, SINK_PLAIN);
             stamp(il, 1);
 #pragma unroll
             for (int i = 0; i < kMaxTasks; i++) {
                 const int t = gw + i * nw;
                 if (t < total) {
-                    const int h = t / n_kv, k = t % n_kv;
+                    const int h = t / n_kv, k = t - h * n_kv;
                     float acc = 0.0f;
 #pragma unroll
                     for (int c = 0; c < DSTEPS; c++) {
@@ -391,9 +419,11 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
                     if (lane == 0) publish(gscores + (size_t) h * ctx + k, __fmul_rn(r, scale), t_sc);
                 }
             }
+#pragma unroll 1
             for (int t = gw + kMaxTasks * nw; t < total; t += nw) {   // (not reached for the supported shapes; keeps the kernel total)
-                const int h = t / n_kv, k = t % n_kv;
+                const int h = t / n_kv, k = t - h * n_kv;
                 float acc = 0.0f;
+#pragma unroll
                 for (int c = 0; c < DSTEPS; c++) {
                     const float kv = (k < n_past) ? __ldcg(Kc + (size_t) k * E + h * D + c * 32 + lane) : consume1(gk + h * D + c * 32 + lane, t_qkv);
                     acc = __fmaf_rn(kv, qs[h * D + c * 32 + lane], acc);
@@ -409,17 +439,19 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
             const int h = pv_h, col0 = h * D + pv_c * 16;
             const int v = tid >> 4, dd = tid & 15;              // thread (v, dd): virtual lane v of output column dd
             const float * Vc = A.mem_v + (size_t) il * ctx * E + col0;
-            // prefetch this thread's chain of V values (older positions)
+            // prefetch this thread's chain of V values (older positions) ...
             float vreg[32];
 #pragma unroll
             for (int c = 0; c < 32; c++) { const int k = v + 32 * c; if (k < np && k < n_past) vreg[c] = __ldcg(Vc + (size_t) k * E + dd); }
-            // leftover rows k = np + v (< 31 of them): one element per thread, parked in shared memory (`act` is idle in this phase)
+            // ... and one element of the leftover rows k = np + v (parked in shared memory later; `act` is idle in this phase)
             const float vl = (np + v < n_past) ? __ldcg(Vc + (size_t)(np + v) * E + dd) : 0.0f;
             const float v_new = consume1(gv + col0 + dd, t_qkv);     // value row of the new position
             float * p = qs;                                          // scores row -> probabilities
             float * csum = part + 32 * 16;
+            consume_to_smem<2>(gscores + (size_t) h * ctx, n_kv, t_sc, p, SINK_PLAIN);
             float mx = __int_as_float(0xff800000);
-            consume_vec(gscores + (size_t) h * ctx, n_kv, t_sc, [&](int i, float s) { p[i] = s; mx = fmaxf(mx, s); });
+#pragma unroll 1
+            for (int i = tid; i < n_kv; i += kThreads) mx = fmaxf(mx, p[i]);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
             float * fred = reinterpret_cast<float *>(red);
@@ -430,12 +462,10 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
             for (int w = 1; w < kWarps; w++) mx = fmaxf(mx, fred[w]);
             const int nchunks = n_kv >> 3;
             if (tid < nchunks) {
-                float e8[8];
-#pragma unroll
-                for (int l = 0; l < 8; l++) e8[l] = ggml_v_expf_dev(__fsub_rn(p[tid * 8 + l], mx));
-#pragma unroll
-                for (int l = 0; l < 8; l++) p[tid * 8 + l] = e8[l];
-                const float t0 = __fadd_rn(e8[4], e8[0]), t1 = __fadd_rn(e8[5], e8[1]), t2 = __fadd_rn(e8[6], e8[2]), t3 = __fadd_rn(e8[7], e8[3]);
+                float * pc8 = p + tid * 8;
+#pragma unroll 1
+                for (int l = 0; l < 8; l++) pc8[l] = ggml_v_expf_dev(__fsub_rn(pc8[l], mx));
+                const float t0 = __fadd_rn(pc8[4], pc8[0]), t1 = __fadd_rn(pc8[5], pc8[1]), t2 = __fadd_rn(pc8[6], pc8[2]), t3 = __fadd_rn(pc8[7], pc8[3]);
                 csum[tid] = __fadd_rn(__fadd_rn(t0, t2), __fadd_rn(t1, t3));
             }
             __syncthreads();
@@ -444,29 +474,32 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
             // ends of the bracket the order cannot matter, else replay sequentially.  Done by warp 0, broadcast through bc[2].
             if (warp == 0) {
                 double s = 0.0;
+#pragma unroll 1
                 for (int c = lane; c < nchunks; c += 32) s += (double) csum[c];
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
                 if (lane == 0) {
                     const double dl = 2.0 * (double)(nchunks + 8) * 0x1p-53 * s * (1.0 + 1e-6);
                     double lo = s - dl, hi = s + dl;
-                    float tails[7]; int nt = 0;
-                    for (int i = nchunks * 8; i < n_kv; i++) { tails[nt] = glibc_expf_dev(__fsub_rn(p[i], mx)); lo = __dadd_rn(lo, (double) tails[nt]); hi = __dadd_rn(hi, (double) tails[nt]); nt++; }
+#pragma unroll 1
+                    for (int i = nchunks * 8; i < n_kv; i++) { const float tl = glibc_expf_dev(__fsub_rn(p[i], mx)); p[i] = tl; lo = __dadd_rn(lo, (double) tl); hi = __dadd_rn(hi, (double) tl); }
                     float f_lo = __double2float_rn(__ddiv_rn(1.0, lo));
                     const float f_hi = __double2float_rn(__ddiv_rn(1.0, hi));
                     if (f_lo != f_hi) {
                         double q2 = 0.0;
+#pragma unroll 1
                         for (int c = 0; c < nchunks; c++) q2 = __dadd_rn(q2, (double) csum[c]);
-                        for (int i = 0; i < nt; i++) q2 = __dadd_rn(q2, (double) tails[i]);
+#pragma unroll 1
+                        for (int i = nchunks * 8; i < n_kv; i++) q2 = __dadd_rn(q2, (double) p[i]);
                         f_lo = __double2float_rn(__ddiv_rn(1.0, q2));
                         if (A.ln_fallbacks) atomicAdd(A.ln_fallbacks + 1, 1u);
                     }
-                    for (int i = 0; i < nt; i++) p[nchunks * 8 + i] = tails[i];
                     bc[2] = f_lo;
                 }
             }
             __syncthreads();
             const float sc_f = bc[2];
+#pragma unroll 1
             for (int i = tid; i < n_kv; i += kThreads) p[i] = __fmul_rn(p[i], sc_f);
             __syncthreads();
             float acc = 0.0f;
@@ -487,47 +520,42 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
                 // rounded multiply + add, then <= 3 fused multiply-adds
                 const int r = n_kv - np;
                 const int n8 = r & ~7, n4 = n8 + ((r - n8) >= 4 ? 4 : 0);
-#pragma unroll
-                for (int j = 0; j < 31; j++) {
-                    if (j < r) {
-                        const float vv = (np + j < n_past) ? act[j * 16 + tid] : v_new;
-                        if (j < n4) sum = __fadd_rn(sum, __fmul_rn(vv, p[np + j])); else sum = __fmaf_rn(vv, p[np + j], sum);
-                    }
+#pragma unroll 1
+                for (int j = 0; j < r; j++) {
+                    const float vv = (np + j < n_past) ? act[j * 16 + tid] : v_new;
+                    if (j < n4) sum = __fadd_rn(sum, __fmul_rn(vv, p[np + j])); else sum = __fmaf_rn(vv, p[np + j], sum);
                 }
                 publish(gatt + col0 + tid, sum, t_att);
             }
+            __syncthreads();                                     // `act` / `qs` are reused by the next phase
         }
         stamp(il, 4);
 
         // ---- P4: c_proj + residual ----
-        consume_vec(gatt, E, t_att, [&](int i, float t) { act[act_index(i)] = kRound ? round_f16(t) : t; });
-        __syncthreads();
+        consume_to_smem<2>(gatt, E, t_att, act, kSinkAct);
         stamp(il, 5);
-        run_phase(4 * il + 1, EP_RESID, il, t_x1);
+        run_phase<WT>(pc, 4 * il + 1, EP_RESID, il, t_x1);
         stamp(il, 6);
 
         // ---- P5: LN2 -> c_fc -> GELU ----
-        consume_vec(gx, E, t_x1, [&](int i, float t) { xs[i] = t; });
-        __syncthreads();
+        consume_to_smem<2>(gx, E, t_x1, xs, SINK_PLAIN);
         stamp(il, 7);
         block_layernorm<kRound>(xs, E, lv.ln_2_g, lv.ln_2_b, act, red, bc, A.ln_fallbacks);
-        run_phase(4 * il + 2, EP_GELU, il, t_ff);
+        run_phase<WT>(pc, 4 * il + 2, EP_GELU, il, t_ff);
         stamp(il, 8);
 
         // ---- P6: mlp/c_proj + residual ----
-        consume_vec(gff, 4 * E, t_ff, [&](int i, float t) { act[act_index(i)] = kRound ? round_f16(t) : t; });
-        __syncthreads();
+        consume_to_smem<8>(gff, 4 * E, t_ff, act, kSinkAct);
         stamp(il, 9);
-        run_phase(4 * il + 3, EP_RESID, il, t_x2);
+        run_phase<WT>(pc, 4 * il + 3, EP_RESID, il, t_x2);
         stamp(il, 10);
 
-        consume_vec(gx, E, t_x2, [&](int i, float t) { xs[i] = t; });
-        __syncthreads();
+        consume_to_smem<2>(gx, E, t_x2, xs, SINK_PLAIN);
         stamp(il, 11);
     }
     // ---- final norm + lm_head window ----
     block_layernorm<kRound>(xs, E, A.ln_f_g, A.ln_f_b, act, red, bc, A.ln_fallbacks);
-    run_phase(4 * L, EP_LOGITS, 0, 0);
+    run_phase<WT>(pc, 4 * L, EP_LOGITS, 0, 0);
 }
 
 static size_t decode_smem_bytes() { return (size_t) SmemLayout::total + 128; }
