@@ -4,9 +4,11 @@
 // arithmetic (common.cuh "Lane order").
 //
 // One CTA per SM, 512 threads.
-//  * Weights are a pure stream: each CTA owns a contiguous row range of every matrix (lane-interleaved rows) and pulls it
-//    with TMA bulk copies (cp.async.bulk + mbarrier complete_tx) into a shared-memory ring several phases ahead of use,
-//    so HBM traffic never waits on the dependent math.
+//  * Weights are a pure stream: each CTA owns a contiguous row range of every matrix (lane-interleaved rows), each warp a
+//    fixed subset of those rows.  As soon as a warp finishes a phase it starts cp.async copies of its rows of the NEXT
+//    phase into a private shared-memory staging area, so HBM latency hides behind the exchange + LayerNorm of that phase
+//    and no block-wide barrier is needed around the weight stream.  (A TMA bulk-copy ring was measured first: the
+//    elected thread's expect_tx + UBLKCP issue cost 1.3 us per phase on the critical path.)
 //  * Activations cross CTAs as TAGGED words: every exchanged float travels in one 8-byte {value, epoch} store; consumers
 //    spin on the words they need until the epoch matches.  Data and "ready" flag arrive in the same L2 transaction, so a
 //    grid-wide dependency costs one store->load latency instead of store + fence + atomic + poll + load (a classic
@@ -29,38 +31,23 @@ namespace {
 
 constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
-constexpr int kSlots = 5;
-constexpr int kSlotBytes = 32 * 1024;
+constexpr int kWarpSlotBytes = 12 * 1024;       // per-warp staging area for the weight rows of one phase
 
 struct SmemLayout {
-    static constexpr int ring = 0;                                  // kSlots x 32 KB weight ring (bulk-copy destination)
-    static constexpr int act = ring + kSlots * kSlotBytes;          // two-plane LI activation operand, up to 4096 floats
+    static constexpr int wslot = 0;                                 // kWarps x 12 KB: each warp's weight rows of its next phase (cp.async)
+    static constexpr int act = wslot + kWarps * kWarpSlotBytes;     // two-plane LI activation operand, up to 4096 floats
     static constexpr int x = act + 4096 * 4;                        // residual stream, up to 1024 floats
     static constexpr int q = x + 1024 * 4;                          // q vector / probabilities row, up to 1024 floats
     static constexpr int part = q + 1024 * 4;                       // P.V lane partials [32][16] + chunk sums [128]
     static constexpr int red = part + (32 * 16 + 128) * 4;          // reduction scratch: 2 x 16 doubles + 4 broadcast slots
-    static constexpr int bar = red + (2 * kWarps + 4) * 8;          // kSlots mbarriers
-    static constexpr int total = bar + kSlots * 8;
+    static constexpr int sched = red + (2 * kWarps + 4) * 8;        // per-CTA row ranges: kMaxPhases x PhaseSched
+    static constexpr int total = sched + 128 * 32;
 };
 
 // ---- PTX helpers -------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void * p) { return (uint32_t) __cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void * src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void * src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // ---- tagged exchange -------------------------------------------------------------------------------------------------
 typedef unsigned long long tagged_t;                                // low 32 bits: float payload, high 32 bits: epoch
@@ -132,32 +119,41 @@ __device__ __noinline__ void block_layernorm(const float * xs, int E, const floa
     for (int i = threadIdx.x; i < E; i += kThreads) { const double v = (double) xs[i]; s += v; a += fabs(v); }
     s = block_sum_to_warp0(s, scratch);
     a = block_sum_to_warp0(a, scratch + kWarps);
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {
+        // lanes 0,1,2 divide s, s-d, s+d at the same time (a double division is a long dependent chain)
         const double d = slack * a;
-        float mean = __double2float_rn(__ddiv_rn(s, (double) E));
-        if (__double2float_rn(__ddiv_rn(s - d, (double) E)) != __double2float_rn(__ddiv_rn(s + d, (double) E))) {
+        const float qv = __double2float_rn(__ddiv_rn(threadIdx.x == 1 ? s - d : threadIdx.x == 2 ? s + d : s, (double) E));
+        float mean = __shfl_sync(0xffffffffu, qv, 0);
+        const bool ambiguous = __shfl_sync(0xffffffffu, qv, 1) != __shfl_sync(0xffffffffu, qv, 2);
+        if (threadIdx.x == 0) {
+        if (ambiguous) {
             double ss = 0.0;                                        // rare: replay the reference's sequential sum
             for (int i = 0; i < E; i++) ss = __dadd_rn(ss, (double) xs[i]);
             mean = __double2float_rn(__ddiv_rn(ss, (double) E));
             if (fallback_counter) atomicAdd(fallback_counter, 1u);
         }
         bc[0] = mean;
+        }
     }
     __syncthreads();
     const float mean = bc[0];
     double s2 = 0.0;
     for (int i = threadIdx.x; i < E; i += kThreads) { const float v = __fsub_rn(xs[i], mean); s2 += (double) __fmul_rn(v, v); }
     s2 = block_sum_to_warp0(s2, scratch);
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {
         const double d = slack * s2;
-        float variance = __double2float_rn(__ddiv_rn(s2, (double) E));
-        if (__double2float_rn(__ddiv_rn(s2 - d, (double) E)) != __double2float_rn(__ddiv_rn(s2 + d, (double) E))) {
+        const float qv = __double2float_rn(__ddiv_rn(threadIdx.x == 1 ? s2 - d : threadIdx.x == 2 ? s2 + d : s2, (double) E));
+        float variance = __shfl_sync(0xffffffffu, qv, 0);
+        const bool ambiguous = __shfl_sync(0xffffffffu, qv, 1) != __shfl_sync(0xffffffffu, qv, 2);
+        if (threadIdx.x == 0) {
+        if (ambiguous) {
             double ss = 0.0;
             for (int i = 0; i < E; i++) { const float v = __fsub_rn(xs[i], mean); ss = __dadd_rn(ss, (double) __fmul_rn(v, v)); }
             variance = __double2float_rn(__ddiv_rn(ss, (double) E));
             if (fallback_counter) atomicAdd(fallback_counter, 1u);
         }
         bc[1] = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(variance, 1e-5f)));
+        }
     }
     __syncthreads();
     const float scale = bc[1];
@@ -171,43 +167,10 @@ __device__ __noinline__ void block_layernorm(const float * xs, int E, const floa
 }
 
 // ---- weight stream --------------------------------------------------------------------------------------------------
-struct Cursor { int phase, sub; };                                  // position in this CTA's chunk sequence
-
-struct StreamCtx {
-    const DecodePhase * phases; int n_phases;
-    int lm_lo, lm_hi;                                               // row window of the last phase (lm_head)
-    int cta, n_cta;
-};
-
-// rows [r0, r1) of `phase` owned by this CTA: balanced split, every CTA gets floor or ceil of n / n_cta rows
-__device__ __forceinline__ void cta_rows(const StreamCtx & sc, int phase, int & r0, int & r1) {
-    const DecodePhase & p = sc.phases[phase];
-    int lo = 0, hi = p.n_out;
-    if (phase == sc.n_phases - 1) { lo = sc.lm_lo; hi = sc.lm_hi; }
-    const int n = hi - lo, base = n / sc.n_cta, rem = n % sc.n_cta;
-    r0 = lo + sc.cta * base + min(sc.cta, rem);
-    r1 = r0 + base + (sc.cta < rem ? 1 : 0);
-}
-__device__ __forceinline__ int rows_per_chunk(const DecodePhase & p) { return kSlotBytes / p.row_bytes; }
-__device__ __forceinline__ int phase_chunks(const StreamCtx & sc, int phase) {
-    int r0, r1; cta_rows(sc, phase, r0, r1);
-    const int rpc = rows_per_chunk(sc.phases[phase]);
-    return (r1 - r0 + rpc - 1) / rpc;
-}
-__device__ __forceinline__ bool cursor_valid(const StreamCtx & sc, Cursor & c) {
-    while (c.phase < sc.n_phases && c.sub >= phase_chunks(sc, c.phase)) { c.phase++; c.sub = 0; }
-    return c.phase < sc.n_phases;
-}
-__device__ __forceinline__ void issue_chunk(const StreamCtx & sc, const Cursor & c, unsigned char * ring, uint32_t bars, int slot) {
-    const DecodePhase & p = sc.phases[c.phase];
-    int r0, r1; cta_rows(sc, c.phase, r0, r1);
-    const int rpc = rows_per_chunk(p);
-    const int a = r0 + c.sub * rpc, b = min(r1, a + rpc);
-    const uint32_t bytes = (uint32_t)(b - a) * (uint32_t) p.row_bytes;
-    const uint32_t bar = bars + slot * 8;
-    mbar_expect_tx(bar, bytes);
-    tma_bulk_g2s(smem_u32(ring + (size_t) slot * kSlotBytes), (const unsigned char *) p.w + (size_t) a * p.row_bytes, bytes, bar);
-}
+// Per-CTA row ranges of every phase, built once per launch in shared memory (the divisions and table look-ups they replace
+// cost ~2 us of single-thread time per phase when done on the fly).
+constexpr int kMaxPhases = 128;
+struct PhaseSched { int r0, r1, K, row_bytes; const unsigned char * w; int pad[2]; };   // rows [r0, r1) of this phase belong to this CTA
 
 enum { EP_QKV = 0, EP_RESID = 1, EP_GELU = 2, EP_LOGITS = 3 };
 
@@ -267,57 +230,70 @@ __device__ __forceinline__ float row_dot(const unsigned char * row, const float 
 
 constexpr int kMaxTasks = 6;        // (h, k) score tasks per warp: H * block_size / (n_cta * kWarps) <= 16 * 1024 / (132 * 16) < 8
 
-// everything run_phase needs; lives in registers/local memory of the kernel and is passed by reference
+// everything run_phase needs; lives in local memory of the kernel and is passed by reference
 struct PhaseCtx {
-    StreamCtx sc;
-    Cursor prod;                     // next chunk to request (thread 0)
-    int cons_n;                      // chunks consumed so far
-    unsigned char * ring; uint32_t bars;
+    const PhaseSched * sched; int n_phases;
+    unsigned char * wslot;           // this warp's staging area
+    int staged_phase;                // phase whose rows currently sit (or are landing) in wslot, -1 if none
     const float * act; const float * xs;
     tagged_t * gq, * gk, * gv, * gx, * gff;
     float * mem_k, * mem_v, * logits;
     const __half * gelu_tab;
     int E, ctx, n_past;
+    unsigned long long * timing;     // debug stamps (CTA 0, thread 0)
 };
 
-// consume every weight chunk of `phase` that belongs to this CTA: one warp per row, lane-order dot against the shared
-// activation operand; outputs are published with epoch `otag` (or stored, for the logits)
+// Start copying this warp's rows of `phase` (rows r0 + warp, r0 + warp + 16, ...) into its staging area with per-lane 16-byte
+// cp.async: the lane-interleaved layout makes every instruction one coalesced 512-byte segment.  Returns immediately.
+__device__ __forceinline__ void stage_rows(PhaseCtx & pc, int phase) {
+    pc.staged_phase = -1;
+    if (phase >= pc.n_phases) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const PhaseSched p = pc.sched[phase];
+    const int nrows = (p.r1 - p.r0 - warp + kWarps - 1) / kWarps;                 // rows of this warp (may be <= 0)
+    if (nrows <= 0) { pc.staged_phase = phase; return; }
+    if (nrows * p.row_bytes > kWarpSlotBytes) return;                             // does not fit: run_phase reads global memory directly
+    const uint32_t dst0 = smem_u32(pc.wslot) + lane * 16;
+    const int vec_per_row = p.row_bytes >> 9;                                      // 512-byte segments per row
+    for (int j = 0; j < nrows; j++) {
+        const unsigned char * src = p.w + (size_t)(p.r0 + warp + j * kWarps) * p.row_bytes + lane * 16;
+        for (int g = 0; g < vec_per_row; g++) cp_async16(dst0 + j * p.row_bytes + g * 512, src + g * 512);
+    }
+    pc.staged_phase = phase;
+}
+
+// This warp's rows of `phase`: lane-order dot against the shared activation operand; outputs are published with epoch
+// `otag` (or stored, for the logits).  Then the rows of the next phase start streaming in.  No block-wide synchronisation.
 template <typename WT>
 __device__ __noinline__ void run_phase(PhaseCtx & pc, int phase, int ep, int layer, uint32_t otag) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const DecodePhase & p = pc.sc.phases[phase];
-    int r0, r1; cta_rows(pc.sc, phase, r0, r1);
-    const int rpc = rows_per_chunk(p);
-    const int nch = (r1 - r0 + rpc - 1) / rpc;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const PhaseSched p = pc.sched[phase];
     const int E = pc.E;
-    for (int sub = 0; sub < nch; sub++) {
-        const int slot = pc.cons_n % kSlots;
-        mbar_wait(pc.bars + slot * 8, (uint32_t)((pc.cons_n / kSlots) & 1));
-        const int a = r0 + sub * rpc, b = min(r1, a + rpc);
-        const unsigned char * base = pc.ring + (size_t) slot * kSlotBytes;
-        for (int r = a + warp; r < b; r += kWarps) {
-            const float v = row_dot<WT>(base + (size_t)(r - a) * p.row_bytes, pc.act, p.K, lane);
-            if (lane == 0) {
-                if (ep == EP_QKV) {
-                    const size_t slot_off = ((size_t) layer * pc.ctx + pc.n_past) * E;
-                    if (r < E) publish(pc.gq + r, v, otag);
-                    else if (r < 2 * E) { publish(pc.gk + (r - E), v, otag); pc.mem_k[slot_off + (r - E)] = v; }
-                    else                { publish(pc.gv + (r - 2 * E), v, otag); pc.mem_v[slot_off + (r - 2 * E)] = v; }
-                } else if (ep == EP_RESID) {
-                    publish(pc.gx + r, __fadd_rn(v, pc.xs[r]), otag);
-                } else if (ep == EP_GELU) {
-                    float gl;
-                    if (v <= -10.0f) gl = 0.0f; else if (v >= 10.0f) gl = v; else gl = __half2float(pc.gelu_tab[__half_as_ushort(__float2half_rn(v))]);
-                    publish(pc.gff + r, gl, otag);
-                } else {
-                    pc.logits[r] = v;
-                }
+    const bool staged = pc.staged_phase == phase;
+    if (staged) { cp_async_wait_all(); __syncwarp(); }
+    int j = 0;
+    for (int r = p.r0 + warp; r < p.r1; r += kWarps, j++) {
+        const unsigned char * row = staged ? pc.wslot + (size_t) j * p.row_bytes : p.w + (size_t) r * p.row_bytes;
+        const float v = row_dot<WT>(row, pc.act, p.K, lane);
+        if (lane == 0) {
+            if (ep == EP_QKV) {
+                const size_t slot_off = ((size_t) layer * pc.ctx + pc.n_past) * E;
+                if (r < E) publish(pc.gq + r, v, otag);
+                else if (r < 2 * E) { publish(pc.gk + (r - E), v, otag); pc.mem_k[slot_off + (r - E)] = v; }
+                else                { publish(pc.gv + (r - 2 * E), v, otag); pc.mem_v[slot_off + (r - 2 * E)] = v; }
+            } else if (ep == EP_RESID) {
+                publish(pc.gx + r, __fadd_rn(v, pc.xs[r]), otag);
+            } else if (ep == EP_GELU) {
+                float gl;
+                if (v <= -10.0f) gl = 0.0f; else if (v >= 10.0f) gl = v; else gl = __half2float(pc.gelu_tab[__half_as_ushort(__float2half_rn(v))]);
+                publish(pc.gff + r, gl, otag);
+            } else {
+                pc.logits[r] = v;
             }
         }
-        pc.cons_n++;
-        __syncthreads();                                  // everyone is done reading this slot
-        if (tid == 0 && cursor_valid(pc.sc, pc.prod)) { issue_chunk(pc.sc, pc.prod, pc.ring, pc.bars, slot); pc.prod.sub++; }
     }
+    __syncwarp();                                             // all lanes are done reading the staging area
+    stage_rows(pc, phase + 1);
 }
 
 }  // namespace
@@ -339,23 +315,29 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
     tagged_t * const gq = (tagged_t *) A.gq, * const gk = (tagged_t *) A.gk, * const gv = (tagged_t *) A.gv, * const gatt = (tagged_t *) A.gatt,
              * const gx = (tagged_t *) A.gx, * const gff = (tagged_t *) A.gff, * const gscores = (tagged_t *) A.gscores;
 
+    // ---- per-CTA row ranges in shared memory ----
+    PhaseSched * sched = reinterpret_cast<PhaseSched *>(smem + SmemLayout::sched);
+    const int n_phases = 4 * L + 1;
+    if (tid < n_phases) {
+        const DecodePhase ph = A.phases[tid];
+        int lo = 0, hi = ph.n_out;
+        if (tid == n_phases - 1) { lo = A.lm_lo; hi = A.lm_hi; }
+        const int n = hi - lo, G = gridDim.x, base = n / G, rem = n % G, cta = blockIdx.x;
+        PhaseSched e;
+        e.r0 = lo + cta * base + min(cta, rem); e.r1 = e.r0 + base + (cta < rem ? 1 : 0);      // balanced split: floor or ceil of n / G rows
+        e.K = ph.K; e.row_bytes = ph.row_bytes; e.w = (const unsigned char *) ph.w; e.pad[0] = e.pad[1] = 0;
+        sched[tid] = e;
+    }
+    __syncthreads();
+
     PhaseCtx pc;
-    pc.sc = StreamCtx{A.phases, 4 * L + 1, A.lm_lo, A.lm_hi, (int) blockIdx.x, (int) gridDim.x};
-    pc.prod = Cursor{0, 0}; pc.cons_n = 0;
-    pc.ring = smem + SmemLayout::ring; pc.bars = smem_u32(smem + SmemLayout::bar);
+    pc.sched = sched; pc.n_phases = n_phases;
+    pc.wslot = smem + SmemLayout::wslot + (size_t) warp * kWarpSlotBytes; pc.staged_phase = -1;
     pc.act = act; pc.xs = xs;
     pc.gq = gq; pc.gk = gk; pc.gv = gv; pc.gx = gx; pc.gff = gff;
     pc.mem_k = A.mem_k; pc.mem_v = A.mem_v; pc.logits = A.logits; pc.gelu_tab = A.gelu_tab;
-    pc.E = E; pc.ctx = ctx; pc.n_past = n_past;
-
-    if (tid == 0) {
-        for (int s = 0; s < kSlots; s++) mbar_init(pc.bars + s * 8, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (tid == 0) {
-        for (int s = 0; s < kSlots && cursor_valid(pc.sc, pc.prod); s++) { issue_chunk(pc.sc, pc.prod, pc.ring, pc.bars, s); pc.prod.sub++; }
-    }
+    pc.E = E; pc.ctx = ctx; pc.n_past = n_past; pc.timing = A.timing;
+    stage_rows(pc, 0);
 
     // embedding of the one new token (bark.cpp:1226-1228, 1259): every CTA keeps its own copy of the residual stream
     for (int i = tid; i < E; i += kThreads) {
@@ -542,6 +524,7 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
         stamp(il, 7);
         block_layernorm<kRound>(xs, E, lv.ln_2_g, lv.ln_2_b, act, red, bc, A.ln_fallbacks);
         run_phase<WT>(pc, 4 * il + 2, EP_GELU, il, t_ff);
+        __syncthreads();                                         // the ff vector lands in `act`, which slower warps may still be reading
         stamp(il, 8);
 
         // ---- P6: mlp/c_proj + residual ----
