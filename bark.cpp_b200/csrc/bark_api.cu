@@ -343,7 +343,7 @@ extern "C" struct bark_context * bark_load_model(const char * model_path, struct
         return nullptr;
     }
     alloc_workspace(ctx);
-    if (getenv("BARK_B200_DECODE_TIMING")) { ctx->d_timing = (unsigned long long *) ctx_alloc(ctx, 64 * 16 * 8); BARK_CUDA_CHECK(cudaMemset(ctx->d_timing, 0, 64 * 16 * 8)); }
+    if (getenv("BARK_B200_DECODE_TIMING")) { ctx->d_timing = (unsigned long long *) ctx_alloc(ctx, 256 * 16 * 8); BARK_CUDA_CHECK(cudaMemset(ctx->d_timing, 0, 256 * 16 * 8)); }
     BARK_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     ctx->rng = std::mt19937(seed);
     ctx->stats.t_load_us = now_us() - t0;
@@ -489,7 +489,7 @@ extern "C" unsigned bark_b200_layernorm_fallbacks(struct bark_context * ctx) {
 }
 extern "C" int bark_b200_decode_timing(struct bark_context * ctx, unsigned long long * out, int n) {
     if (!ctx || !ctx->d_timing || !out) return 0;
-    BARK_CUDA_CHECK(cudaMemcpy(out, ctx->d_timing, sizeof(unsigned long long) * (size_t) std::min(n, 64 * 16), cudaMemcpyDeviceToHost));
-    return std::min(n, 64 * 16);
+    BARK_CUDA_CHECK(cudaMemcpy(out, ctx->d_timing, sizeof(unsigned long long) * (size_t) std::min(n, 256 * 16), cudaMemcpyDeviceToHost));
+    return std::min(n, 256 * 16);
 }
 extern "C" const char * bark_b200_version(void) { return "bark_b200 r1 (sm_100a, parity path)"; }

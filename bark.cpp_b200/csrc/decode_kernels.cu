@@ -31,7 +31,8 @@ namespace {
 
 constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
-constexpr int kWarpSlotBytes = 12 * 1024;       // per-warp staging area for the weight rows of one phase
+constexpr int kWarpSlotBytes = 12 * 1024;       // per-warp staging area: two halves, phases alternate (rows are fetched two phases ahead)
+constexpr int kHalfSlotBytes = kWarpSlotBytes / 2;
 
 struct SmemLayout {
     static constexpr int wslot = 0;                                 // kWarps x 12 KB: each warp's weight rows of its next phase (cp.async)
@@ -47,7 +48,8 @@ struct SmemLayout {
 // ---- PTX helpers -------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void * p) { return (uint32_t) __cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void * src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all_but_newest() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
 // ---- tagged exchange -------------------------------------------------------------------------------------------------
 typedef unsigned long long tagged_t;                                // low 32 bits: float payload, high 32 bits: epoch
@@ -62,7 +64,7 @@ __device__ __forceinline__ tagged_t peek(const tagged_t * p) {
 }
 __device__ __forceinline__ float consume1(const tagged_t * p, uint32_t tag) {
     tagged_t w = peek(p);
-    while ((uint32_t)(w >> 32) != tag) w = peek(p);
+    while ((uint32_t)(w >> 32) != tag) { __nanosleep(40); w = peek(p); }       // back off: thousands of pollers share a few L2 lines
     return __uint_as_float((uint32_t) w);
 }
 // two-plane LI index of column k in the shared activation operand: LDS.128 of one plane is contiguous across lanes
@@ -84,7 +86,7 @@ __device__ __noinline__ void consume_to_smem(const tagged_t * g, int n, uint32_t
     for (int j = 0; j < MAXJ; j++) {
         const int i = threadIdx.x + j * kThreads;
         if (i < n) {
-            while ((uint32_t)(w[j] >> 32) != tag) w[j] = peek(g + i);
+            while ((uint32_t)(w[j] >> 32) != tag) { __nanosleep(40); w[j] = peek(g + i); }
             const float v = __uint_as_float((uint32_t) w[j]);
             if (mode == SINK_PLAIN) dst[i] = v; else dst[act_index(i)] = mode == SINK_ACT_R16 ? round_f16(v) : v;
         }
@@ -92,71 +94,54 @@ __device__ __noinline__ void consume_to_smem(const tagged_t * g, int n, uint32_t
     __syncthreads();
 }
 
-// Block-wide sum of doubles with few FP64 instructions: warp shuffles, one partial per warp, warp 0 folds them.
-// Returns the total in warp 0 (all its lanes); other warps get 0.  Contains one __syncthreads.
-__device__ __forceinline__ double block_sum_to_warp0(double v, double * scratch) {
+__device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
-    __syncthreads();
-    double s = 0.0;
-    if (threadIdx.x < 32) {
-        s = threadIdx.x < kWarps ? scratch[threadIdx.x] : 0.0;
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        s = __shfl_sync(0xffffffffu, s, 0);
-    }
-    return s;
+    return v;
 }
 
 // LayerNorm of xs[0..E) (ggml.c:11964-12013; order-independence argument in layernorm_act_kernel, gpt_kernels.cu) ->
-// activation operand (optionally f16-rounded) in two-plane LI order.  `bc` = broadcast slots in shared memory.
+// activation operand (optionally f16-rounded) in two-plane LI order.
+// Every WARP redundantly reduces the whole row (24-32 elements per lane, shuffles only), so all 16 warps hold identical
+// mean / scale without a single block barrier; each warp then writes its own slice of the operand.  One barrier at the end.
 template <bool ROUND16>
-__device__ __noinline__ void block_layernorm(const float * xs, int E, const float * __restrict__ g, const float * __restrict__ b, float * act, double * scratch,
-                                float * bc, unsigned * fallback_counter) {
+__device__ __noinline__ void block_layernorm(const float * xs, int E, const float * __restrict__ g, const float * __restrict__ b, float * act,
+                                             unsigned * fallback_counter) {
+    const int lane = threadIdx.x & 31;
     const double slack = 2.0 * (double) E * 0x1p-53 * (1.0 + 1e-6);
     double s = 0.0, a = 0.0;
-    for (int i = threadIdx.x; i < E; i += kThreads) { const double v = (double) xs[i]; s += v; a += fabs(v); }
-    s = block_sum_to_warp0(s, scratch);
-    a = block_sum_to_warp0(a, scratch + kWarps);
-    if (threadIdx.x < 32) {
-        // lanes 0,1,2 divide s, s-d, s+d at the same time (a double division is a long dependent chain)
+#pragma unroll 4
+    for (int i = lane; i < E; i += 32) { const double v = (double) xs[i]; s += v; a += fabs(v); }
+    s = warp_sum_d(s); a = warp_sum_d(a);
+    float mean;
+    {   // lanes 0,1,2 divide s, s-d, s+d at the same time (a double division is a long dependent chain)
         const double d = slack * a;
-        const float qv = __double2float_rn(__ddiv_rn(threadIdx.x == 1 ? s - d : threadIdx.x == 2 ? s + d : s, (double) E));
-        float mean = __shfl_sync(0xffffffffu, qv, 0);
-        const bool ambiguous = __shfl_sync(0xffffffffu, qv, 1) != __shfl_sync(0xffffffffu, qv, 2);
-        if (threadIdx.x == 0) {
-        if (ambiguous) {
-            double ss = 0.0;                                        // rare: replay the reference's sequential sum
+        const float qv = __double2float_rn(__ddiv_rn(lane == 1 ? s - d : lane == 2 ? s + d : s, (double) E));
+        mean = __shfl_sync(0xffffffffu, qv, 0);
+        if (__shfl_sync(0xffffffffu, qv, 1) != __shfl_sync(0xffffffffu, qv, 2)) {      // rare: replay the reference's sequential sum
+            double ss = 0.0;
             for (int i = 0; i < E; i++) ss = __dadd_rn(ss, (double) xs[i]);
             mean = __double2float_rn(__ddiv_rn(ss, (double) E));
-            if (fallback_counter) atomicAdd(fallback_counter, 1u);
-        }
-        bc[0] = mean;
+            if (threadIdx.x == 0 && fallback_counter) atomicAdd(fallback_counter, 1u);
         }
     }
-    __syncthreads();
-    const float mean = bc[0];
     double s2 = 0.0;
-    for (int i = threadIdx.x; i < E; i += kThreads) { const float v = __fsub_rn(xs[i], mean); s2 += (double) __fmul_rn(v, v); }
-    s2 = block_sum_to_warp0(s2, scratch);
-    if (threadIdx.x < 32) {
+#pragma unroll 4
+    for (int i = lane; i < E; i += 32) { const float v = __fsub_rn(xs[i], mean); s2 += (double) __fmul_rn(v, v); }
+    s2 = warp_sum_d(s2);
+    float variance;
+    {
         const double d = slack * s2;
-        const float qv = __double2float_rn(__ddiv_rn(threadIdx.x == 1 ? s2 - d : threadIdx.x == 2 ? s2 + d : s2, (double) E));
-        float variance = __shfl_sync(0xffffffffu, qv, 0);
-        const bool ambiguous = __shfl_sync(0xffffffffu, qv, 1) != __shfl_sync(0xffffffffu, qv, 2);
-        if (threadIdx.x == 0) {
-        if (ambiguous) {
+        const float qv = __double2float_rn(__ddiv_rn(lane == 1 ? s2 - d : lane == 2 ? s2 + d : s2, (double) E));
+        variance = __shfl_sync(0xffffffffu, qv, 0);
+        if (__shfl_sync(0xffffffffu, qv, 1) != __shfl_sync(0xffffffffu, qv, 2)) {
             double ss = 0.0;
             for (int i = 0; i < E; i++) { const float v = __fsub_rn(xs[i], mean); ss = __dadd_rn(ss, (double) __fmul_rn(v, v)); }
             variance = __double2float_rn(__ddiv_rn(ss, (double) E));
-            if (fallback_counter) atomicAdd(fallback_counter, 1u);
-        }
-        bc[1] = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(variance, 1e-5f)));
+            if (threadIdx.x == 0 && fallback_counter) atomicAdd(fallback_counter, 1u);
         }
     }
-    __syncthreads();
-    const float scale = bc[1];
+    const float scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(variance, 1e-5f)));
     for (int i = threadIdx.x; i < E; i += kThreads) {
         float y = __fmul_rn(__fsub_rn(xs[i], mean), scale);
         y = __fmul_rn(y, g[i]);
@@ -166,7 +151,6 @@ __device__ __noinline__ void block_layernorm(const float * xs, int E, const floa
     __syncthreads();
 }
 
-// ---- weight stream --------------------------------------------------------------------------------------------------
 // Per-CTA row ranges of every phase, built once per launch in shared memory (the divisions and table look-ups they replace
 // cost ~2 us of single-thread time per phase when done on the fly).
 constexpr int kMaxPhases = 128;
@@ -234,7 +218,7 @@ constexpr int kMaxTasks = 6;        // (h, k) score tasks per warp: H * block_si
 struct PhaseCtx {
     const PhaseSched * sched; int n_phases;
     unsigned char * wslot;           // this warp's staging area
-    int staged_phase;                // phase whose rows currently sit (or are landing) in wslot, -1 if none
+    int staged_mask;                 // bit h: half h of wslot holds (or is receiving) the rows of the phase with parity h
     const float * act; const float * xs;
     tagged_t * gq, * gk, * gv, * gx, * gff;
     float * mem_k, * mem_v, * logits;
@@ -243,23 +227,28 @@ struct PhaseCtx {
     unsigned long long * timing;     // debug stamps (CTA 0, thread 0)
 };
 
-// Start copying this warp's rows of `phase` (rows r0 + warp, r0 + warp + 16, ...) into its staging area with per-lane 16-byte
-// cp.async: the lane-interleaved layout makes every instruction one coalesced 512-byte segment.  Returns immediately.
+// Start copying this warp's rows of `phase` (rows r0 + warp, r0 + warp + 16, ...) into half (phase & 1) of its staging area
+// with per-lane 16-byte cp.async: the lane-interleaved layout makes every instruction one coalesced 512-byte segment.
+// Always commits exactly one cp.async group (possibly empty) so that run_phase can wait for "all but the newest".
+// Returns immediately; bit (phase & 1) of pc.staged_mask says whether the rows will be in shared memory.
 __device__ __forceinline__ void stage_rows(PhaseCtx & pc, int phase) {
-    pc.staged_phase = -1;
-    if (phase >= pc.n_phases) return;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const PhaseSched p = pc.sched[phase];
-    const int nrows = (p.r1 - p.r0 - warp + kWarps - 1) / kWarps;                 // rows of this warp (may be <= 0)
-    if (nrows <= 0) { pc.staged_phase = phase; return; }
-    if (nrows * p.row_bytes > kWarpSlotBytes) return;                             // does not fit: run_phase reads global memory directly
-    const uint32_t dst0 = smem_u32(pc.wslot) + lane * 16;
-    const int vec_per_row = p.row_bytes >> 9;                                      // 512-byte segments per row
-    for (int j = 0; j < nrows; j++) {
-        const unsigned char * src = p.w + (size_t)(p.r0 + warp + j * kWarps) * p.row_bytes + lane * 16;
-        for (int g = 0; g < vec_per_row; g++) cp_async16(dst0 + j * p.row_bytes + g * 512, src + g * 512);
+    const int half = phase & 1;
+    pc.staged_mask &= ~(1 << half);
+    if (phase < pc.n_phases) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const PhaseSched p = pc.sched[phase];
+        const int nrows = (p.r1 - p.r0 - warp + kWarps - 1) / kWarps;             // rows of this warp (may be <= 0)
+        if (nrows > 0 && nrows * p.row_bytes <= kHalfSlotBytes) {                 // else run_phase reads global memory directly
+            const uint32_t dst0 = smem_u32(pc.wslot) + half * kHalfSlotBytes + lane * 16;
+            const int vec_per_row = p.row_bytes >> 9;                              // 512-byte segments per row
+            for (int j = 0; j < nrows; j++) {
+                const unsigned char * src = p.w + (size_t)(p.r0 + warp + j * kWarps) * p.row_bytes + lane * 16;
+                for (int g = 0; g < vec_per_row; g++) cp_async16(dst0 + j * p.row_bytes + g * 512, src + g * 512);
+            }
+            pc.staged_mask |= 1 << half;
+        }
     }
-    pc.staged_phase = phase;
+    cp_async_commit();
 }
 
 // This warp's rows of `phase`: lane-order dot against the shared activation operand; outputs are published with epoch
@@ -269,11 +258,13 @@ __device__ __noinline__ void run_phase(PhaseCtx & pc, int phase, int ep, int lay
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const PhaseSched p = pc.sched[phase];
     const int E = pc.E;
-    const bool staged = pc.staged_phase == phase;
-    if (staged) { cp_async_wait_all(); __syncwarp(); }
+    const int half = phase & 1;
+    const bool staged = (pc.staged_mask >> half) & 1;
+    cp_async_wait_all_but_newest();                           // the group of `phase` is complete; `phase + 1` may still be in flight
+    __syncwarp();
     int j = 0;
     for (int r = p.r0 + warp; r < p.r1; r += kWarps, j++) {
-        const unsigned char * row = staged ? pc.wslot + (size_t) j * p.row_bytes : p.w + (size_t) r * p.row_bytes;
+        const unsigned char * row = staged ? pc.wslot + half * kHalfSlotBytes + (size_t) j * p.row_bytes : p.w + (size_t) r * p.row_bytes;
         const float v = row_dot<WT>(row, pc.act, p.K, lane);
         if (lane == 0) {
             if (ep == EP_QKV) {
@@ -292,8 +283,8 @@ __device__ __noinline__ void run_phase(PhaseCtx & pc, int phase, int ep, int lay
             }
         }
     }
-    __syncwarp();                                             // all lanes are done reading the staging area
-    stage_rows(pc, phase + 1);
+    __syncwarp();                                             // all lanes are done reading this half
+    stage_rows(pc, phase + 2);
 }
 
 }  // namespace
@@ -332,12 +323,13 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
 
     PhaseCtx pc;
     pc.sched = sched; pc.n_phases = n_phases;
-    pc.wslot = smem + SmemLayout::wslot + (size_t) warp * kWarpSlotBytes; pc.staged_phase = -1;
+    pc.wslot = smem + SmemLayout::wslot + (size_t) warp * kWarpSlotBytes; pc.staged_mask = 0;
     pc.act = act; pc.xs = xs;
     pc.gq = gq; pc.gk = gk; pc.gv = gv; pc.gx = gx; pc.gff = gff;
     pc.mem_k = A.mem_k; pc.mem_v = A.mem_v; pc.logits = A.logits; pc.gelu_tab = A.gelu_tab;
     pc.E = E; pc.ctx = ctx; pc.n_past = n_past; pc.timing = A.timing;
     stage_rows(pc, 0);
+    stage_rows(pc, 1);
 
     // embedding of the one new token (bark.cpp:1226-1228, 1259): every CTA keeps its own copy of the residual stream
     for (int i = tid; i < E; i += kThreads) {
@@ -349,7 +341,11 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
     uint32_t tag = A.tag_base;                               // unique epoch per exchange; the host advances the base by 6 * L per launch
     const float scale = 1.0f / sqrtf((float) E / (float) H);
     auto stamp = [&](int layer, int i) {
-        if (A.timing && blockIdx.x == 0 && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); A.timing[layer * 16 + i] = t; }
+        if (A.timing && tid == 0 && (blockIdx.x == 0 || layer == 5)) {      // CTA 0: every layer; all CTAs: layer 5 (rows 64.. of the buffer)
+            unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (blockIdx.x == 0) A.timing[layer * 16 + i] = t;
+            if (layer == 5) A.timing[(64 + blockIdx.x) * 16 + i] = t;
+        }
     };
 
     const int parts = D >> 4;                                // P3: CTAs per head
@@ -364,7 +360,7 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
         tag += 6;
         stamp(il, 12);
         // ---- P1: LN1 -> QKV ----
-        block_layernorm<kRound>(xs, E, lv.ln_1_g, lv.ln_1_b, act, red, bc, A.ln_fallbacks);
+        block_layernorm<kRound>(xs, E, lv.ln_1_g, lv.ln_1_b, act, A.ln_fallbacks);
         run_phase<WT>(pc, 4 * il + 0, EP_QKV, il, t_qkv);
         stamp(il, 0);
 
@@ -522,7 +518,7 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
         // ---- P5: LN2 -> c_fc -> GELU ----
         consume_to_smem<2>(gx, E, t_x1, xs, SINK_PLAIN);
         stamp(il, 7);
-        block_layernorm<kRound>(xs, E, lv.ln_2_g, lv.ln_2_b, act, red, bc, A.ln_fallbacks);
+        block_layernorm<kRound>(xs, E, lv.ln_2_g, lv.ln_2_b, act, A.ln_fallbacks);
         run_phase<WT>(pc, 4 * il + 2, EP_GELU, il, t_ff);
         __syncthreads();                                         // the ff vector lands in `act`, which slower warps may still be reading
         stamp(il, 8);
@@ -537,7 +533,7 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
         stamp(il, 11);
     }
     // ---- final norm + lm_head window ----
-    block_layernorm<kRound>(xs, E, A.ln_f_g, A.ln_f_b, act, red, bc, A.ln_fallbacks);
+    block_layernorm<kRound>(xs, E, A.ln_f_g, A.ln_f_b, act, A.ln_fallbacks);
     run_phase<WT>(pc, 4 * L, EP_LOGITS, 0, 0);
 }
 
