@@ -334,6 +334,7 @@ extern "C" struct bark_context * bark_load_model(const char * model_path, struct
     bark_context * ctx = new bark_context();
     ctx->device = dev;
     ctx->n_sm = prop.multiProcessorCount;
+    { const char * e = getenv("BARK_B200_DECODE_CTAS"); if (e && atoi(e) >= 64 && atoi(e) <= ctx->n_sm) ctx->n_sm = atoi(e); }   // experiment knob: CTAs of the persistent decode kernel
     { const char * e = getenv("BARK_B200_DECODE"); ctx->use_decode_kernel = !(e && !strcmp(e, "multi")); }   // "multi": one kernel per op (debug / A-B)
     ctx->params = params;
     BARK_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));

@@ -94,60 +94,89 @@ __device__ __noinline__ void consume_to_smem(const tagged_t * g, int n, uint32_t
     __syncthreads();
 }
 
-__device__ __forceinline__ double warp_sum_d(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
+// FP64 is scarce on this part (a double division is ~2400 cycles of dependent latency — measured: it dominated the whole
+// LayerNorm), so the kernel never divides in double on the common path.  It only has to decide which FLOAT the
+// reference's (float)(sum / n) is: with c = sum * (1/n) and a rigorous half-width w covering both the summation-order
+// uncertainty and the error of the multiply-by-reciprocal, both ends of [c - w, c + w] rounding to the same float
+// settles it; the exact (slow) path runs otherwise.
+
+// reciprocal of a positive double to ~2^-50 relative error: float seed + 2 Newton steps (4 DFMA)
+__device__ __forceinline__ double approx_rcp(double x) {
+    double y = (double) __frcp_rn((float) x);
+    double e = __fma_rn(-x, y, 1.0); y = __fma_rn(y, e, y);
+    e = __fma_rn(-x, y, 1.0);        y = __fma_rn(y, e, y);
+    return y;
 }
 
 // LayerNorm of xs[0..E) (ggml.c:11964-12013; order-independence argument in layernorm_act_kernel, gpt_kernels.cu) ->
-// activation operand (optionally f16-rounded) in two-plane LI order.
-// Every WARP redundantly reduces the whole row (24-32 elements per lane, shuffles only), so all 16 warps hold identical
-// mean / scale without a single block barrier; each warp then writes its own slice of the operand.  One barrier at the end.
+// activation operand (optionally f16-rounded) in two-plane LI order.  Block-wide: each thread owns <= 2 elements.
 template <bool ROUND16>
-__device__ __noinline__ void block_layernorm(const float * xs, int E, const float * __restrict__ g, const float * __restrict__ b, float * act,
-                                             unsigned * fallback_counter) {
-    const int lane = threadIdx.x & 31;
+__device__ __noinline__ void block_layernorm(const float * xs, int E, double inv_E, const float * __restrict__ g, const float * __restrict__ b, float * act,
+                                             double * scratch, float * bc, unsigned * fallback_counter) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float * fscratch = reinterpret_cast<float *>(scratch + kWarps);
+    const int i0 = tid, i1 = tid + kThreads;
+    const bool h0 = i0 < E, h1 = i1 < E;
+    // gains / biases are different vectors every layer (L2 or HBM latency): fetch them now, use them at the end
+    const float g0 = h0 ? __ldg(g + i0) : 0.f, g1 = h1 ? __ldg(g + i1) : 0.f;
+    const float b0 = (b && h0) ? __ldg(b + i0) : 0.f, b1 = (b && h1) ? __ldg(b + i1) : 0.f;
+    const float x0 = h0 ? xs[i0] : 0.f, x1 = h1 ? xs[i1] : 0.f;
     const double slack = 2.0 * (double) E * 0x1p-53 * (1.0 + 1e-6);
-    double s = 0.0, a = 0.0;
-#pragma unroll 4
-    for (int i = lane; i < E; i += 32) { const double v = (double) xs[i]; s += v; a += fabs(v); }
-    s = warp_sum_d(s); a = warp_sum_d(a);
-    float mean;
-    {   // lanes 0,1,2 divide s, s-d, s+d at the same time (a double division is a long dependent chain)
-        const double d = slack * a;
-        const float qv = __double2float_rn(__ddiv_rn(lane == 1 ? s - d : lane == 2 ? s + d : s, (double) E));
-        mean = __shfl_sync(0xffffffffu, qv, 0);
-        if (__shfl_sync(0xffffffffu, qv, 1) != __shfl_sync(0xffffffffu, qv, 2)) {      // rare: replay the reference's sequential sum
-            double ss = 0.0;
-            for (int i = 0; i < E; i++) ss = __dadd_rn(ss, (double) xs[i]);
-            mean = __double2float_rn(__ddiv_rn(ss, (double) E));
-            if (threadIdx.x == 0 && fallback_counter) atomicAdd(fallback_counter, 1u);
+
+    // ---- mean ----
+    double s = (double) x0 + (double) x1;
+    float a = fabsf(x0) + fabsf(x1);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); a += __shfl_xor_sync(0xffffffffu, a, o); }
+    if (lane == 0) { scratch[warp] = s; fscratch[warp] = a; }
+    __syncthreads();
+    if (warp == 0) {
+        s = lane < kWarps ? scratch[lane] : 0.0; a = lane < kWarps ? fscratch[lane] : 0.f;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); a += __shfl_xor_sync(0xffffffffu, a, o); }
+        if (lane == 0) {
+            const double c = s * inv_E;
+            const double w = (slack * (double) a * 1.001) * inv_E + fabs(c) * 0x1p-50;      // 1.001: the float abs-sum may be low by n*2^-24
+            float mean = __double2float_rn(c - w);
+            if (mean != __double2float_rn(c + w)) {                                         // rare: replay the reference's sequential sum
+                double ss = 0.0;
+                for (int i = 0; i < E; i++) ss = __dadd_rn(ss, (double) xs[i]);
+                mean = __double2float_rn(__ddiv_rn(ss, (double) E));
+                if (fallback_counter) atomicAdd(fallback_counter, 1u);
+            }
+            bc[0] = mean;
         }
     }
-    double s2 = 0.0;
-#pragma unroll 4
-    for (int i = lane; i < E; i += 32) { const float v = __fsub_rn(xs[i], mean); s2 += (double) __fmul_rn(v, v); }
-    s2 = warp_sum_d(s2);
-    float variance;
-    {
-        const double d = slack * s2;
-        const float qv = __double2float_rn(__ddiv_rn(lane == 1 ? s2 - d : lane == 2 ? s2 + d : s2, (double) E));
-        variance = __shfl_sync(0xffffffffu, qv, 0);
-        if (__shfl_sync(0xffffffffu, qv, 1) != __shfl_sync(0xffffffffu, qv, 2)) {
-            double ss = 0.0;
-            for (int i = 0; i < E; i++) { const float v = __fsub_rn(xs[i], mean); ss = __dadd_rn(ss, (double) __fmul_rn(v, v)); }
-            variance = __double2float_rn(__ddiv_rn(ss, (double) E));
-            if (threadIdx.x == 0 && fallback_counter) atomicAdd(fallback_counter, 1u);
+    __syncthreads();
+    const float mean = bc[0];
+    // ---- variance ----
+    const float v0 = __fsub_rn(x0, mean), v1 = __fsub_rn(x1, mean);
+    double s2 = (h0 ? (double) __fmul_rn(v0, v0) : 0.0) + (h1 ? (double) __fmul_rn(v1, v1) : 0.0);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    if (lane == 0) scratch[warp] = s2;
+    __syncthreads();
+    if (warp == 0) {
+        s2 = lane < kWarps ? scratch[lane] : 0.0;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        if (lane == 0) {
+            const double c = s2 * inv_E;
+            const double w = (slack * s2) * inv_E + c * 0x1p-50;
+            float variance = __double2float_rn(c - w);
+            if (variance != __double2float_rn(c + w)) {
+                double ss = 0.0;
+                for (int i = 0; i < E; i++) { const float v = __fsub_rn(xs[i], mean); ss = __dadd_rn(ss, (double) __fmul_rn(v, v)); }
+                variance = __double2float_rn(__ddiv_rn(ss, (double) E));
+                if (fallback_counter) atomicAdd(fallback_counter, 1u);
+            }
+            bc[1] = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(variance, 1e-5f)));
         }
     }
-    const float scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(variance, 1e-5f)));
-    for (int i = threadIdx.x; i < E; i += kThreads) {
-        float y = __fmul_rn(__fsub_rn(xs[i], mean), scale);
-        y = __fmul_rn(y, g[i]);
-        if (b) y = __fadd_rn(y, b[i]);
-        act[act_index(i)] = ROUND16 ? round_f16(y) : y;
-    }
+    __syncthreads();
+    const float scale = bc[1];
+    if (h0) { float y = __fmul_rn(__fmul_rn(v0, scale), g0); if (b) y = __fadd_rn(y, b0); act[act_index(i0)] = ROUND16 ? round_f16(y) : y; }
+    if (h1) { float y = __fmul_rn(__fmul_rn(v1, scale), g1); if (b) y = __fadd_rn(y, b1); act[act_index(i1)] = ROUND16 ? round_f16(y) : y; }
     __syncthreads();
 }
 
@@ -340,6 +369,7 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
 
     uint32_t tag = A.tag_base;                               // unique epoch per exchange; the host advances the base by 6 * L per launch
     const float scale = 1.0f / sqrtf((float) E / (float) H);
+    const double inv_E = A.inv_E;
     auto stamp = [&](int layer, int i) {
         if (A.timing && tid == 0 && (blockIdx.x == 0 || layer == 5)) {      // CTA 0: every layer; all CTAs: layer 5 (rows 64.. of the buffer)
             unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -360,7 +390,7 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
         tag += 6;
         stamp(il, 12);
         // ---- P1: LN1 -> QKV ----
-        block_layernorm<kRound>(xs, E, lv.ln_1_g, lv.ln_1_b, act, A.ln_fallbacks);
+        block_layernorm<kRound>(xs, E, inv_E, lv.ln_1_g, lv.ln_1_b, act, red, bc, A.ln_fallbacks);
         run_phase<WT>(pc, 4 * il + 0, EP_QKV, il, t_qkv);
         stamp(il, 0);
 
@@ -461,8 +491,11 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
                     double lo = s - dl, hi = s + dl;
 #pragma unroll 1
                     for (int i = nchunks * 8; i < n_kv; i++) { const float tl = glibc_expf_dev(__fsub_rn(p[i], mx)); p[i] = tl; lo = __dadd_rn(lo, (double) tl); hi = __dadd_rn(hi, (double) tl); }
-                    float f_lo = __double2float_rn(__ddiv_rn(1.0, lo));
-                    const float f_hi = __double2float_rn(__ddiv_rn(1.0, hi));
+                    // 1/sum without a double division: y ~ 1/mid to 2^-50, the bracket [lo, hi] and that error go into the half-width
+                    const double mid = 0.5 * (lo + hi), y = approx_rcp(mid);
+                    const double rw = (hi - lo) * y * 0.5 + 0x1p-48;                       // relative half-width
+                    float f_lo = __double2float_rn(y * (1.0 - rw));
+                    const float f_hi = __double2float_rn(y * (1.0 + rw));
                     if (f_lo != f_hi) {
                         double q2 = 0.0;
 #pragma unroll 1
@@ -518,7 +551,7 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
         // ---- P5: LN2 -> c_fc -> GELU ----
         consume_to_smem<2>(gx, E, t_x1, xs, SINK_PLAIN);
         stamp(il, 7);
-        block_layernorm<kRound>(xs, E, lv.ln_2_g, lv.ln_2_b, act, A.ln_fallbacks);
+        block_layernorm<kRound>(xs, E, inv_E, lv.ln_2_g, lv.ln_2_b, act, red, bc, A.ln_fallbacks);
         run_phase<WT>(pc, 4 * il + 2, EP_GELU, il, t_ff);
         __syncthreads();                                         // the ff vector lands in `act`, which slower warps may still be reading
         stamp(il, 8);
@@ -533,7 +566,7 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
         stamp(il, 11);
     }
     // ---- final norm + lm_head window ----
-    block_layernorm<kRound>(xs, E, A.ln_f_g, A.ln_f_b, act, A.ln_fallbacks);
+    block_layernorm<kRound>(xs, E, inv_E, A.ln_f_g, A.ln_f_b, act, red, bc, A.ln_fallbacks);
     run_phase<WT>(pc, 4 * L, EP_LOGITS, 0, 0);
 }
 
