@@ -29,6 +29,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void * src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
@@ -73,26 +74,36 @@ template <> struct Cvt<float> {
 
 }  // namespace
 
-// C[m][o] = lane-order dot(act[m], W[o]) for a 32 x 16 block tile; 8 warps as 4 (m) x 2 (o), 8 x 8 outputs per warp.
+// C[m][o] = lane-order dot(act[m], W[o]).  Persistent CTAs walk 32 x 16 block tiles (o fastest, so CTAs running at the
+// same time share activation rows in L2); 8 warps as 4 (m) x 2 (o), 8 x 8 outputs per warp.  The k-steps of ALL of a CTA's
+// tiles form one stream through the 4-stage ring: warp 0 lane-issues the bulk copies of step s + 4 as soon as the 8 warps
+// have released the slot (per-slot `empty` mbarrier), so the loads of the next tile fly while this tile's tail and
+// butterfly epilogue run — with K = 768 a tile is only 3 k-steps, and a non-persistent version spent a third of its
+// time filling the pipe (ncu: 37% FMA-pipe active, top stall = barrier).
 template <typename T>
 __global__ void __launch_bounds__(256, 2) lane_gemm_tiled_kernel(const T * __restrict__ W, int K, int Kp, int O, const T * __restrict__ act, int M, MatmulEpilogue ep) {
     constexpr int G = Cvt<T>::G;
     extern __shared__ __align__(128) unsigned char smem[];
-    const uint32_t bars = smem_u32(smem + kStages * kStageBytes);
+    const uint32_t full = smem_u32(smem + kStages * kStageBytes), empty = full + kStages * 8;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp >> 1, wo = warp & 1;
-    const int m0 = blockIdx.y * kBM, o0 = blockIdx.x * kBO;
     const int nsteps = K >> 5;
-    const int ngroups = (nsteps + G - 1) / G;                 // k-stages; the last may be partial
+    const int ngroups = (nsteps + G - 1) / G;                 // k-steps per tile; the last may be partial
+    const int tiles_o = (O + kBO - 1) / kBO, tiles_m = (M + kBM - 1) / kBM, n_tiles = tiles_o * tiles_m;
+    const int my_tiles = ((int) blockIdx.x < n_tiles) ? (n_tiles - 1 - (int) blockIdx.x) / (int) gridDim.x + 1 : 0;
+    const int total_steps = my_tiles * ngroups;
 
     if (tid == 0) {
-        for (int s = 0; s < kStages; s++) mbar_init(bars + s * 8, 1);
+        for (int s = 0; s < kStages; s++) { mbar_init(full + s * 8, 1); mbar_init(empty + s * 8, 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    auto issue = [&](int g) {                                  // executed by warp 0
-        const int slot = g % kStages;
-        const uint32_t bar = bars + slot * 8;
+    auto issue = [&](int step) {                               // executed by warp 0: global k-step `step` of this CTA's stream
+        const int ti = step / ngroups, g = step - ti * ngroups;
+        const int tile = blockIdx.x + ti * gridDim.x;
+        const int m0 = (tile / tiles_o) * kBM, o0 = (tile % tiles_o) * kBO;
+        const int slot = step % kStages;
+        const uint32_t bar = full + slot * 8;
         if (lane == 0) mbar_expect_tx(bar, kStageBytes);
         __syncwarp();
         const uint32_t dst = smem_u32(smem + (size_t) slot * kStageBytes);
@@ -105,61 +116,71 @@ __global__ void __launch_bounds__(256, 2) lane_gemm_tiled_kernel(const T * __res
             tma_bulk_g2s(dst + (kBM + lane) * kRowBytes, (const unsigned char *) (W + (size_t) o * Kp) + (size_t) g * kRowBytes, kRowBytes, bar);
         }
     };
-    if (warp == 0) for (int g = 0; g < kStages && g < ngroups; g++) issue(g);
+    if (warp == 0) for (int s0 = 0; s0 < kStages && s0 < total_steps; s0++) issue(s0);
 
-    float acc[64];
+    int step = 0;
+    for (int ti = 0; ti < my_tiles; ti++) {
+        const int tile = blockIdx.x + ti * gridDim.x;
+        const int m0 = (tile / tiles_o) * kBM, o0 = (tile % tiles_o) * kBO;
+        float acc[64];
 #pragma unroll
-    for (int i = 0; i < 64; i++) acc[i] = 0.0f;
-
-    for (int g = 0; g < ngroups; g++) {
-        const int slot = g % kStages;
-        mbar_wait(bars + slot * 8, (uint32_t)((g / kStages) & 1));
-        const unsigned char * st = smem + (size_t) slot * kStageBytes;
-        const int steps = min(G, nsteps - g * G);              // chain steps present in this group
-        uint4 pa[8];
+        for (int i = 0; i < 64; i++) acc[i] = 0.0f;
+        for (int g = 0; g < ngroups; g++, step++) {
+            const int slot = step % kStages;
+            const uint32_t use = (uint32_t)(step / kStages);
+            mbar_wait(full + slot * 8, use & 1);
+            const unsigned char * st = smem + (size_t) slot * kStageBytes;
+            const int steps = min(G, nsteps - g * G);          // chain steps present in this group
+            uint4 pa[8];
 #pragma unroll
-        for (int mi = 0; mi < 8; mi++) pa[mi] = *reinterpret_cast<const uint4 *>(st + (wm * 8 + mi) * kRowBytes + lane * 16);
+            for (int mi = 0; mi < 8; mi++) pa[mi] = *reinterpret_cast<const uint4 *>(st + (wm * 8 + mi) * kRowBytes + lane * 16);
 #pragma unroll
-        for (int oh = 0; oh < 2; oh++) {
-            uint4 pw[4];
+            for (int oh = 0; oh < 2; oh++) {
+                uint4 pw[4];
 #pragma unroll
-            for (int oi = 0; oi < 4; oi++) pw[oi] = *reinterpret_cast<const uint4 *>(st + (kBM + wo * 8 + oh * 4 + oi) * kRowBytes + lane * 16);
+                for (int oi = 0; oi < 4; oi++) pw[oi] = *reinterpret_cast<const uint4 *>(st + (kBM + wo * 8 + oh * 4 + oi) * kRowBytes + lane * 16);
 #pragma unroll
-            for (int e = 0; e < G; e++) {
-                if (e < steps) {                               // uniform across the block
-                    float wf[4];
+                for (int e = 0; e < G; e++) {
+                    if (e < steps) {                           // uniform across the block
+                        float wf[4];
 #pragma unroll
-                    for (int oi = 0; oi < 4; oi++) wf[oi] = Cvt<T>::elem(pw[oi], e);
+                        for (int oi = 0; oi < 4; oi++) wf[oi] = Cvt<T>::elem(pw[oi], e);
 #pragma unroll
-                    for (int mi = 0; mi < 8; mi++) {
-                        const float af = Cvt<T>::elem(pa[mi], e);
+                        for (int mi = 0; mi < 8; mi++) {
+                            const float af = Cvt<T>::elem(pa[mi], e);
 #pragma unroll
-                        for (int oi = 0; oi < 4; oi++) acc[mi * 8 + oh * 4 + oi] = __fmaf_rn(wf[oi], af, acc[mi * 8 + oh * 4 + oi]);
+                            for (int oi = 0; oi < 4; oi++) acc[mi * 8 + oh * 4 + oi] = __fmaf_rn(wf[oi], af, acc[mi * 8 + oh * 4 + oi]);
+                        }
                     }
                 }
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + slot * 8);      // this warp is done with the slot
+            if (warp == 0 && step + kStages < total_steps) {   // refill it for k-step `step + kStages` once all 8 warps released it
+                mbar_wait(empty + slot * 8, use & 1);
+                issue(step + kStages);
+            }
         }
-        __syncthreads();                                       // every warp is done with this slot
-        if (warp == 0 && g + kStages < ngroups) issue(g + kStages);
-    }
-
-    const int base = butterfly_reduce64(acc, lane);            // outputs base, base+1 of the warp tile (index = mi*8 + oi)
-    const int m = m0 + wm * 8 + (base >> 3), o = o0 + wo * 8 + (base & 7);
-    if (m < M) {
-        if (o < O) matmul_epilogue(ep, m, o, acc[0]);
-        if (o + 1 < O) matmul_epilogue(ep, m, o + 1, acc[1]);
+        const int base = butterfly_reduce64(acc, lane);        // outputs base, base+1 of the warp tile (index = mi*8 + oi)
+        const int m = m0 + wm * 8 + (base >> 3), o = o0 + wo * 8 + (base & 7);
+        if (m < M) {
+            if (o < O) matmul_epilogue(ep, m, o, acc[0]);
+            if (o + 1 < O) matmul_epilogue(ep, m, o + 1, acc[1]);
+        }
     }
 }
 
 void lane_gemm_tiled(const DMat & W, const void * act, int rows, const MatmulEpilogue & ep, cudaStream_t s) {
-    const size_t smem = (size_t) kStages * kStageBytes + kStages * 8 + 64;
-    const dim3 grid((W.n_out + kBO - 1) / kBO, (rows + kBM - 1) / kBM);
-    static bool configured = false;
-    if (!configured) {
+    const size_t smem = (size_t) kStages * kStageBytes + 2 * kStages * 8 + 64;
+    static int n_sm = 0;
+    if (!n_sm) {
+        int dev = 0; BARK_CUDA_CHECK(cudaGetDevice(&dev));
+        BARK_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
         BARK_CUDA_CHECK(cudaFuncSetAttribute(lane_gemm_tiled_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         BARK_CUDA_CHECK(cudaFuncSetAttribute(lane_gemm_tiled_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        configured = true;
     }
+    const int n_tiles = ((W.n_out + kBO - 1) / kBO) * ((rows + kBM - 1) / kBM);
+    const int grid = min(n_tiles, 2 * n_sm);                   // persistent: two CTAs per SM (registers and shared memory allow exactly that)
     if (W.type == W_F16) BARK_LAUNCH((lane_gemm_tiled_kernel<__half>), grid, 256, smem, s, (const __half *) W.p, W.K, W.Kp, W.n_out, (const __half *) act, rows, ep);
     else                 BARK_LAUNCH((lane_gemm_tiled_kernel<float>), grid, 256, smem, s, (const float *) W.p, W.K, W.Kp, W.n_out, (const float *) act, rows, ep);
 }
