@@ -45,7 +45,7 @@ EXPORTS = [
     "bark_context_default_params", "bark_load_model", "bark_generate_audio", "bark_get_audio_data", "bark_get_audio_data_size",
     "bark_get_load_time", "bark_get_eval_time", "bark_reset_statistics", "bark_model_quantize", "bark_free",
     "bark_b200_set_device", "bark_b200_version", "bark_b200_gpt_eval", "bark_b200_fine_eval", "bark_b200_encodec_decode",
-    "bark_b200_sample", "bark_b200_reseed", "bark_b200_tokenize", "bark_b200_forward_text_encoder",
+    "bark_b200_sample", "bark_b200_sample_rows", "bark_b200_reseed", "bark_b200_tokenize", "bark_b200_forward_text_encoder",
     "bark_b200_forward_coarse_encoder", "bark_b200_forward_fine_encoder", "bark_b200_get_tokens", "bark_b200_set_tokens",
     "bark_b200_get_stats", "bark_b200_get_hparams", "bark_b200_kernel_launches", "bark_b200_layernorm_fallbacks",
     "bark_b200_profile_enable", "bark_b200_profile_report", "bark_b200_io_counters", "bark_b200_decode_timing",
@@ -91,6 +91,8 @@ def lib() -> C.CDLL:
     L.bark_b200_encodec_decode.argtypes = [vp, i32p, C.c_int, f32p, C.c_int]
     L.bark_b200_sample.restype = C.c_int
     L.bark_b200_sample.argtypes = [vp, C.c_int, f32p, C.c_int, C.c_float, C.POINTER(C.c_float)]
+    L.bark_b200_sample_rows.restype = C.c_int
+    L.bark_b200_sample_rows.argtypes = [vp, f32p, C.c_int, C.c_int, C.c_float, i32p, f32p]
     L.bark_b200_reseed.argtypes = [vp, C.c_uint32]
     L.bark_b200_tokenize.argtypes = [vp, C.c_char_p, i32p]
     for n in ("bark_b200_forward_text_encoder", "bark_b200_forward_coarse_encoder", "bark_b200_forward_fine_encoder"):
@@ -221,6 +223,16 @@ class Bark:
         l = np.ascontiguousarray(logits, np.float32)
         e = C.c_float(0)
         return lib().bark_b200_sample(self.ctx, which, _p(l), l.size, temp, C.byref(e)), e.value
+
+    def sample_rows(self, logits_rows, temp: float):
+        """Device sampler over [rows][n] logits; returns (tokens, eos_p, n_rows_replayed_on_host)."""
+        l = np.ascontiguousarray(logits_rows, np.float32)
+        rows, n = l.shape
+        tok = np.zeros(rows, np.int32); eos = np.zeros(rows, np.float32)
+        r = lib().bark_b200_sample_rows(self.ctx, _p(l), n, rows, temp, _p(tok), _p(eos))
+        if r < 0:
+            raise RuntimeError("bark_b200_sample_rows failed")
+        return tok, eos, r
 
     def reseed(self, seed: int):
         lib().bark_b200_reseed(self.ctx, seed)

@@ -138,6 +138,37 @@ int32_t sample_token(bark_context * ctx, GPTModel & m, const float * logits, int
     return next;
 }
 
+}  // namespace
+
+// gpt_sample with the uniform draw already made: the reference's arithmetic end to end, discrete_distribution restated
+// (bits/random.tcc: normalise in double, sequential partial sums, last one forced to 1.0, lower_bound of the draw).
+// Only rows the device kernel flags as too close to call come here.
+int32_t bark::sample_token_given_u(const float * logits, int n, float temp, double u, float * eos_p) {
+    std::vector<float> p(logits, logits + n);
+    const float div = temp == 0.0f ? 0.7f : temp;
+    for (float & v : p) v /= div;
+    float mx = -INFINITY;
+    for (float v : p) mx = std::max(mx, v);
+    float sum = 0.0f;
+    for (float & v : p) { v = (float) exp((double)(v - mx)); sum += v; }
+    for (float & v : p) v /= sum;
+    if (eos_p) *eos_p = p.back();
+    if (temp == 0.0f) {
+        float best = -INFINITY; int32_t next = 0;
+        for (int i = 0; i < n; i++) if (p[(size_t) i] > best) { best = p[(size_t) i]; next = i; }
+        return next;
+    }
+    std::vector<double> cp(p.begin(), p.end());
+    double tot = 0.0;
+    for (double v : cp) tot += v;
+    for (double & v : cp) v /= tot;
+    for (size_t i = 1; i < cp.size(); i++) cp[i] += cp[i - 1];
+    cp.back() = 1.0;
+    return (int32_t)(std::lower_bound(cp.begin(), cp.end(), u) - cp.begin());
+}
+
+namespace {
+
 void print_stage_stats(const GPTModel & m) {                                      // bark_print_statistics, bark.cpp:176-182
     if (quiet()) return;
     printf("\n\n");
@@ -151,6 +182,63 @@ void print_stage_stats(const GPTModel & m) {                                    
 // ---------------------------------------------------------------------------------------------
 // stage loops
 // ---------------------------------------------------------------------------------------------
+// Runs `n` consecutive sampling steps of one causal stream with the sampler on the device (sampling.cu).  Step 0 evaluates
+// `first_in` (a prompt or the single token the host already knows); every later step reads its input token from device
+// memory, where the previous step's sampler left it — so all n decode + sample launches are enqueued without a host round
+// trip and there is one synchronisation at the end.  lo_of(j) is the offset of step j's logit window in the vocabulary
+// (samp_n logits wide); tokens come back with that offset added.  A step the kernel flags as too close to call (see
+// sampling.cu) is replayed on the host with the reference's arithmetic and the same uniform draw, and the chain restarts
+// behind it; tokens and RNG state are identical to the step-by-step host path either way.
+template <typename LoOf>
+bool run_chain(bark_context * ctx, GPTModel & m, const std::vector<int32_t> & first_in, bool merge_ctx, int * n_past, int n, LoOf lo_of, int samp_n, float temp,
+               int32_t * out_tok, float * out_eos) {
+    if (n < 1 || n > 1024) return false;
+    const int64_t t_begin = now_us();
+    cudaStream_t s = ctx->stream;
+    if (temp != 0.0f) {
+        for (int j = 0; j < n; j++) ctx->h_u[j] = std::generate_canonical<double, 53>(ctx->rng);     // one draw per sample, as discrete_distribution::operator() makes
+        BARK_CUDA_CHECK(cudaMemcpyAsync(ctx->d_u, ctx->h_u, (size_t) n * sizeof(double), cudaMemcpyHostToDevice, s)); bark::g_h2d_bytes += (size_t) n * sizeof(double);
+    }
+    const bool chain = ctx->use_decode_kernel;
+    std::vector<int> past_before((size_t) n);
+    std::vector<int32_t> cur_in = first_in;
+    std::vector<float> host_logits;
+    int start = 0;
+    while (start < n) {
+        const int stop = chain ? n : start + 1;
+        for (int j = start; j < stop; j++) {
+            const int lo = lo_of(j);
+            past_before[(size_t) j] = *n_past;
+            if (j == start) { if (!gpt_eval(ctx, m, cur_in.data(), (int) cur_in.size(), n_past, merge_ctx && *n_past == 0, nullptr, lo, lo + samp_n)) return false; }
+            else if (!gpt_decode_chained(ctx, m, ctx->d_feed, n_past, lo, lo + samp_n)) return false;
+            const int force = ctx->debug_flag_every > 0 && (ctx->n_sample_calls++ % ctx->debug_flag_every) == 0;
+            sample_rows(ctx->last_logits + lo, m.n_out_vocab, samp_n, 1, temp, ctx->d_u + j, ctx->d_stok + j, lo, ctx->d_feed, ctx->d_seos + j, ctx->d_sflags + j, force, s);
+        }
+        const size_t cnt = (size_t)(stop - start);
+        BARK_CUDA_CHECK(cudaMemcpyAsync(ctx->h_stok + start, ctx->d_stok + start, cnt * 4, cudaMemcpyDeviceToHost, s));
+        BARK_CUDA_CHECK(cudaMemcpyAsync(ctx->h_sflags + start, ctx->d_sflags + start, cnt * 4, cudaMemcpyDeviceToHost, s));
+        BARK_CUDA_CHECK(cudaMemcpyAsync(ctx->h_seos + start, ctx->d_seos + start, cnt * 4, cudaMemcpyDeviceToHost, s)); bark::g_d2h_bytes += cnt * 12;
+        BARK_CUDA_CHECK(cudaStreamSynchronize(s));
+        int f = start;
+        while (f < stop && !ctx->h_sflags[f]) f++;
+        if (f == stop) { start = stop; if (start < n) cur_in.assign(1, ctx->h_stok[start - 1]); continue; }
+        // step f must be decided on the host: re-evaluate it with its logits read back (steps before f stand)
+        if (f > start) cur_in.assign(1, ctx->h_stok[f - 1]);
+        *n_past = past_before[(size_t) f];
+        const int lo = lo_of(f);
+        host_logits.resize((size_t) m.n_out_vocab);
+        if (!gpt_eval(ctx, m, cur_in.data(), (int) cur_in.size(), n_past, merge_ctx && *n_past == 0, host_logits.data(), lo, lo + samp_n)) return false;
+        ctx->h_stok[f] = lo + sample_token_given_u(host_logits.data() + lo, samp_n, temp, ctx->h_u[f], &ctx->h_seos[f]);
+        ctx->n_sample_host_replays++;
+        start = f + 1;
+        cur_in.assign(1, ctx->h_stok[f]);
+    }
+    for (int j = 0; j < n; j++) { out_tok[j] = ctx->h_stok[j]; if (out_eos) out_eos[j] = ctx->h_seos[j]; }
+    m.n_sample += n;
+    m.t_predict_us += now_us() - t_begin;      // evaluation and sampling overlap on the device: the split the reference prints does not exist here
+    return true;
+}
+
 bool run_semantic(bark_context * ctx) {
     const int64_t t_start = now_us();
     GPTModel & m = ctx->semantic;
@@ -158,6 +246,29 @@ bool run_semantic(bark_context * ctx) {
     std::vector<float> logits((size_t) m.n_out_vocab);
     std::vector<int32_t> input = ctx->tokens, output;
     int n_past = 0; float eos_p = 0.0f;
+    const bool dev = ctx->sample_on_device && (size_t) m.n_out_vocab * 4 <= 64 * 1024;
+    if (dev) {
+        // batches of kBatch steps run ahead of the stop test; if the stop falls inside a batch, the RNG is wound back to
+        // where the step-by-step loop would have left it and the surplus steps are dropped (their KV rows are never read)
+        constexpr int kBatch = 64;
+        std::vector<int32_t> tok(kBatch); std::vector<float> eos(kBatch);
+        bool done = false;
+        for (int i = 0; i < P.n_steps_text_encoder && !done; i += kBatch) {
+            const int nb = std::min(kBatch, P.n_steps_text_encoder - i);
+            const std::mt19937 saved = ctx->rng;
+            if (!run_chain(ctx, m, input, true, &n_past, nb, [](int) { return 0; }, m.n_out_vocab, P.temp, tok.data(), eos.data())) { fprintf(stderr, "%s: Could not generate token\n", __func__); return false; }
+            for (int j = 0; j < nb; j++) {
+                if (P.progress_callback) P.progress_callback(ctx, SEMANTIC, 100 * (i + j + 1) / P.n_steps_text_encoder, P.progress_callback_user_data);
+                if (tok[(size_t) j] == P.semantic_vocab_size || eos[(size_t) j] >= P.min_eos_p) {               // bark.cpp:1675-1677
+                    if (P.temp != 0.0f) { ctx->rng = saved; for (int k = 0; k <= j; k++) (void) std::generate_canonical<double, 53>(ctx->rng); }
+                    m.n_sample -= nb - (j + 1);
+                    done = true; break;
+                }
+                output.push_back(tok[(size_t) j]);
+            }
+            if (!done && nb > 0) input.assign(1, tok[(size_t) nb - 1]);
+        }
+    } else
     for (int i = 0; i < P.n_steps_text_encoder; i++) {
         if (P.progress_callback) P.progress_callback(ctx, SEMANTIC, 100 * (i + 1) / P.n_steps_text_encoder, P.progress_callback_user_data);
         if (!gpt_eval(ctx, m, input.data(), (int) input.size(), &n_past, true, logits.data())) { fprintf(stderr, "%s: Could not generate token\n", __func__); return false; }
@@ -187,6 +298,7 @@ bool run_coarse(bark_context * ctx) {
     if (n_steps <= 0 || P.n_coarse_codebooks != 2) { fprintf(stderr, "%s: nothing to generate (%zu semantic tokens)\n", __func__, sem.size()); return false; }
     const int n_windows = (int) ceilf((float) n_steps / P.sliding_window_size);
     std::vector<int32_t> out; out.reserve((size_t) n_steps);
+    const bool dev = ctx->sample_on_device && P.sliding_window_size <= 1024 && P.semantic_vocab_size + 2 * P.codebook_size <= m.n_out_vocab;
     int step = 0;
     for (int w = 0; w < n_windows; w++) {
         const int semantic_idx = (int) roundf(step / stc_ratio);
@@ -197,11 +309,22 @@ bool run_coarse(bark_context * ctx) {
         const size_t hist = std::min<size_t>((size_t) P.max_coarse_history, out.size());
         in.insert(in.end(), out.end() - (std::ptrdiff_t) hist, out.end());
         int n_past = 0;
+        if (dev) {
+            // only logits [lo, lo + codebook_size) are ever looked at in this stage (bark.cpp:1829-1833): the window alternates with the codebook
+            const int nw = std::min(P.sliding_window_size, n_steps - step), step0 = step;
+            std::vector<int32_t> tok((size_t) nw);
+            auto lo_of = [&](int j) { return P.semantic_vocab_size + (((step0 + j) % P.n_coarse_codebooks == 0) ? 0 : 1) * P.codebook_size; };
+            if (!run_chain(ctx, m, in, false, &n_past, nw, lo_of, P.codebook_size, P.temp, tok.data(), nullptr)) { fprintf(stderr, "%s: Could not generate token\n", __func__); return false; }
+            for (int j = 0; j < nw; j++) {
+                if (P.progress_callback) P.progress_callback(ctx, COARSE, 100 * (step + 1) / n_steps, P.progress_callback_user_data);
+                out.push_back(tok[(size_t) j]); step++;
+            }
+            continue;
+        }
         for (int j = 0; j < P.sliding_window_size && step < n_steps; j++) {
             if (P.progress_callback) P.progress_callback(ctx, COARSE, 100 * (step + 1) / n_steps, P.progress_callback_user_data);
             const bool major = step % P.n_coarse_codebooks == 0;
             const int lo = P.semantic_vocab_size + (major ? 0 : 1) * P.codebook_size;
-            // only logits [lo, lo + codebook_size) are ever looked at in this stage (bark.cpp:1829-1833): decode steps compute just that window of lm_head
             if (!gpt_eval(ctx, m, in.data(), (int) in.size(), &n_past, false, logits.data(), lo, lo + P.codebook_size)) { fprintf(stderr, "%s: Could not generate token\n", __func__); return false; }
             const int32_t next = lo + sample_token(ctx, m, logits.data() + lo, P.codebook_size, P.temp, nullptr);
             in.assign(1, next);
@@ -233,15 +356,17 @@ bool run_fine(bark_context * ctx) {
     for (int t = 0; t < T; t++) { arr[(size_t) t * 8] = ctx->coarse_tokens[(size_t) t * 2]; arr[(size_t) t * 8 + 1] = ctx->coarse_tokens[(size_t) t * 2 + 1]; }
     const int n_loops = std::max(0, (int) ceilf((len - 1024) / 512.f)) + 1;
     std::vector<float> logits((size_t) 1024 * m.n_out_vocab);
-    std::vector<int32_t> buf((size_t) 8 * 1024);
+    std::vector<int32_t> buf((size_t) 8 * 1024), sampled(1024);
+    const bool dev = ctx->sample_on_device;
     for (int n = 0; n < n_loops; n++) {
         const int start = std::min(n * 512, len - 1024), fill = std::min(n * 512, len - 512), rel = fill - start;
         for (int c = 0; c < 8; c++) for (int j = 0; j < 1024; j++) buf[(size_t) c * 1024 + j] = arr[(size_t)(start + j) * 8 + c];
         for (int nn = n_coarse; nn < n_cb; nn++) {
             if (P.progress_callback) P.progress_callback(ctx, FINE, 100 * (n * (n_cb - n_coarse) + (nn - n_coarse + 1)) / (n_loops * (n_cb - n_coarse)), P.progress_callback_user_data);
-            if (!fine_eval(ctx, buf.data(), nn, logits.data())) { fprintf(stderr, "%s: Could not generate token\n", __func__); return false; }
+            if (!fine_eval(ctx, buf.data(), nn, dev ? nullptr : logits.data())) { fprintf(stderr, "%s: Could not generate token\n", __func__); return false; }
+            if (dev && !sample_device(ctx, m, ctx->last_logits, m.n_out_vocab, cb_size, 1024, P.fine_temp, sampled.data(), nullptr)) return false;
             for (int i = 0; i < 1024; i++) {
-                const int32_t next = sample_token(ctx, m, logits.data() + (size_t) i * m.n_out_vocab, cb_size, P.fine_temp, nullptr);
+                const int32_t next = dev ? sampled[(size_t) i] : sample_token(ctx, m, logits.data() + (size_t) i * m.n_out_vocab, cb_size, P.fine_temp, nullptr);
                 // For clips <= 1024 frames (rel == 0) this is the reference's write (bark.cpp:2037).  For longer clips the
                 // reference indexes buf[nn*1024 + rel + i] and runs off the buffer (SURVEY finding 5); there we keep the
                 // original Bark semantics: every row is sampled (same RNG consumption) and rows >= rel are written in place.
@@ -280,6 +405,12 @@ void alloc_workspace(bark_context * ctx) {
     ws.tok  = (int32_t *) ctx_alloc(ctx, 8 * 1024 * 4);
     BARK_CUDA_CHECK(cudaMallocHost(&ctx->h_logits, n_logits * 4));
     BARK_CUDA_CHECK(cudaMallocHost(&ctx->h_tok, 8 * 1024 * 4));
+    ctx->d_u = (double *) ctx_alloc(ctx, 1024 * 8); ctx->d_stok = (int32_t *) ctx_alloc(ctx, 1024 * 4);
+    ctx->d_sflags = (int32_t *) ctx_alloc(ctx, 1024 * 4); ctx->d_seos = (float *) ctx_alloc(ctx, 1024 * 4);
+    ctx->d_feed = (int32_t *) ctx_alloc(ctx, 64); BARK_CUDA_CHECK(cudaMemset(ctx->d_feed, 0, 64));
+    BARK_CUDA_CHECK(cudaMemset(ctx->d_u, 0, 1024 * 8));
+    BARK_CUDA_CHECK(cudaMallocHost(&ctx->h_u, 1024 * 8)); BARK_CUDA_CHECK(cudaMallocHost(&ctx->h_stok, 1024 * 4));
+    BARK_CUDA_CHECK(cudaMallocHost(&ctx->h_sflags, 1024 * 4)); BARK_CUDA_CHECK(cudaMallocHost(&ctx->h_seos, 1024 * 4));
 }
 
 }  // namespace
@@ -335,6 +466,8 @@ extern "C" struct bark_context * bark_load_model(const char * model_path, struct
     ctx->device = dev;
     ctx->n_sm = prop.multiProcessorCount;
     { const char * e = getenv("BARK_B200_DECODE_CTAS"); if (e && atoi(e) >= 64 && atoi(e) <= ctx->n_sm) ctx->n_sm = atoi(e); }   // experiment knob: CTAs of the persistent decode kernel
+    { const char * e = getenv("BARK_B200_SAMPLE_FLAG_EVERY"); ctx->debug_flag_every = e ? atoi(e) : 0; }
+    { const char * e = getenv("BARK_B200_SAMPLE"); ctx->sample_on_device = !(e && !strcmp(e, "host")); }      // "host": read logits back and sample on the CPU (A-B)
     { const char * e = getenv("BARK_B200_DECODE"); ctx->use_decode_kernel = !(e && !strcmp(e, "multi")); }   // "multi": one kernel per op (debug / A-B)
     ctx->params = params;
     BARK_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
@@ -424,6 +557,10 @@ extern "C" void bark_free(struct bark_context * ctx) {
     if (ctx->d_codes) cudaFree(ctx->d_codes);
     if (ctx->h_logits) cudaFreeHost(ctx->h_logits);
     if (ctx->h_tok) cudaFreeHost(ctx->h_tok);
+    if (ctx->h_u) cudaFreeHost(ctx->h_u);
+    if (ctx->h_stok) cudaFreeHost(ctx->h_stok);
+    if (ctx->h_sflags) cudaFreeHost(ctx->h_sflags);
+    if (ctx->h_seos) cudaFreeHost(ctx->h_seos);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -454,6 +591,16 @@ extern "C" int bark_b200_encodec_decode(struct bark_context * ctx, const int32_t
 extern "C" int bark_b200_sample(struct bark_context * ctx, int which, const float * logits, int n, float temp, float * eos_p) {
     if (!ctx || !logits || n < 1) return -1;
     return sample_token(ctx, *pick(ctx, which < 0 || which > 2 ? 0 : which), logits, n, temp, eos_p);
+}
+extern "C" int bark_b200_sample_rows(struct bark_context * ctx, const float * logits, int n, int rows, float temp, int32_t * tokens_out, float * eos_p_out) {
+    if (!ctx || !logits || !tokens_out || rows < 1 || rows > 1024 || n < 2 || (size_t) n * 4 > 64 * 1024) return -1;
+    const size_t cap = std::max<size_t>({(size_t) ctx->semantic.n_out_vocab, (size_t) ctx->coarse.n_out_vocab, (size_t) 1024 * ctx->fine.n_out_vocab});
+    if ((size_t) rows * n > cap) return -1;
+    BARK_CUDA_CHECK(cudaSetDevice(ctx->device));
+    BARK_CUDA_CHECK(cudaMemcpyAsync(ctx->ws.logits, logits, (size_t) rows * n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    const long long before = ctx->n_sample_host_replays;
+    if (!sample_device(ctx, ctx->fine, ctx->ws.logits, n, n, rows, temp, tokens_out, eos_p_out)) return -1;
+    return (int)(ctx->n_sample_host_replays - before);
 }
 extern "C" void bark_b200_reseed(struct bark_context * ctx, uint32_t seed) { if (ctx) ctx->rng = std::mt19937(seed); }
 extern "C" void bark_b200_tokenize(struct bark_context * ctx, const char * text, int32_t * out513) {

@@ -24,6 +24,13 @@ struct bark_context {
     unsigned long long * d_timing = nullptr;         // optional phase timestamps of the decode kernel (BARK_B200_DECODE_TIMING=1)
 
     bark::Workspace ws;
+    const float * last_logits = nullptr;             // device logits of the latest gpt_eval / fine_eval
+    double * d_u = nullptr, * h_u = nullptr;         // device sampling: uniforms, tokens, flags, eos probabilities (1024 rows)
+    int32_t * d_stok = nullptr, * h_stok = nullptr, * d_sflags = nullptr, * h_sflags = nullptr;
+    float * d_seos = nullptr, * h_seos = nullptr;
+    int32_t * d_feed = nullptr;                      // token handed from sample_rows_kernel to the next decode step
+    bool sample_on_device = true; long long n_sample_host_replays = 0;
+    int debug_flag_every = 0; long long n_sample_calls = 0;   // BARK_B200_SAMPLE_FLAG_EVERY=k: force every k-th sample through the host replay (tests)
     float * h_logits = nullptr;                      // pinned, max(n_out) or 1024*fine_vocab
     int32_t * h_tok = nullptr;                       // pinned, 8*1024 ids
 
@@ -61,6 +68,13 @@ void build_decode_tables(bark_context * ctx, GPTModel & m);
 bool fine_eval(bark_context * ctx, const int32_t * in_buffer /*[8][1024]*/, int nn, float * logits_host /*[1024][n_out]*/);
 // EnCodec decode; codes [8][T] on the host; result in ctx->audio
 bool codec_decode(bark_context * ctx, const int32_t * codes, int T);
+
+// sampling.cu / gpt_forward.cu / bark_api.cu
+void sample_rows(const float * logits, int ld, int n, int rows, float temp, const double * d_u, int32_t * d_out_tok, int tok_add, int32_t * d_feed,
+                 float * d_eos_p, int32_t * d_flags, int force_flag, cudaStream_t s);
+bool gpt_decode_chained(bark_context * ctx, GPTModel & m, const int32_t * d_token, int * n_past, int lm_lo, int lm_hi);
+bool sample_device(bark_context * ctx, GPTModel & m, const float * d_logits, int ld, int n, int rows, float temp, int32_t * out_tok, float * out_eos);
+int32_t sample_token_given_u(const float * logits, int n, float temp, double u, float * eos_p);
 
 int64_t now_us();
 

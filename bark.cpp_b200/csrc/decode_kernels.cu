@@ -361,8 +361,9 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
     stage_rows(pc, 1);
 
     // embedding of the one new token (bark.cpp:1226-1228, 1259): every CTA keeps its own copy of the residual stream
+    const int token = A.token_ptr ? min(max(__ldcg(A.token_ptr), 0), A.n_vocab_in - 1) : A.token;
     for (int i = tid; i < E; i += kThreads) {
-        const float t = kRound ? __half2float(((const __half *) A.wte)[(size_t) A.token * E + i]) : ((const float *) A.wte)[(size_t) A.token * E + i];
+        const float t = kRound ? __half2float(((const __half *) A.wte)[(size_t) token * E + i]) : ((const float *) A.wte)[(size_t) token * E + i];
         xs[i] = __fadd_rn(t, A.wpe[(size_t) n_past * E + i]);
     }
     __syncthreads();

@@ -74,7 +74,7 @@ void build_decode_tables(bark_context * ctx, GPTModel & m) {
 }
 
 // one decode token through the persistent kernel
-static void decode_step(bark_context * ctx, GPTModel & m, int token, int n_past, int lm_lo, int lm_hi) {
+static void decode_step(bark_context * ctx, GPTModel & m, int token, const int32_t * d_token, int n_past, int lm_lo, int lm_hi) {
     DecodeArgs a{};
     a.phases = (const DecodePhase *) m.d_phases; a.layer_vecs = (const DecodeLayerVec *) m.d_layer_vecs;
     a.wte = m.wte[0]; a.wpe = m.wpe; a.ln_f_g = m.ln_f_g; a.ln_f_b = m.ln_f_b; a.gelu_tab = ctx->d_gelu_tab;
@@ -82,6 +82,7 @@ static void decode_step(bark_context * ctx, GPTModel & m, int token, int n_past,
     a.gx = m.gx; a.gq = m.gq; a.gk = m.gk; a.gv = m.gv; a.gatt = m.gatt; a.gff = m.gff; a.gscores = m.gscores; a.logits = m.glogits;
     a.tag_base = ctx->tag_base; a.ln_fallbacks = ctx->d_ln_fallbacks; a.timing = ctx->d_timing;
     a.E = m.n_embd; a.H = m.n_head; a.L = m.n_layer; a.block_size = m.block_size; a.n_past = n_past; a.token = token; a.lm_lo = lm_lo; a.lm_hi = lm_hi;
+    a.token_ptr = d_token; a.n_vocab_in = m.n_in_vocab;
     a.inv_E = 1.0 / (double) m.n_embd;
     const double es = m.wtype == W_F16 ? 2.0 : 4.0;
     const double E = m.n_embd, L = m.n_layer;
@@ -103,11 +104,14 @@ bool gpt_eval(bark_context * ctx, GPTModel & m, const int32_t * tokens, int n, i
     if (*n_past > 0) {
         if (N != 1) { fprintf(stderr, "%s: decoding expects one token per step (got %d)\n", __func__, N); return false; }
         if (ctx->use_decode_kernel && *n_past + 1 <= m.block_size && tokens[0] >= 0 && tokens[0] < m.n_in_vocab) {
-            decode_step(ctx, m, tokens[0], *n_past, lm_lo, lm_hi);
-            const size_t nb = (size_t)(lm_hi - lm_lo) * sizeof(float);
-            BARK_CUDA_CHECK(cudaMemcpyAsync(ctx->h_logits, m.glogits + lm_lo, nb, cudaMemcpyDeviceToHost, s)); g_d2h_bytes += nb;
-            BARK_CUDA_CHECK(cudaStreamSynchronize(s));
-            memcpy(logits_host + lm_lo, ctx->h_logits, nb);
+            decode_step(ctx, m, tokens[0], nullptr, *n_past, lm_lo, lm_hi);
+            ctx->last_logits = m.glogits;
+            if (logits_host) {
+                const size_t nb = (size_t)(lm_hi - lm_lo) * sizeof(float);
+                BARK_CUDA_CHECK(cudaMemcpyAsync(ctx->h_logits, m.glogits + lm_lo, nb, cudaMemcpyDeviceToHost, s)); g_d2h_bytes += nb;
+                BARK_CUDA_CHECK(cudaStreamSynchronize(s));
+                memcpy(logits_host + lm_lo, ctx->h_logits, nb);
+            }
             *n_past += 1;
             m.t_predict_us += now_us() - t0;
             return true;
@@ -126,11 +130,26 @@ bool gpt_eval(bark_context * ctx, GPTModel & m, const int32_t * tokens, int n, i
     layernorm_act(ws.x + (size_t)(N - 1) * E, 1, E, m.ln_f_g, m.ln_f_b, ws.act, m.wtype, kpE, ctx->d_ln_fallbacks, s);
     MatmulEpilogue st; st.mode = EPI_STORE; st.out = ws.logits; st.ldo = m.n_out_vocab;
     lane_matmul(m.lm_head[0], ws.act, 1, st, s);
-    BARK_CUDA_CHECK(cudaMemcpyAsync(ctx->h_logits, ws.logits, (size_t) m.n_out_vocab * sizeof(float), cudaMemcpyDeviceToHost, s)); g_d2h_bytes += (size_t) m.n_out_vocab * sizeof(float);
-    BARK_CUDA_CHECK(cudaStreamSynchronize(s));
-    memcpy(logits_host, ctx->h_logits, (size_t) m.n_out_vocab * sizeof(float));
+    ctx->last_logits = ws.logits;
+    if (logits_host) {
+        BARK_CUDA_CHECK(cudaMemcpyAsync(ctx->h_logits, ws.logits, (size_t) m.n_out_vocab * sizeof(float), cudaMemcpyDeviceToHost, s)); g_d2h_bytes += (size_t) m.n_out_vocab * sizeof(float);
+        BARK_CUDA_CHECK(cudaStreamSynchronize(s));
+        memcpy(logits_host, ctx->h_logits, (size_t) m.n_out_vocab * sizeof(float));
+    }
     *n_past += N;
     m.t_predict_us += now_us() - t0;
+    return true;
+}
+
+// One decode step whose input token is read from device memory (the previous step's sample): nothing to wait for on the
+// host, so a whole window of steps is enqueued back to back.
+bool gpt_decode_chained(bark_context * ctx, GPTModel & m, const int32_t * d_token, int * n_past, int lm_lo, int lm_hi) {
+    if (!ctx->use_decode_kernel || *n_past < 1) { fprintf(stderr, "%s: needs the persistent decode kernel and a filled KV cache\n", __func__); return false; }
+    if (*n_past + 1 > m.block_size) { fprintf(stderr, "%s: context overflow (n_past %d + 1 > %d)\n", __func__, *n_past, m.block_size); return false; }
+    if (lm_hi <= 0 || lm_hi > m.n_out_vocab || lm_lo < 0 || lm_lo >= lm_hi) { lm_lo = 0; lm_hi = m.n_out_vocab; }
+    decode_step(ctx, m, 0, d_token, *n_past, lm_lo, lm_hi);
+    ctx->last_logits = m.glogits;
+    *n_past += 1;
     return true;
 }
 
@@ -149,11 +168,47 @@ bool fine_eval(bark_context * ctx, const int32_t * in_buffer, int nn, float * lo
     layernorm_act(ws.x, N, E, m.ln_f_g, m.ln_f_b, ws.act, m.wtype, kpE, ctx->d_ln_fallbacks, s);
     MatmulEpilogue st; st.mode = EPI_STORE; st.out = ws.logits; st.ldo = m.n_out_vocab;
     lane_matmul(m.lm_head[nn - 1], ws.act, N, st, s);                                                           // n_codes_given = 1 (bark.cpp:61,1573)
-    const size_t nb = (size_t) N * m.n_out_vocab * sizeof(float);
-    BARK_CUDA_CHECK(cudaMemcpyAsync(ctx->h_logits, ws.logits, nb, cudaMemcpyDeviceToHost, s)); g_d2h_bytes += nb;
-    BARK_CUDA_CHECK(cudaStreamSynchronize(s));
-    memcpy(logits_host, ctx->h_logits, nb);
+    ctx->last_logits = ws.logits;
+    if (logits_host) {
+        const size_t nb = (size_t) N * m.n_out_vocab * sizeof(float);
+        BARK_CUDA_CHECK(cudaMemcpyAsync(ctx->h_logits, ws.logits, nb, cudaMemcpyDeviceToHost, s)); g_d2h_bytes += nb;
+        BARK_CUDA_CHECK(cudaStreamSynchronize(s));
+        memcpy(logits_host, ctx->h_logits, nb);
+    }
     m.t_predict_us += now_us() - t0;
+    return true;
+}
+
+// Sample `rows` tokens from device-resident logits (sampling.cu); rows the kernel could not decide bit-safely are replayed
+// on the host with the reference's exact arithmetic and the same uniform draw.  Leaves tokens (and optionally the
+// probability of the last logit) in out_tok / out_eos.  The RNG stream advances exactly as gpt_sample would advance it.
+bool sample_device(bark_context * ctx, GPTModel & m, const float * d_logits, int ld, int n, int rows, float temp, int32_t * out_tok, float * out_eos) {
+    const int64_t t0 = now_us();
+    cudaStream_t s = ctx->stream;
+    if (rows < 1 || rows > 1024 || n < 2 || (size_t) n * 4 > 64 * 1024) { fprintf(stderr, "%s: unsupported shape (%d rows of %d)\n", __func__, rows, n); return false; }
+    if (temp != 0.0f) {
+        for (int r = 0; r < rows; r++) ctx->h_u[r] = std::generate_canonical<double, 53>(ctx->rng);   // what discrete_distribution::operator() draws
+        BARK_CUDA_CHECK(cudaMemcpyAsync(ctx->d_u, ctx->h_u, (size_t) rows * sizeof(double), cudaMemcpyHostToDevice, s)); g_h2d_bytes += (size_t) rows * sizeof(double);
+    }
+    const int force = ctx->debug_flag_every > 0 && (ctx->n_sample_calls++ % ctx->debug_flag_every) == 0;
+    sample_rows(d_logits, ld, n, rows, temp, ctx->d_u, ctx->d_stok, 0, nullptr, ctx->d_seos, ctx->d_sflags, force, s);
+    BARK_CUDA_CHECK(cudaMemcpyAsync(ctx->h_stok, ctx->d_stok, (size_t) rows * 4, cudaMemcpyDeviceToHost, s));
+    BARK_CUDA_CHECK(cudaMemcpyAsync(ctx->h_sflags, ctx->d_sflags, (size_t) rows * 4, cudaMemcpyDeviceToHost, s));
+    BARK_CUDA_CHECK(cudaMemcpyAsync(ctx->h_seos, ctx->d_seos, (size_t) rows * 4, cudaMemcpyDeviceToHost, s)); g_d2h_bytes += (size_t) rows * 12;
+    BARK_CUDA_CHECK(cudaStreamSynchronize(s));
+    std::vector<float> row;
+    for (int r = 0; r < rows; r++) {
+        if (ctx->h_sflags[r]) {
+            row.resize((size_t) n);
+            BARK_CUDA_CHECK(cudaMemcpy(row.data(), d_logits + (size_t) r * ld, (size_t) n * 4, cudaMemcpyDeviceToHost)); g_d2h_bytes += (size_t) n * 4;
+            ctx->h_stok[r] = sample_token_given_u(row.data(), n, temp, ctx->h_u[r], &ctx->h_seos[r]);
+            ctx->n_sample_host_replays++;
+        }
+        out_tok[r] = ctx->h_stok[r];
+        if (out_eos) out_eos[r] = ctx->h_seos[r];
+    }
+    m.t_sample_us += now_us() - t0;
+    m.n_sample += rows;
     return true;
 }
 

@@ -7,6 +7,7 @@
  *   bark_b200_fine_eval ....... one fine pass              == bark_eval_fine_encoder_internal (bark.cpp:1907-1959)
  *   bark_b200_encodec_decode .. codes -> waveform          == encodec_decompress_audio        (encodec.cpp/encodec.cpp:902-924)
  *   bark_b200_sample .......... gpt_sample on the context RNG                                 (bark.cpp:249-270)
+ *   bark_b200_sample_rows ..... the same for `rows` logit rows, on the device sampler the stages use (host replay of rows it cannot decide)
  *   bark_b200_forward_* ....... extern "C" names for bark_forward_{text,coarse,fine}_encoder  (bark.cpp:1703,1865,2061)
  *   bark_b200_tokenize ........ bark_tokenize_input                                           (bark.cpp:622-662)
  *
@@ -31,6 +32,8 @@ BARK_API int  bark_b200_fine_eval(struct bark_context * ctx, const int32_t * in_
 /* codes: [8][n_frames]; returns number of samples (320 * n_frames), copies min(n, out_cap) floats to out (may be NULL) */
 BARK_API int  bark_b200_encodec_decode(struct bark_context * ctx, const int32_t * codes, int n_frames, float * out, int out_cap);
 BARK_API int  bark_b200_sample(struct bark_context * ctx, int which, const float * logits, int n, float temp, float * eos_p);
+BARK_API int  bark_b200_sample_rows(struct bark_context * ctx, const float * logits /*[rows][n], host*/, int n, int rows, float temp, int32_t * tokens_out,
+                                     float * eos_p_out /*[rows] or NULL*/);   /* returns the number of rows replayed on the host, <0 on error */
 BARK_API void bark_b200_reseed(struct bark_context * ctx, uint32_t seed);
 BARK_API void bark_b200_tokenize(struct bark_context * ctx, const char * text, int32_t * out513);
 

@@ -74,6 +74,64 @@ def test_host_sampler_matches_oracle(pkg, orc, weights_file):
             assert b.sample(0, lg, temp) == o.sample(lg, temp)
 
 
+def test_device_sampler_matches_oracle(pkg, orc, weights_file):
+    """sample_rows_kernel (the sampler the stages use) against gpt_sample of the oracle: same tokens, same RNG stream."""
+    path = weights_file("tiny", "f16")
+    o = orc.Oracle(path)
+    rng = np.random.default_rng(13)
+    with pkg.Bark(path) as b:
+        b.reseed(9); o.reseed(9)
+        replays = 0
+        for case, (rows, n, scale, temp) in enumerate([(1024, 1024, 5.0, 0.5), (1, 10048, 5.0, 0.7), (1, 1024, 0.01, 0.7), (64, 1024, 40.0, 0.7),
+                                                        (7, 1056, 1.0, 0.0), (1, 10048, 3.0, 0.0), (33, 777, 8.0, 1.3)]):
+            lg = (rng.standard_normal((rows, n)) * scale).astype(np.float32)
+            if case == 3:
+                lg[:, -1] += 200.0               # one dominant logit: everything else underflows to 0
+            tok, eos, r = b.sample_rows(lg, temp)
+            replays += r
+            for i in range(rows):
+                t, e = o.sample(lg[i], temp)
+                assert tok[i] == t, f"case {case} row {i}: device {tok[i]} oracle {t}"
+                assert bits(np.float32(eos[i])) == bits(np.float32(e))
+        assert replays < 8                        # flagged rows are the rare exception, not the path
+
+
+def test_sampler_paths_agree(pkg, weights_file, monkeypatch):
+    """Device sampler (chained decode), forced host replays inside the chain, and the plain host sampler: same tokens and
+    same RNG state afterwards (second clip on the same context)."""
+    path = weights_file("mini", "f16")
+    runs = []
+    for env in ({}, {"BARK_B200_SAMPLE_FLAG_EVERY": "5"}, {"BARK_B200_SAMPLE": "host"}, {"BARK_B200_DECODE": "multi"}):
+        for k in ("BARK_B200_SAMPLE_FLAG_EVERY", "BARK_B200_SAMPLE", "BARK_B200_DECODE"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        with pkg.Bark(path, seed=3, n_steps_text_encoder=70) as b:
+            a1 = b.generate("one two three"); t1 = [b.tokens(i).copy() for i in range(3)]
+            a2 = b.generate("four"); t2 = [b.tokens(i).copy() for i in range(3)]
+        runs.append((a1, t1, a2, t2))
+    for a1, t1, a2, t2 in runs[1:]:
+        for i in range(3):
+            assert np.array_equal(t1[i], runs[0][1][i]) and np.array_equal(t2[i], runs[0][3][i])
+        assert np.array_equal(bits(a1), bits(runs[0][0])) and np.array_equal(bits(a2), bits(runs[0][2]))
+
+
+def test_semantic_early_stop_inside_a_batch(pkg, orc, weights_file):
+    """min_eos_p low enough that the stop test fires mid-batch: the device path runs ahead, then must drop the surplus
+    steps and rewind the RNG so the coarse and fine stages draw what the reference draws."""
+    path = weights_file("tiny", "f16")
+    hit = 0
+    for seed, eos in ((0, 7.0e-6), (1, 1.2e-5), (2, 3.6e-6)):      # stops after 39, 85 and 37 tokens (batches are 64 steps)
+        ref = orc.Oracle(path, seed=seed, n_steps=150, min_eos_p=eos).generate("hello world")
+        with pkg.Bark(path, seed=seed, n_steps_text_encoder=150, min_eos_p=eos) as b:
+            b.generate("hello world")
+            assert np.array_equal(b.tokens(0), ref["semantic"])
+            assert np.array_equal(b.tokens(1), ref["coarse"])
+            assert np.array_equal(b.tokens(2), ref["fine"])
+        hit += 0 < len(ref["semantic"]) < 150
+    assert hit == 3, "no early stop happened: adjust min_eos_p in this test"
+
+
 @pytest.mark.parametrize("config,ftype,n_steps", [("tiny", "f16", 20), ("mini", "f32", 45), ("mini", "f16", 30)])
 def test_generate_tokens_bit_exact_and_waveform(pkg, orc, weights_file, config, ftype, n_steps):
     path = weights_file(config, ftype)
