@@ -61,6 +61,15 @@ __host__ __device__ inline int li_group(int elem_bytes) { return 16 / elem_bytes
 __host__ __device__ inline int li_padded_k(int K, int elem_bytes) { const int q = 32 * li_group(elem_bytes); return (K + q - 1) / q * q; }
 __host__ __device__ inline int li_offset(int k, int G) { const int v = k & 31, c = k >> 5; return ((c / G) * 32 + v) * G + (c % G); }
 
+// Group-major ("GM") operand layout of the multi-row mat-muls.  A k-group is 128 consecutive columns = 4 chain steps of
+// every lane; element (row r, column k) lives at  (k/128) * gs + r * 128 + (k%32) * 4 + (k/32)%4  with gs = rows_cap * 128.
+// For a fixed group the rows are contiguous, so a block tile of R rows x 128 columns is ONE contiguous R*128-element span
+// (one bulk copy), and lane v's 4 elements of a row are one 8-byte (f16) / 16-byte (f32) word at stride = word size:
+// bank-conflict free in shared memory.
+constexpr int kGmGroup = 128;
+__host__ __device__ inline size_t gm_offset(int r, int k, size_t gs) { return (size_t)(k >> 7) * gs + (size_t) r * kGmGroup + (size_t)((k & 31) << 2) + (size_t)((k >> 5) & 3); }
+__host__ __device__ inline int gm_groups(int K) { return (K + kGmGroup - 1) / kGmGroup; }
+
 #ifdef __CUDACC__
 // GGML_F32x8_REDUCE (ggml.c:1405-1422) over the 32 lane partials; every lane returns the result.
 // x0+=x2, x1+=x3 (xor 16); x0+=x1 (xor 8); t[l]=x0[l]+x0[l+4] (xor 4); (t0+t1)+(t2+t3) (xor 1, xor 2).

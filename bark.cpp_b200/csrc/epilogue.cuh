@@ -9,19 +9,11 @@ namespace bark {
 // activation operand writers: an activation value for column k of row m, in the format the next
 // mul_mat consumes (the reference converts src1 to the weight's vec_dot_type, ggml.c:12530-12558)
 // ------------------------------------------------------------------------------------------------
-template <typename T> struct ActIO;
-template <> struct ActIO<__half> {
-    static constexpr int G = 8;
-    __device__ static void store(void * act, size_t row_off, int k, float v) { ((__half *) act)[row_off + li_offset(k, 8)] = __float2half_rn(v); }
-};
-template <> struct ActIO<float> {
-    static constexpr int G = 4;
-    __device__ static void store(void * act, size_t row_off, int k, float v) { ((float *) act)[row_off + li_offset(k, 4)] = v; }
-};
-
-__device__ __forceinline__ void store_act(void * act, int wt, int Kp, int m, int k, float v) {
-    if (wt == W_F16) ActIO<__half>::store(act, (size_t) m * Kp, k, v);
-    else             ActIO<float>::store(act, (size_t) m * Kp, k, v);
+// activations are written in the group-major layout (common.cuh), gs = group stride in elements (= row capacity * 128)
+__device__ __forceinline__ void store_act(void * act, int wt, int gs, int m, int k, float v) {
+    const size_t off = gm_offset(m, k, (size_t) gs);
+    if (wt == W_F16) ((__half *) act)[off] = __float2half_rn(v);
+    else             ((float *) act)[off] = v;
 }
 
 template <typename T> __device__ __forceinline__ void unpack16(const uint4 & u, float (&f)[16 / sizeof(T)]);

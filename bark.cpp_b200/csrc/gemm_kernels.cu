@@ -8,8 +8,8 @@
 // different lanes different outputs.  The 32 partials of all 64 outputs are then combined with a transposed
 // butterfly (62 shuffles instead of 64 x 5) that performs exactly the additions of GGML_F32x8_REDUCE.
 //
-// Both operands are in the lane-interleaved layout, so a k-step of the block tile is 48 rows x 512 contiguous
-// bytes: one TMA bulk copy per row into a 4-stage shared-memory ring (mbarrier complete_tx).
+// Both operands are in the group-major layout (common.cuh), so a pipeline stage of the block tile is a handful of
+// contiguous spans: 2-4 TMA bulk copies into a 4-stage shared-memory ring (mbarrier complete_tx).
 #include "epilogue.cuh"
 #include "gpt_kernels.h"
 
@@ -55,68 +55,76 @@ __device__ __forceinline__ int butterfly_reduce64(float (&r)[64], int lane) {
     return ((lane & 16) << 1) | ((lane & 8) << 1) | ((lane & 4) << 1) | ((lane & 1) << 2) | (lane & 2);
 }
 
-constexpr int kBM = 32, kBO = 16, kStages = 4, kRowBytes = 512;
-constexpr int kStageBytes = (kBM + kBO) * kRowBytes;     // 24 KB
+constexpr int kBM = 32, kBO = 16, kStages = 4;
+constexpr int kStageBytes = (kBM + kBO) * 512;           // 24 KB: 256 columns of f16 (two groups) or 128 columns of f32 (one group)
 
-template <typename T> struct Cvt;
-template <> struct Cvt<__half> {
-    static constexpr int G = 8;
-    __device__ __forceinline__ static float elem(const uint4 & u, int e) {        // e is a compile-time constant after unrolling
-        const uint32_t w = e < 2 ? u.x : e < 4 ? u.y : e < 6 ? u.z : u.w;
+// lane v's four elements of one row of one 128-column group (group-major layout, common.cuh)
+template <typename T> struct QuadOp;
+template <> struct QuadOp<__half> {
+    typedef uint2 V;
+    static constexpr int kGroupsPerStage = 2;
+    __device__ __forceinline__ static float elem(const uint2 & u, int c) {       // c is a compile-time constant after unrolling
+        const uint32_t w = c < 2 ? u.x : u.y;
         const __half2 h = *reinterpret_cast<const __half2 *>(&w);
-        return (e & 1) ? __high2float(h) : __low2float(h);
+        return (c & 1) ? __high2float(h) : __low2float(h);
     }
 };
-template <> struct Cvt<float> {
-    static constexpr int G = 4;
-    __device__ __forceinline__ static float elem(const uint4 & u, int e) { return __uint_as_float(e == 0 ? u.x : e == 1 ? u.y : e == 2 ? u.z : u.w); }
+template <> struct QuadOp<float> {
+    typedef uint4 V;
+    static constexpr int kGroupsPerStage = 1;
+    __device__ __forceinline__ static float elem(const uint4 & u, int c) { return __uint_as_float(c == 0 ? u.x : c == 1 ? u.y : c == 2 ? u.z : u.w); }
 };
 
 }  // namespace
 
 // C[m][o] = lane-order dot(act[m], W[o]).  Persistent CTAs walk 32 x 16 block tiles (o fastest, so CTAs running at the
-// same time share activation rows in L2); 8 warps as 4 (m) x 2 (o), 8 x 8 outputs per warp.  The k-steps of ALL of a CTA's
-// tiles form one stream through the 4-stage ring: warp 0 lane-issues the bulk copies of step s + 4 as soon as the 8 warps
-// have released the slot (per-slot `empty` mbarrier), so the loads of the next tile fly while this tile's tail and
-// butterfly epilogue run — with K = 768 a tile is only 3 k-steps, and a non-persistent version spent a third of its
-// time filling the pipe (ncu: 37% FMA-pipe active, top stall = barrier).
+// same time share activation rows in L2); 8 warps as 4 (m) x 2 (o), 8 x 8 outputs per warp.
+//
+// Both operands are group-major: for one 128-column group the 32 activation rows of a tile are one contiguous span, the
+// 16 weight rows another, so a pipeline stage is 2 (f32) or 4 (f16) bulk copies issued by ONE thread.  (A first version
+// with row-major operands needed 48 row copies per stage; the copy instruction takes uniform operands, the compiler
+// serialised the 48 lanes, and the issuing warp - also a consumer - fell ~1.5k cycles behind per stage: ncu showed 30% of
+// all stall samples on the `full`-barrier wait of the other seven warps.)
+//
+// The k-steps of ALL of a CTA's tiles form one stream through the 4-stage ring.  Nobody waits to refill a slot: every warp
+// bumps the slot's counter when it is done reading, and the warp that arrives last issues the copies for stage s + 4.
 template <typename T>
-__global__ void __launch_bounds__(256, 2) lane_gemm_tiled_kernel(const T * __restrict__ W, int K, int Kp, int O, const T * __restrict__ act, int M, MatmulEpilogue ep) {
-    constexpr int G = Cvt<T>::G;
+__global__ void __launch_bounds__(256, 2) lane_gemm_tiled_kernel(const T * __restrict__ Wg, int K, int w_gs, int O, const T * __restrict__ act, int act_gs, int M, MatmulEpilogue ep) {
+    typedef typename QuadOp<T>::V QV;
+    constexpr int GPS = QuadOp<T>::kGroupsPerStage;
+    constexpr int kRowB = kGmGroup * sizeof(T);              // bytes of one row of one group: 256 (f16) / 512 (f32)
     extern __shared__ __align__(128) unsigned char smem[];
-    const uint32_t full = smem_u32(smem + kStages * kStageBytes), empty = full + kStages * 8;
+    const uint32_t full = smem_u32(smem + kStages * kStageBytes);
+    int * const cnt = reinterpret_cast<int *>(smem + kStages * kStageBytes + kStages * 8);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp >> 1, wo = warp & 1;
-    const int nsteps = K >> 5;
-    const int ngroups = (nsteps + G - 1) / G;                 // k-steps per tile; the last may be partial
+    const int nsteps = K >> 5;                                // chain steps per lane
+    const int ngroups = (nsteps + 3) >> 2;                    // 128-column groups; the last may be partial
+    const int nstages = (ngroups + GPS - 1) / GPS;            // pipeline stages per tile
     const int tiles_o = (O + kBO - 1) / kBO, tiles_m = (M + kBM - 1) / kBM, n_tiles = tiles_o * tiles_m;
     const int my_tiles = ((int) blockIdx.x < n_tiles) ? (n_tiles - 1 - (int) blockIdx.x) / (int) gridDim.x + 1 : 0;
-    const int total_steps = my_tiles * ngroups;
+    const int total_steps = my_tiles * nstages;
 
     if (tid == 0) {
-        for (int s = 0; s < kStages; s++) { mbar_init(full + s * 8, 1); mbar_init(empty + s * 8, 8); }
+        for (int s = 0; s < kStages; s++) { mbar_init(full + s * 8, 1); cnt[s] = 0; }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    auto issue = [&](int step) {                               // executed by warp 0: global k-step `step` of this CTA's stream
-        const int ti = step / ngroups, g = step - ti * ngroups;
+    auto issue = [&](int step) {                              // ONE thread: stage `step` of this CTA's stream
+        const int ti = step / nstages, sg = step - ti * nstages;
         const int tile = blockIdx.x + ti * gridDim.x;
         const int m0 = (tile / tiles_o) * kBM, o0 = (tile % tiles_o) * kBO;
         const int slot = step % kStages;
         const uint32_t bar = full + slot * 8;
-        if (lane == 0) mbar_expect_tx(bar, kStageBytes);
-        __syncwarp();
+        const int g0 = sg * GPS, ng = min(GPS, ngroups - g0);
+        mbar_expect_tx(bar, (uint32_t)(ng * (kBM + kBO) * kRowB));
         const uint32_t dst = smem_u32(smem + (size_t) slot * kStageBytes);
-        {   // activation rows (clamped: rows past M repeat the last row and are masked at the store)
-            const int m = min(m0 + lane, M - 1);
-            tma_bulk_g2s(dst + lane * kRowBytes, (const unsigned char *) (act + (size_t) m * Kp) + (size_t) g * kRowBytes, kRowBytes, bar);
-        }
-        if (lane < kBO) {
-            const int o = min(o0 + lane, O - 1);
-            tma_bulk_g2s(dst + (kBM + lane) * kRowBytes, (const unsigned char *) (W + (size_t) o * Kp) + (size_t) g * kRowBytes, kRowBytes, bar);
+        for (int j = 0; j < ng; j++) {
+            tma_bulk_g2s(dst + j * (kBM + kBO) * kRowB, act + (size_t)(g0 + j) * act_gs + (size_t) m0 * kGmGroup, kBM * kRowB, bar);
+            tma_bulk_g2s(dst + j * (kBM + kBO) * kRowB + kBM * kRowB, Wg + (size_t)(g0 + j) * w_gs + (size_t) o0 * kGmGroup, kBO * kRowB, bar);
         }
     };
-    if (warp == 0) for (int s0 = 0; s0 < kStages && s0 < total_steps; s0++) issue(s0);
+    if (tid == 0) for (int s0 = 0; s0 < kStages && s0 < total_steps; s0++) issue(s0);
 
     int step = 0;
     for (int ti = 0; ti < my_tiles; ti++) {
@@ -125,40 +133,46 @@ __global__ void __launch_bounds__(256, 2) lane_gemm_tiled_kernel(const T * __res
         float acc[64];
 #pragma unroll
         for (int i = 0; i < 64; i++) acc[i] = 0.0f;
-        for (int g = 0; g < ngroups; g++, step++) {
+        for (int sg = 0; sg < nstages; sg++, step++) {
             const int slot = step % kStages;
-            const uint32_t use = (uint32_t)(step / kStages);
-            mbar_wait(full + slot * 8, use & 1);
+            mbar_wait(full + slot * 8, (uint32_t)(step / kStages) & 1);
             const unsigned char * st = smem + (size_t) slot * kStageBytes;
-            const int steps = min(G, nsteps - g * G);          // chain steps present in this group
-            uint4 pa[8];
 #pragma unroll
-            for (int mi = 0; mi < 8; mi++) pa[mi] = *reinterpret_cast<const uint4 *>(st + (wm * 8 + mi) * kRowBytes + lane * 16);
+            for (int j = 0; j < GPS; j++) {
+                const int g = sg * GPS + j;
+                if (g < ngroups) {                            // uniform across the block
+                    const int steps = min(4, nsteps - g * 4); // chain steps present in this group
+                    const unsigned char * ga = st + j * (kBM + kBO) * kRowB + lane * sizeof(QV), * gw = ga + kBM * kRowB;
+                    QV pa[8], pw[8];
 #pragma unroll
-            for (int oh = 0; oh < 2; oh++) {
-                uint4 pw[4];
+                    for (int mi = 0; mi < 8; mi++) pa[mi] = *reinterpret_cast<const QV *>(ga + (wm * 8 + mi) * kRowB);
 #pragma unroll
-                for (int oi = 0; oi < 4; oi++) pw[oi] = *reinterpret_cast<const uint4 *>(st + (kBM + wo * 8 + oh * 4 + oi) * kRowBytes + lane * 16);
+                    for (int oi = 0; oi < 8; oi++) pw[oi] = *reinterpret_cast<const QV *>(gw + (wo * 8 + oi) * kRowB);
 #pragma unroll
-                for (int e = 0; e < G; e++) {
-                    if (e < steps) {                           // uniform across the block
-                        float wf[4];
+                    for (int c = 0; c < 4; c++) {
+                        if (c < steps) {
+                            float af[8], wf[8];
 #pragma unroll
-                        for (int oi = 0; oi < 4; oi++) wf[oi] = Cvt<T>::elem(pw[oi], e);
+                            for (int mi = 0; mi < 8; mi++) af[mi] = QuadOp<T>::elem(pa[mi], c);
 #pragma unroll
-                        for (int mi = 0; mi < 8; mi++) {
-                            const float af = Cvt<T>::elem(pa[mi], e);
+                            for (int oi = 0; oi < 8; oi++) wf[oi] = QuadOp<T>::elem(pw[oi], c);
 #pragma unroll
-                            for (int oi = 0; oi < 4; oi++) acc[mi * 8 + oh * 4 + oi] = __fmaf_rn(wf[oi], af, acc[mi * 8 + oh * 4 + oi]);
+                            for (int mi = 0; mi < 8; mi++)
+#pragma unroll
+                                for (int oi = 0; oi < 8; oi++) acc[mi * 8 + oi] = __fmaf_rn(wf[oi], af[mi], acc[mi * 8 + oi]);
                         }
                     }
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(empty + slot * 8);      // this warp is done with the slot
-            if (warp == 0 && step + kStages < total_steps) {   // refill it for k-step `step + kStages` once all 8 warps released it
-                mbar_wait(empty + slot * 8, use & 1);
-                issue(step + kStages);
+            if (lane == 0) {                                  // release the slot; the last of the 8 warps refills it
+                __threadfence_block();
+                if (atomicAdd_block(&cnt[slot], 1) == 7) {
+                    cnt[slot] = 0;
+                    __threadfence_block();
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    if (step + kStages < total_steps) issue(step + kStages);
+                }
             }
         }
         const int base = butterfly_reduce64(acc, lane);        // outputs base, base+1 of the warp tile (index = mi*8 + oi)
@@ -170,8 +184,8 @@ __global__ void __launch_bounds__(256, 2) lane_gemm_tiled_kernel(const T * __res
     }
 }
 
-void lane_gemm_tiled(const DMat & W, const void * act, int rows, const MatmulEpilogue & ep, cudaStream_t s) {
-    const size_t smem = (size_t) kStages * kStageBytes + 2 * kStages * 8 + 64;
+void lane_gemm_tiled(const DMat & W, const void * act, int act_gs, int rows, const MatmulEpilogue & ep, cudaStream_t s) {
+    const size_t smem = (size_t) kStages * kStageBytes + kStages * 8 + kStages * 4 + 64;
     static int n_sm = 0;
     if (!n_sm) {
         int dev = 0; BARK_CUDA_CHECK(cudaGetDevice(&dev));
@@ -179,10 +193,12 @@ void lane_gemm_tiled(const DMat & W, const void * act, int rows, const MatmulEpi
         BARK_CUDA_CHECK(cudaFuncSetAttribute(lane_gemm_tiled_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         BARK_CUDA_CHECK(cudaFuncSetAttribute(lane_gemm_tiled_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     }
+    if (!W.p_gm) { fprintf(stderr, "bark_b200: matrix has no group-major copy for the tiled mat-mul\n"); abort(); }
     const int n_tiles = ((W.n_out + kBO - 1) / kBO) * ((rows + kBM - 1) / kBM);
     const int grid = min(n_tiles, 2 * n_sm);                   // persistent: two CTAs per SM (registers and shared memory allow exactly that)
-    if (W.type == W_F16) BARK_LAUNCH((lane_gemm_tiled_kernel<__half>), grid, 256, smem, s, (const __half *) W.p, W.K, W.Kp, W.n_out, (const __half *) act, rows, ep);
-    else                 BARK_LAUNCH((lane_gemm_tiled_kernel<float>), grid, 256, smem, s, (const float *) W.p, W.K, W.Kp, W.n_out, (const float *) act, rows, ep);
+    const int w_gs = W.o_pad * kGmGroup;
+    if (W.type == W_F16) BARK_LAUNCH((lane_gemm_tiled_kernel<__half>), grid, 256, smem, s, (const __half *) W.p_gm, W.K, w_gs, W.n_out, (const __half *) act, act_gs, rows, ep);
+    else                 BARK_LAUNCH((lane_gemm_tiled_kernel<float>), grid, 256, smem, s, (const float *) W.p_gm, W.K, w_gs, W.n_out, (const float *) act, act_gs, rows, ep);
 }
 
 // ------------------------------------------------------------------------------------------------

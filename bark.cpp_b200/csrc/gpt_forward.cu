@@ -17,8 +17,6 @@ int64_t now_us() {
     return (int64_t) ts.tv_sec * 1000000 + ts.tv_nsec / 1000;
 }
 
-static int act_kp(const GPTModel & m, int K) { return li_padded_k(K, m.wtype == W_F16 ? 2 : 4); }
-static size_t act_elem(const GPTModel & m) { return m.wtype == W_F16 ? 2 : 4; }
 
 // transformer body shared by the causal and the fine model; x [N][E] is updated in place.
 // K/V rows of this call go to k_dst/v_dst (KV-cache slot of position n_past, or the fine model's scratch),
@@ -27,7 +25,7 @@ static void run_layers(bark_context * ctx, GPTModel & m, int N, int n_past, bool
     Workspace & ws = ctx->ws;
     cudaStream_t s = ctx->stream;
     const int E = m.n_embd, H = m.n_head;
-    const int kpE = act_kp(m, E), kp4E = act_kp(m, 4 * E);
+    const int kpE = ws.max_rows * kGmGroup, kp4E = kpE;      // group stride of the activation operands (group-major layout)
     for (int il = 0; il < m.n_layer; il++) {
         const GPTLayer & L = m.layers[(size_t) il];
         layernorm_act(ws.x, N, E, L.ln_1_g, L.ln_1_b, ws.act, m.wtype, kpE, ctx->d_ln_fallbacks, s);
@@ -39,14 +37,14 @@ static void run_layers(bark_context * ctx, GPTModel & m, int N, int n_past, bool
             k_all = k_dst = ws.kbuf; v_all = v_dst = ws.vbuf; n_kv = N;
         }
         MatmulEpilogue qkv; qkv.mode = EPI_QKV; qkv.out = ws.q; qkv.ldo = E; qkv.k_out = k_dst; qkv.v_out = v_dst;
-        lane_matmul(L.c_attn, ws.act, N, qkv, s);
+        lane_matmul(L.c_attn, ws.act, kpE, N, qkv, s);
         attention(ws.q, k_all, v_all, N, n_kv, n_past, E, H, causal, ws.scores, ws.act, m.wtype, kpE, s);
         MatmulEpilogue res; res.mode = EPI_RESID; res.out = ws.x; res.ldo = E;
-        lane_matmul(L.c_proj, ws.act, N, res, s);                                                              // + inpL
+        lane_matmul(L.c_proj, ws.act, kpE, N, res, s);                                                              // + inpL
         layernorm_act(ws.x, N, E, L.ln_2_g, L.ln_2_b, ws.act, m.wtype, kpE, ctx->d_ln_fallbacks, s);
         MatmulEpilogue ge; ge.mode = EPI_GELU_ACT; ge.act_out = ws.act2; ge.act_wt = (int) m.wtype; ge.act_Kp = kp4E; ge.gelu_tab = ctx->d_gelu_tab;
-        lane_matmul(L.fc, ws.act, N, ge, s);
-        lane_matmul(L.proj, ws.act2, N, res, s);                                                                // + inpFF
+        lane_matmul(L.fc, ws.act, kpE, N, ge, s);
+        lane_matmul(L.proj, ws.act2, kp4E, N, res, s);                                                                // + inpFF
     }
 }
 
@@ -126,10 +124,10 @@ bool gpt_eval(bark_context * ctx, GPTModel & m, const int32_t * tokens, int n, i
     gpt_embed_causal(m, ws.tok, N, *n_past, merge, ws.x, s);
     run_layers(ctx, m, N, *n_past, true);
     // final norm + lm_head on the last position only (bark.cpp:1391-1405)
-    const int kpE = act_kp(m, E);
+    const int kpE = ws.max_rows * kGmGroup;
     layernorm_act(ws.x + (size_t)(N - 1) * E, 1, E, m.ln_f_g, m.ln_f_b, ws.act, m.wtype, kpE, ctx->d_ln_fallbacks, s);
     MatmulEpilogue st; st.mode = EPI_STORE; st.out = ws.logits; st.ldo = m.n_out_vocab;
-    lane_matmul(m.lm_head[0], ws.act, 1, st, s);
+    lane_matmul(m.lm_head[0], ws.act, kpE, 1, st, s);
     ctx->last_logits = ws.logits;
     if (logits_host) {
         BARK_CUDA_CHECK(cudaMemcpyAsync(ctx->h_logits, ws.logits, (size_t) m.n_out_vocab * sizeof(float), cudaMemcpyDeviceToHost, s)); g_d2h_bytes += (size_t) m.n_out_vocab * sizeof(float);
@@ -164,10 +162,10 @@ bool fine_eval(bark_context * ctx, const int32_t * in_buffer, int nn, float * lo
     BARK_CUDA_CHECK(cudaMemcpyAsync(ws.tok, ctx->h_tok, (size_t) 8 * 1024 * sizeof(int32_t), cudaMemcpyHostToDevice, s)); g_h2d_bytes += (size_t) 8 * 1024 * sizeof(int32_t);
     gpt_embed_fine(m, ws.tok, nn, ws.x, s);
     run_layers(ctx, m, N, 0, false);
-    const int kpE = act_kp(m, E);
+    const int kpE = ws.max_rows * kGmGroup;
     layernorm_act(ws.x, N, E, m.ln_f_g, m.ln_f_b, ws.act, m.wtype, kpE, ctx->d_ln_fallbacks, s);
     MatmulEpilogue st; st.mode = EPI_STORE; st.out = ws.logits; st.ldo = m.n_out_vocab;
-    lane_matmul(m.lm_head[nn - 1], ws.act, N, st, s);                                                           // n_codes_given = 1 (bark.cpp:61,1573)
+    lane_matmul(m.lm_head[nn - 1], ws.act, kpE, N, st, s);                                                           // n_codes_given = 1 (bark.cpp:61,1573)
     ctx->last_logits = ws.logits;
     if (logits_host) {
         const size_t nb = (size_t) N * m.n_out_vocab * sizeof(float);

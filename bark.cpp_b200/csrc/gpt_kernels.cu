@@ -36,6 +36,22 @@ void permute_to_li(const void * src, void * dst, int n_out, int K, WType t, cuda
     else            { const int Kp = li_padded_k(K, 4); BARK_LAUNCH(permute_to_li_kernel<float>, 1184, 256, 0, s, (const float *) src, (float *) dst, n_out, K, Kp); }
 }
 
+// row-major [n_out][K] -> group-major [groups][o_pad][128] (common.cuh); padding rows / columns are zero
+template <typename T>
+__global__ void permute_to_gm_kernel(const T * __restrict__ src, T * __restrict__ dst, int n_out, int o_pad, int K) {
+    const size_t gs = (size_t) o_pad * kGmGroup, total = (size_t) gm_groups(K) * gs;
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x) {
+        const int g = (int)(i / gs), r = (int)(i % gs), o = r / kGmGroup, w = r % kGmGroup, v = w >> 2, c = w & 3;
+        const int k = g * kGmGroup + c * 32 + v;
+        dst[i] = (o < n_out && k < K) ? src[(size_t) o * K + k] : T(0);
+    }
+}
+
+void permute_to_gm(const void * src, void * dst, int n_out, int o_pad, int K, WType t, cudaStream_t s) {
+    if (t == W_F16) BARK_LAUNCH(permute_to_gm_kernel<__half>, 1184, 256, 0, s, (const __half *) src, (__half *) dst, n_out, o_pad, K);
+    else            BARK_LAUNCH(permute_to_gm_kernel<float>, 1184, 256, 0, s, (const float *) src, (float *) dst, n_out, o_pad, K);
+}
+
 // ------------------------------------------------------------------------------------------------
 // embeddings
 // ------------------------------------------------------------------------------------------------
@@ -143,39 +159,53 @@ void layernorm_act(const float * x, int rows, int E, const float * g, const floa
 // chain with fused multiply-adds, then the fixed tree.  Weights and activations are both in LI
 // layout, so each chain group is one coalesced 16-byte load per lane.
 // ------------------------------------------------------------------------------------------------
+template <typename T> struct Quad;       // lane v's 4 elements of one row of one group of a group-major operand
+template <> struct Quad<__half> {
+    typedef uint2 V;
+    __device__ static void unpack(const uint2 & u, float (&f)[4]) {
+        const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2 *>(&u.y));
+        f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+    }
+};
+template <> struct Quad<float> {
+    typedef uint4 V;
+    __device__ static void unpack(const uint4 & u, float (&f)[4]) { f[0] = __uint_as_float(u.x); f[1] = __uint_as_float(u.y); f[2] = __uint_as_float(u.z); f[3] = __uint_as_float(u.w); }
+};
+
+// Few-row version (rows < 16: the 1-row lm_head of a prefill, tiny test shapes).  Weights in the row-major LI layout the
+// decode kernel streams; activations in the group-major layout every producer writes.
 template <typename T, int MT>
-__global__ void __launch_bounds__(256) lane_matmul_kernel(const T * __restrict__ W, int K, int Kp, int O, const T * __restrict__ act, int M, MatmulEpilogue ep) {
-    constexpr int G = 16 / sizeof(T);
+__global__ void __launch_bounds__(256) lane_matmul_kernel(const T * __restrict__ W, int K, int Kp, int O, const T * __restrict__ act, int act_gs, int M, MatmulEpilogue ep) {
+    constexpr int G = 16 / sizeof(T), QPG = G / 4;             // quads (128-column groups of the activation) per weight group
+    typedef typename Quad<T>::V QV;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int o = blockIdx.x * 8 + warp;
     const int m0 = blockIdx.y * MT;
     if (o >= O) return;
     const int nsteps = K >> 5;
-    const int ngroups_full = nsteps / G, tail = nsteps % G;
+    const int ngroups = (nsteps + G - 1) / G;
     const uint4 * wrow = reinterpret_cast<const uint4 *>(W + (size_t) o * Kp) + lane;
-    const uint4 * arow[MT];
+    const QV * arow[MT];
     int mvalid = 0;
 #pragma unroll
-    for (int mi = 0; mi < MT; mi++) { const int m = min(m0 + mi, M - 1); arow[mi] = reinterpret_cast<const uint4 *>(act + (size_t) m * Kp) + lane; if (m0 + mi < M) mvalid = mi + 1; }
+    for (int mi = 0; mi < MT; mi++) { const int m = min(m0 + mi, M - 1); arow[mi] = reinterpret_cast<const QV *>(act + (size_t) m * kGmGroup) + lane; if (m0 + mi < M) mvalid = mi + 1; }
+    const size_t qstride = (size_t) act_gs * sizeof(T) / sizeof(QV);      // one activation group, in QV words
     float acc[MT];
 #pragma unroll
     for (int mi = 0; mi < MT; mi++) acc[mi] = 0.0f;
-    for (int g = 0; g < ngroups_full; g++) {
+    for (int g = 0; g < ngroups; g++) {
+        const int steps = min(G, nsteps - g * G);
         float w[G]; unpack16<T>(__ldg(wrow + g * 32), w);
 #pragma unroll
         for (int mi = 0; mi < MT; mi++) {
-            float a[G]; unpack16<T>(__ldg(arow[mi] + g * 32), a);
 #pragma unroll
-            for (int e = 0; e < G; e++) acc[mi] = __fmaf_rn(w[e], a[e], acc[mi]);
-        }
-    }
-    if (tail) {
-        float w[G]; unpack16<T>(__ldg(wrow + ngroups_full * 32), w);
+            for (int qd = 0; qd < QPG; qd++) {
+                if (qd * 4 < steps) {
+                    float a[4]; Quad<T>::unpack(__ldg(arow[mi] + (size_t)(g * QPG + qd) * qstride), a);
 #pragma unroll
-        for (int mi = 0; mi < MT; mi++) {
-            float a[G]; unpack16<T>(__ldg(arow[mi] + ngroups_full * 32), a);
-#pragma unroll
-            for (int e = 0; e < G; e++) if (e < tail) acc[mi] = __fmaf_rn(w[e], a[e], acc[mi]);
+                    for (int e = 0; e < 4; e++) if (qd * 4 + e < steps) acc[mi] = __fmaf_rn(w[qd * 4 + e], a[e], acc[mi]);
+                }
+            }
         }
     }
 #pragma unroll
@@ -187,20 +217,20 @@ __global__ void __launch_bounds__(256) lane_matmul_kernel(const T * __restrict__
 
 static bool use_tiled() { static const bool t = [] { const char * e = getenv("BARK_B200_GEMM"); return !(e && !strcmp(e, "simple")); }(); return t; }
 
-void lane_matmul(const DMat & W, const void * act, int rows, const MatmulEpilogue & ep, cudaStream_t s) {
+void lane_matmul(const DMat & W, const void * act, int act_gs, int rows, const MatmulEpilogue & ep, cudaStream_t s) {
     const int gx = (W.n_out + 7) / 8;
     {   // roofline annotation: algorithmic HBM bytes (weights once + operands) and flops of this mat-mul
         const double es = W.type == W_F16 ? 2.0 : 4.0;
         g_next_bytes = (double) W.n_out * W.K * es + (double) rows * (W.K * es + W.n_out * 4.0);
         g_next_flops = 2.0 * rows * (double) W.n_out * W.K;
     }
-    if (rows >= 16 && use_tiled() && (W.type == W_F16 || W.type == W_F32)) { lane_gemm_tiled(W, act, rows, ep, s); return; }
+    if (rows >= 16 && use_tiled() && (W.type == W_F16 || W.type == W_F32)) { lane_gemm_tiled(W, act, act_gs, rows, ep, s); return; }
     if (W.type == W_F16) {
-        if (rows == 1) BARK_LAUNCH((lane_matmul_kernel<__half, 1>), dim3(gx, 1), 256, 0, s, (const __half *) W.p, W.K, W.Kp, W.n_out, (const __half *) act, rows, ep);
-        else           BARK_LAUNCH((lane_matmul_kernel<__half, 8>), dim3(gx, (rows + 7) / 8), 256, 0, s, (const __half *) W.p, W.K, W.Kp, W.n_out, (const __half *) act, rows, ep);
+        if (rows == 1) BARK_LAUNCH((lane_matmul_kernel<__half, 1>), dim3(gx, 1), 256, 0, s, (const __half *) W.p, W.K, W.Kp, W.n_out, (const __half *) act, act_gs, rows, ep);
+        else           BARK_LAUNCH((lane_matmul_kernel<__half, 8>), dim3(gx, (rows + 7) / 8), 256, 0, s, (const __half *) W.p, W.K, W.Kp, W.n_out, (const __half *) act, act_gs, rows, ep);
     } else if (W.type == W_F32) {
-        if (rows == 1) BARK_LAUNCH((lane_matmul_kernel<float, 1>), dim3(gx, 1), 256, 0, s, (const float *) W.p, W.K, W.Kp, W.n_out, (const float *) act, rows, ep);
-        else           BARK_LAUNCH((lane_matmul_kernel<float, 8>), dim3(gx, (rows + 7) / 8), 256, 0, s, (const float *) W.p, W.K, W.Kp, W.n_out, (const float *) act, rows, ep);
+        if (rows == 1) BARK_LAUNCH((lane_matmul_kernel<float, 1>), dim3(gx, 1), 256, 0, s, (const float *) W.p, W.K, W.Kp, W.n_out, (const float *) act, act_gs, rows, ep);
+        else           BARK_LAUNCH((lane_matmul_kernel<float, 8>), dim3(gx, (rows + 7) / 8), 256, 0, s, (const float *) W.p, W.K, W.Kp, W.n_out, (const float *) act, act_gs, rows, ep);
     } else {
         fprintf(stderr, "bark_b200: q4_0 mul_mat is not built in this revision\n"); abort();
     }

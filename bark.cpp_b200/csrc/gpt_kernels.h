@@ -10,25 +10,27 @@ struct MatmulEpilogue {
     int mode = EPI_STORE;
     float * out = nullptr; int ldo = 0;              // STORE / RESID target ([m][ldo]); QKV: q rows with ldo = E
     float * k_out = nullptr, * v_out = nullptr;      // QKV: K/V rows (KV cache slot of the first new position, or the fine model's buffers)
-    void * act_out = nullptr; int act_wt = 0, act_Kp = 0;   // GELU_ACT: operand for the following mul_mat
+    void * act_out = nullptr; int act_wt = 0, act_Kp = 0;   // GELU_ACT: operand for the following mul_mat (act_Kp = its group stride)
     const __half * gelu_tab = nullptr;
 };
 
 void permute_to_li(const void * src_rowmajor, void * dst_li, int n_out, int K, WType t, cudaStream_t s);
+void permute_to_gm(const void * src_rowmajor, void * dst_gm, int n_out, int o_pad, int K, WType t, cudaStream_t s);
 
 void gpt_embed_causal(const GPTModel & m, const int32_t * d_tok, int N, int n_past, bool merge, float * x, cudaStream_t s);
 void gpt_embed_fine(const GPTModel & m, const int32_t * d_ids, int nn, float * x, cudaStream_t s);
 
+// `Kp` of the activation operands below is the GROUP STRIDE of the group-major layout (elements), not a row length
 void layernorm_act(const float * x, int rows, int E, const float * g, const float * b, void * act, WType wt, int Kp,
                    unsigned * fallback_counter, cudaStream_t s);
 
-void lane_matmul(const DMat & W, const void * act, int rows, const MatmulEpilogue & ep, cudaStream_t s);
+void lane_matmul(const DMat & W, const void * act, int act_gs, int rows, const MatmulEpilogue & ep, cudaStream_t s);
 
 void attention(const float * Q, const float * Kc, const float * Vc, int N, int n_kv, int n_past, int E, int H, bool causal,
                float * scores, void * act, WType wt, int Kp, cudaStream_t s);
 
 // ---- register-tiled multi-row kernels (gemm_kernels.cu) ------------------------------------------------------------
-void lane_gemm_tiled(const DMat & W, const void * act, int rows, const MatmulEpilogue & ep, cudaStream_t s);
+void lane_gemm_tiled(const DMat & W, const void * act, int act_gs, int rows, const MatmulEpilogue & ep, cudaStream_t s);
 void attention_tiled_scores(const float * Q, const float * Kc, int N, int n_kv, int n_past, int E, int H, float scale, bool causal, float * scores, cudaStream_t s);
 void attention_tiled_pv(const float * scores, const float * Vc, int N, int n_kv, int E, int H, void * act, WType wt, int Kp, cudaStream_t s);
 

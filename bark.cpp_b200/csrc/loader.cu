@@ -72,6 +72,7 @@ struct Slot {              // where a named GPT tensor goes
     enum Kind { VEC, WPE, TABLE, MATRIX } kind;
     int ne0, ne1;
     float ** vec = nullptr; void ** table = nullptr; DMat * mat = nullptr;
+    bool gm = false;        // MATRIX: also keep a group-major copy (operand of the multi-row tiled mat-mul)
 };
 
 bool load_gpt(bark_context * ctx, std::ifstream & f, GPTModel & m, const char * what) {
@@ -98,9 +99,9 @@ bool load_gpt(bark_context * ctx, std::ifstream & f, GPTModel & m, const char * 
 
     std::map<std::string, Slot> slots;                                        // same names as bark.cpp:885-938
     auto vec = [&](const std::string & n, float ** p, int len) { Slot s{Slot::VEC, len, 1}; s.vec = p; slots[n] = s; };
-    auto mat = [&](const std::string & n, DMat * p, int K, int O) { Slot s{Slot::MATRIX, K, O}; s.mat = p; slots[n] = s; };
+    auto mat = [&](const std::string & n, DMat * p, int K, int O, bool gm) { Slot s{Slot::MATRIX, K, O}; s.mat = p; s.gm = gm; slots[n] = s; };
     for (int i = 0; i < m.n_wtes; i++) { Slot s{Slot::TABLE, E, m.n_in_vocab}; s.table = &m.wte[i]; slots["model/wte/" + std::to_string(i)] = s; }
-    for (int i = 0; i < m.n_lm_heads; i++) mat("model/lm_head/" + std::to_string(i), &m.lm_head[i], E, m.n_out_vocab);
+    for (int i = 0; i < m.n_lm_heads; i++) mat("model/lm_head/" + std::to_string(i), &m.lm_head[i], E, m.n_out_vocab, !causal);   // causal models apply lm_head to one row only
     { Slot s{Slot::WPE, E, m.block_size}; s.vec = &m.wpe; slots["model/wpe"] = s; }
     vec("model/ln_f/g", &m.ln_f_g, E);
     if (m.bias) vec("model/ln_f/b", &m.ln_f_b, E);
@@ -109,8 +110,8 @@ bool load_gpt(bark_context * ctx, std::ifstream & f, GPTModel & m, const char * 
         GPTLayer & L = m.layers[(size_t) l];
         vec(p + "/ln_1/g", &L.ln_1_g, E); vec(p + "/ln_2/g", &L.ln_2_g, E);
         if (m.bias) { vec(p + "/ln_1/b", &L.ln_1_b, E); vec(p + "/ln_2/b", &L.ln_2_b, E); }
-        mat(p + "/attn/c_attn/w", &L.c_attn, E, 3 * E); mat(p + "/attn/c_proj/w", &L.c_proj, E, E);
-        mat(p + "/mlp/c_fc/w", &L.fc, E, 4 * E);        mat(p + "/mlp/c_proj/w", &L.proj, 4 * E, E);
+        mat(p + "/attn/c_attn/w", &L.c_attn, E, 3 * E, true); mat(p + "/attn/c_proj/w", &L.c_proj, E, E, true);
+        mat(p + "/mlp/c_fc/w", &L.fc, E, 4 * E, true);        mat(p + "/mlp/c_proj/w", &L.proj, 4 * E, E, true);
     }
 
     int32_t n_tensors = 0;
@@ -138,6 +139,12 @@ bool load_gpt(bark_context * ctx, std::ifstream & f, GPTModel & m, const char * 
             d.n_out = s.ne1; d.K = s.ne0; d.type = m.wtype; d.Kp = li_padded_k(d.K, m.wtype == W_F16 ? 2 : 4);
             d.p = ctx_alloc(ctx, (size_t) d.n_out * d.Kp * (m.wtype == W_F16 ? 2 : 4));
             permute_to_li(raw, d.p, d.n_out, d.K, m.wtype, ctx->stream);
+            if (s.gm) {                                  // second copy for the multi-row tiled mat-mul (group-major, rows padded to 16)
+                d.o_pad = (d.n_out + 15) / 16 * 16;
+                const size_t gm_bytes = (size_t) gm_groups(d.K) * d.o_pad * kGmGroup * (m.wtype == W_F16 ? 2 : 4);
+                d.p_gm = ctx_alloc(ctx, gm_bytes);
+                permute_to_gm(raw, d.p_gm, d.n_out, d.o_pad, d.K, m.wtype, ctx->stream);
+            }
             BARK_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
             BARK_CUDA_CHECK(cudaFree(raw));
         } else {
