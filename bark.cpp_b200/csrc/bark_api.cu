@@ -300,6 +300,7 @@ bool run_coarse(bark_context * ctx) {
     std::vector<int32_t> out; out.reserve((size_t) n_steps);
     const bool dev = ctx->sample_on_device && P.sliding_window_size <= 1024 && P.semantic_vocab_size + 2 * P.codebook_size <= m.n_out_vocab;
     int step = 0;
+    std::vector<int32_t> kv_ids;                                                  // ids whose K/V rows the coarse cache holds, by position
     for (int w = 0; w < n_windows; w++) {
         const int semantic_idx = (int) roundf(step / stc_ratio);
         // window input: semantic tokens from the history start TO THE END, cut/padded to 256 (quirk D.5), infer token, coarse history
@@ -308,16 +309,31 @@ bool run_coarse(bark_context * ctx) {
         in.push_back(P.coarse_infer_token);
         const size_t hist = std::min<size_t>((size_t) P.max_coarse_history, out.size());
         in.insert(in.end(), out.end() - (std::ptrdiff_t) hist, out.end());
+        // Prefix reuse.  The reference re-evaluates the whole window prompt from n_past = 0 (bark.cpp:1795-1812).  Every row of
+        // that evaluation depends only on the ids at positions <= its own (causal mask; each mat-mul / soft_max row is computed
+        // independently of the batch it is in), so a position whose id prefix is unchanged has bit-identical K/V rows to the ones
+        // already in the cache from the previous window.  While the prompt is [same 256 semantic ids, infer token, ALL coarse
+        // history] (clips up to max_coarse_history = 630 coarse tokens / 209 semantic tokens) that is every position but the
+        // last one: the window start costs one decode step instead of a <= 887-row prefill.  kv_ids records what the cache holds.
         int n_past = 0;
+        if (ctx->kv_reuse) {
+            size_t common = 0;
+            while (common < kv_ids.size() && common + 1 < in.size() && kv_ids[common] == in[common]) common++;   // keep >= 1 id to evaluate
+            n_past = (int) common;
+            ctx->n_kv_reused += common;
+        }
+        std::vector<int32_t> in_eval(in.begin() + n_past, in.end());
+        kv_ids = in;
         if (dev) {
             // only logits [lo, lo + codebook_size) are ever looked at in this stage (bark.cpp:1829-1833): the window alternates with the codebook
             const int nw = std::min(P.sliding_window_size, n_steps - step), step0 = step;
             std::vector<int32_t> tok((size_t) nw);
             auto lo_of = [&](int j) { return P.semantic_vocab_size + (((step0 + j) % P.n_coarse_codebooks == 0) ? 0 : 1) * P.codebook_size; };
-            if (!run_chain(ctx, m, in, false, &n_past, nw, lo_of, P.codebook_size, P.temp, tok.data(), nullptr)) { fprintf(stderr, "%s: Could not generate token\n", __func__); return false; }
+            if (!run_chain(ctx, m, in_eval, false, &n_past, nw, lo_of, P.codebook_size, P.temp, tok.data(), nullptr)) { fprintf(stderr, "%s: Could not generate token\n", __func__); return false; }
             for (int j = 0; j < nw; j++) {
                 if (P.progress_callback) P.progress_callback(ctx, COARSE, 100 * (step + 1) / n_steps, P.progress_callback_user_data);
                 out.push_back(tok[(size_t) j]); step++;
+                if (j + 1 < nw) kv_ids.push_back(tok[(size_t) j]);      // the window's last sample is never evaluated
             }
             continue;
         }
@@ -325,9 +341,10 @@ bool run_coarse(bark_context * ctx) {
             if (P.progress_callback) P.progress_callback(ctx, COARSE, 100 * (step + 1) / n_steps, P.progress_callback_user_data);
             const bool major = step % P.n_coarse_codebooks == 0;
             const int lo = P.semantic_vocab_size + (major ? 0 : 1) * P.codebook_size;
-            if (!gpt_eval(ctx, m, in.data(), (int) in.size(), &n_past, false, logits.data(), lo, lo + P.codebook_size)) { fprintf(stderr, "%s: Could not generate token\n", __func__); return false; }
+            if (j > 0) kv_ids.push_back(in_eval[0]);
+            if (!gpt_eval(ctx, m, in_eval.data(), (int) in_eval.size(), &n_past, false, logits.data(), lo, lo + P.codebook_size)) { fprintf(stderr, "%s: Could not generate token\n", __func__); return false; }
             const int32_t next = lo + sample_token(ctx, m, logits.data() + lo, P.codebook_size, P.temp, nullptr);
-            in.assign(1, next);
+            in_eval.assign(1, next);
             out.push_back(next);
             step++;
         }
@@ -468,6 +485,7 @@ extern "C" struct bark_context * bark_load_model(const char * model_path, struct
     { const char * e = getenv("BARK_B200_DECODE_CTAS"); if (e && atoi(e) >= 64 && atoi(e) <= ctx->n_sm) ctx->n_sm = atoi(e); }   // experiment knob: CTAs of the persistent decode kernel
     { const char * e = getenv("BARK_B200_SAMPLE_FLAG_EVERY"); ctx->debug_flag_every = e ? atoi(e) : 0; }
     { const char * e = getenv("BARK_B200_SAMPLE"); ctx->sample_on_device = !(e && !strcmp(e, "host")); }      // "host": read logits back and sample on the CPU (A-B)
+    { const char * e = getenv("BARK_B200_KV_REUSE"); ctx->kv_reuse = !(e && !strcmp(e, "0")); }              // "0": re-prefill every coarse window like the reference (A-B)
     { const char * e = getenv("BARK_B200_DECODE"); ctx->use_decode_kernel = !(e && !strcmp(e, "multi")); }   // "multi": one kernel per op (debug / A-B)
     ctx->params = params;
     BARK_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
@@ -477,7 +495,7 @@ extern "C" struct bark_context * bark_load_model(const char * model_path, struct
         return nullptr;
     }
     alloc_workspace(ctx);
-    if (getenv("BARK_B200_DECODE_TIMING")) { ctx->d_timing = (unsigned long long *) ctx_alloc(ctx, 256 * 16 * 8); BARK_CUDA_CHECK(cudaMemset(ctx->d_timing, 0, 256 * 16 * 8)); }
+    if (getenv("BARK_B200_DECODE_TIMING")) { ctx->d_timing = (unsigned long long *) ctx_alloc(ctx, 256 * 32 * 8); BARK_CUDA_CHECK(cudaMemset(ctx->d_timing, 0, 256 * 32 * 8)); }
     BARK_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     ctx->rng = std::mt19937(seed);
     ctx->stats.t_load_us = now_us() - t0;
@@ -637,7 +655,7 @@ extern "C" unsigned bark_b200_layernorm_fallbacks(struct bark_context * ctx) {
 }
 extern "C" int bark_b200_decode_timing(struct bark_context * ctx, unsigned long long * out, int n) {
     if (!ctx || !ctx->d_timing || !out) return 0;
-    BARK_CUDA_CHECK(cudaMemcpy(out, ctx->d_timing, sizeof(unsigned long long) * (size_t) std::min(n, 256 * 16), cudaMemcpyDeviceToHost));
-    return std::min(n, 256 * 16);
+    BARK_CUDA_CHECK(cudaMemcpy(out, ctx->d_timing, sizeof(unsigned long long) * (size_t) std::min(n, 256 * 32), cudaMemcpyDeviceToHost));
+    return std::min(n, 256 * 32);
 }
 extern "C" const char * bark_b200_version(void) { return "bark_b200 r1 (sm_100a, parity path)"; }

@@ -73,6 +73,19 @@ __device__ __forceinline__ int act_index(int k) {
     return (((g << 1) + (e >> 2)) * 32 + v) * 4 + (e & 3);
 }
 
+// debug stamps (BARK_B200_DECODE_TIMING=1): thread 0 of CTA 0 stamps every layer (rows 0..L-1 of the buffer), thread 0 of
+// every CTA stamps layer 5 (rows 64 + cta); 32 slots per row, %globaltimer nanoseconds.  s_tim is null in normal runs.
+__shared__ unsigned long long * s_tim;
+__shared__ int s_tim_layer;
+__device__ __forceinline__ void tstamp(int i) {
+    if (threadIdx.x == 0 && s_tim) {
+        unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        const int layer = s_tim_layer;
+        if (blockIdx.x == 0) s_tim[layer * 32 + i] = t;
+        if (layer == 5) s_tim[(64 + blockIdx.x) * 32 + i] = t;
+    }
+}
+
 // Fetch a published vector into shared memory.  Every thread takes entries tid, tid + 512, ... (n <= MAXJ * 512): all loads
 // go out together, stragglers are re-polled.  Deliberately NOT inlined: the kernel lives or dies by its instruction-cache
 // footprint (a 100 KB body re-fetched from L2 every layer cost 5-10x), so shared pieces are real calls.
@@ -112,7 +125,7 @@ __device__ __forceinline__ double approx_rcp(double x) {
 // activation operand (optionally f16-rounded) in two-plane LI order.  Block-wide: each thread owns <= 2 elements.
 template <bool ROUND16>
 __device__ __noinline__ void block_layernorm(const float * xs, int E, double inv_E, const float * __restrict__ g, const float * __restrict__ b, float * act,
-                                             double * scratch, float * bc, unsigned * fallback_counter) {
+                                             double * scratch, float * bc, unsigned * fallback_counter, int sb) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float * fscratch = reinterpret_cast<float *>(scratch + kWarps);
     const int i0 = tid, i1 = tid + kThreads;
@@ -149,6 +162,7 @@ __device__ __noinline__ void block_layernorm(const float * xs, int E, double inv
     }
     __syncthreads();
     const float mean = bc[0];
+    tstamp(sb);
     // ---- variance ----
     const float v0 = __fsub_rn(x0, mean), v1 = __fsub_rn(x1, mean);
     double s2 = (h0 ? (double) __fmul_rn(v0, v0) : 0.0) + (h1 ? (double) __fmul_rn(v1, v1) : 0.0);
@@ -283,7 +297,7 @@ __device__ __forceinline__ void stage_rows(PhaseCtx & pc, int phase) {
 // This warp's rows of `phase`: lane-order dot against the shared activation operand; outputs are published with epoch
 // `otag` (or stored, for the logits).  Then the rows of the next phase start streaming in.  No block-wide synchronisation.
 template <typename WT>
-__device__ __noinline__ void run_phase(PhaseCtx & pc, int phase, int ep, int layer, uint32_t otag) {
+__device__ __noinline__ void run_phase(PhaseCtx & pc, int phase, int ep, int layer, uint32_t otag, int sb) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const PhaseSched p = pc.sched[phase];
     const int E = pc.E;
@@ -291,6 +305,7 @@ __device__ __noinline__ void run_phase(PhaseCtx & pc, int phase, int ep, int lay
     const bool staged = (pc.staged_mask >> half) & 1;
     cp_async_wait_all_but_newest();                           // the group of `phase` is complete; `phase + 1` may still be in flight
     __syncwarp();
+    tstamp(sb);
     int j = 0;
     for (int r = p.r0 + warp; r < p.r1; r += kWarps, j++) {
         const unsigned char * row = staged ? pc.wslot + half * kHalfSlotBytes + (size_t) j * p.row_bytes : p.w + (size_t) r * p.row_bytes;
@@ -313,7 +328,9 @@ __device__ __noinline__ void run_phase(PhaseCtx & pc, int phase, int ep, int lay
         }
     }
     __syncwarp();                                             // all lanes are done reading this half
+    tstamp(sb + 1);
     stage_rows(pc, phase + 2);
+    tstamp(sb + 2);
 }
 
 }  // namespace
@@ -371,13 +388,8 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
     uint32_t tag = A.tag_base;                               // unique epoch per exchange; the host advances the base by 6 * L per launch
     const float scale = 1.0f / sqrtf((float) E / (float) H);
     const double inv_E = A.inv_E;
-    auto stamp = [&](int layer, int i) {
-        if (A.timing && tid == 0 && (blockIdx.x == 0 || layer == 5)) {      // CTA 0: every layer; all CTAs: layer 5 (rows 64.. of the buffer)
-            unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-            if (blockIdx.x == 0) A.timing[layer * 16 + i] = t;
-            if (layer == 5) A.timing[(64 + blockIdx.x) * 16 + i] = t;
-        }
-    };
+    if (tid == 0) { s_tim = A.timing; s_tim_layer = 0; }
+    __syncthreads();
 
     const int parts = D >> 4;                                // P3: CTAs per head
     const bool pv_cta = (int) blockIdx.x < H * parts;
@@ -389,11 +401,12 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
         const DecodeLayerVec lv = A.layer_vecs[il];
         const uint32_t t_qkv = tag + 1, t_sc = tag + 2, t_att = tag + 3, t_x1 = tag + 4, t_ff = tag + 5, t_x2 = tag + 6;
         tag += 6;
-        stamp(il, 12);
+        if (tid == 0) s_tim_layer = il;                       // (tid 0 is the only reader)
+        tstamp(0);
         // ---- P1: LN1 -> QKV ----
-        block_layernorm<kRound>(xs, E, inv_E, lv.ln_1_g, lv.ln_1_b, act, red, bc, A.ln_fallbacks);
-        run_phase<WT>(pc, 4 * il + 0, EP_QKV, il, t_qkv);
-        stamp(il, 0);
+        block_layernorm<kRound>(xs, E, inv_E, lv.ln_1_g, lv.ln_1_b, act, red, bc, A.ln_fallbacks, 1);
+        tstamp(2);
+        run_phase<WT>(pc, 4 * il + 0, EP_QKV, il, t_qkv, 3);
 
         // ---- P2: scores.  K rows of older positions are fetched before q arrives. ----
         {
@@ -411,8 +424,9 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
                     }
                 }
             }
+            tstamp(6);
             consume_to_smem<2>(gq, E, t_qkv, qs, SINK_PLAIN);
-            stamp(il, 1);
+            tstamp(7);
 #pragma unroll
             for (int i = 0; i < kMaxTasks; i++) {
                 const int t = gw + i * nw;
@@ -441,7 +455,7 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
                 if (lane == 0) publish(gscores + (size_t) h * ctx + k, __fmul_rn(r, scale), t_sc);
             }
         }
-        stamp(il, 2);
+        tstamp(8);
 
         // ---- P3: soft_max + P.V, one CTA per (head, 16 columns of the head) ----
         if (pv_cta) {
@@ -455,9 +469,11 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
             // ... and one element of the leftover rows k = np + v (parked in shared memory later; `act` is idle in this phase)
             const float vl = (np + v < n_past) ? __ldcg(Vc + (size_t)(np + v) * E + dd) : 0.0f;
             const float v_new = consume1(gv + col0 + dd, t_qkv);     // value row of the new position
+            tstamp(9);
             float * p = qs;                                          // scores row -> probabilities
             float * csum = part + 32 * 16;
             consume_to_smem<2>(gscores + (size_t) h * ctx, n_kv, t_sc, p, SINK_PLAIN);
+            tstamp(10);
             float mx = __int_as_float(0xff800000);
 #pragma unroll 1
             for (int i = tid; i < n_kv; i += kThreads) mx = fmaxf(mx, p[i]);
@@ -469,6 +485,7 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
             mx = fred[0];
 #pragma unroll
             for (int w = 1; w < kWarps; w++) mx = fmaxf(mx, fred[w]);
+            tstamp(11);
             const int nchunks = n_kv >> 3;
             if (tid < nchunks) {
                 float * pc8 = p + tid * 8;
@@ -478,6 +495,7 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
                 csum[tid] = __fadd_rn(__fadd_rn(t0, t2), __fadd_rn(t1, t3));
             }
             __syncthreads();
+            tstamp(12);
             // sum = sequential double accumulation of the chunk sums, then the libm-expf tail (ggml.c:2845-2888).  All terms are
             // positive, so a tree sum S brackets the sequential one within +-2n*2^-53*S; if 1/sum rounds to the same float at both
             // ends of the bracket the order cannot matter, else replay sequentially.  Done by warp 0, broadcast through bc[2].
@@ -510,10 +528,12 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
                 }
             }
             __syncthreads();
+            tstamp(13);
             const float sc_f = bc[2];
 #pragma unroll 1
             for (int i = tid; i < n_kv; i += kThreads) p[i] = __fmul_rn(p[i], sc_f);
             __syncthreads();
+            tstamp(14);
             float acc = 0.0f;
 #pragma unroll
             for (int c = 0; c < 32; c++) {
@@ -523,6 +543,7 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
             part[v * 16 + dd] = acc;
             act[v * 16 + dd] = vl;
             __syncthreads();
+            tstamp(15);
             if (tid < 16) {
                 float a32[32];
 #pragma unroll
@@ -541,34 +562,35 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
             }
             __syncthreads();                                     // `act` / `qs` are reused by the next phase
         }
-        stamp(il, 4);
+        tstamp(16);
 
         // ---- P4: c_proj + residual ----
         consume_to_smem<2>(gatt, E, t_att, act, kSinkAct);
-        stamp(il, 5);
-        run_phase<WT>(pc, 4 * il + 1, EP_RESID, il, t_x1);
-        stamp(il, 6);
+        tstamp(17);
+        run_phase<WT>(pc, 4 * il + 1, EP_RESID, il, t_x1, 18);
 
         // ---- P5: LN2 -> c_fc -> GELU ----
         consume_to_smem<2>(gx, E, t_x1, xs, SINK_PLAIN);
-        stamp(il, 7);
-        block_layernorm<kRound>(xs, E, inv_E, lv.ln_2_g, lv.ln_2_b, act, red, bc, A.ln_fallbacks);
-        run_phase<WT>(pc, 4 * il + 2, EP_GELU, il, t_ff);
+        tstamp(21);
+        block_layernorm<kRound>(xs, E, inv_E, lv.ln_2_g, lv.ln_2_b, act, red, bc, A.ln_fallbacks, 22);
+        tstamp(23);
+        run_phase<WT>(pc, 4 * il + 2, EP_GELU, il, t_ff, 24);
         __syncthreads();                                         // the ff vector lands in `act`, which slower warps may still be reading
-        stamp(il, 8);
+        tstamp(27);
 
         // ---- P6: mlp/c_proj + residual ----
         consume_to_smem<8>(gff, 4 * E, t_ff, act, kSinkAct);
-        stamp(il, 9);
-        run_phase<WT>(pc, 4 * il + 3, EP_RESID, il, t_x2);
-        stamp(il, 10);
+        tstamp(28);
+        run_phase<WT>(pc, 4 * il + 3, EP_RESID, il, t_x2, 29);
 
         consume_to_smem<2>(gx, E, t_x2, xs, SINK_PLAIN);
-        stamp(il, 11);
     }
+    if (tid == 0) s_tim_layer = L;                            // row L: start of the final norm
     // ---- final norm + lm_head window ----
-    block_layernorm<kRound>(xs, E, inv_E, A.ln_f_g, A.ln_f_b, act, red, bc, A.ln_fallbacks);
-    run_phase<WT>(pc, 4 * L, EP_LOGITS, 0, 0);
+    tstamp(0);
+    block_layernorm<kRound>(xs, E, inv_E, A.ln_f_g, A.ln_f_b, act, red, bc, A.ln_fallbacks, 1);
+    tstamp(2);
+    run_phase<WT>(pc, 4 * L, EP_LOGITS, 0, 0, 3);
 }
 
 static size_t decode_smem_bytes() { return (size_t) SmemLayout::total + 128; }

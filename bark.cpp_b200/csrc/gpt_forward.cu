@@ -99,8 +99,7 @@ bool gpt_eval(bark_context * ctx, GPTModel & m, const int32_t * tokens, int n, i
     int N = n;
     bool merge = false;
     if (lm_hi <= 0 || lm_hi > m.n_out_vocab || lm_lo < 0 || lm_lo >= lm_hi) { lm_lo = 0; lm_hi = m.n_out_vocab; }
-    if (*n_past > 0) {
-        if (N != 1) { fprintf(stderr, "%s: decoding expects one token per step (got %d)\n", __func__, N); return false; }
+    if (*n_past > 0 && N == 1) {
         if (ctx->use_decode_kernel && *n_past + 1 <= m.block_size && tokens[0] >= 0 && tokens[0] < m.n_in_vocab) {
             decode_step(ctx, m, tokens[0], nullptr, *n_past, lm_lo, lm_hi);
             ctx->last_logits = m.glogits;
@@ -114,7 +113,7 @@ bool gpt_eval(bark_context * ctx, GPTModel & m, const int32_t * tokens, int n, i
             m.t_predict_us += now_us() - t0;
             return true;
         }
-    } else if (merge_ctx) {
+    } else if (merge_ctx && *n_past == 0) {
         if (N != 513) { fprintf(stderr, "%s: merged prompt must hold 256+256+1 ids (got %d)\n", __func__, N); return false; }
         N = 257; merge = true;                                                                                  // bark.cpp:1230-1233
     }

@@ -46,7 +46,7 @@ struct DecodeArgs {
     unsigned long long * gx, * gq, * gk, * gv, * gatt, * gff, * gscores;
     float * logits;
     unsigned tag_base; unsigned * ln_fallbacks;
-    unsigned long long * timing;         // optional [L][16] globaltimer stamps of CTA 0 (debug)
+    unsigned long long * timing;         // optional [256][32] globaltimer stamps (debug, decode_kernels.cu tstamp)
     int E, H, L, block_size, n_past, token, lm_lo, lm_hi;
     const int32_t * token_ptr; int n_vocab_in;   // token_ptr != null: read the input token from device memory (written by sample_rows_kernel), clamped to the vocabulary
     double inv_E;                        // 1.0 / E (double), for the division-free LayerNorm decision

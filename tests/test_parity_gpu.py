@@ -45,6 +45,15 @@ def test_teacher_forced_logits_bit_exact(pkg, orc, weights_file, config, ftype):
             lo, po = o.gpt_eval(1, toks, po, False)
             assert np.array_equal(bits(lg), bits(lo)), f"coarse step {step} (n_past {po}): {int((lg != lo).sum())} logits differ, max {np.abs(lg - lo).max():.3e}"
             toks = np.array([10000 + int(np.argmax(lo[10000:12048]))], np.int32)
+        # a multi-row evaluation on top of a filled cache (what a coarse window start becomes when only part of its prompt is
+        # cached): rows are batch-independent, so it must equal the oracle's from-scratch evaluation of the whole sequence
+        full = np.concatenate([rng.integers(0, 10000, 256), [12050], rng.integers(10000, 12048, 75)]).astype(np.int32)
+        for cut in (257, 300, 331):
+            _, pg = b.gpt_eval(1, full[:cut], 0, False)
+            lg, pg = b.gpt_eval(1, full[cut:], pg, False)
+            lo, po = o.gpt_eval(1, full, 0, False)
+            assert pg == po == full.size
+            assert np.array_equal(bits(lg), bits(lo)), f"suffix evaluation after {cut} cached rows: {int((lg != lo).sum())} logits differ"
 
 
 @pytest.mark.parametrize("config,ftype", [("tiny", "f16"), ("mini", "f32")])
@@ -101,8 +110,9 @@ def test_sampler_paths_agree(pkg, weights_file, monkeypatch):
     same RNG state afterwards (second clip on the same context)."""
     path = weights_file("mini", "f16")
     runs = []
-    for env in ({}, {"BARK_B200_SAMPLE_FLAG_EVERY": "5"}, {"BARK_B200_SAMPLE": "host"}, {"BARK_B200_DECODE": "multi"}):
-        for k in ("BARK_B200_SAMPLE_FLAG_EVERY", "BARK_B200_SAMPLE", "BARK_B200_DECODE"):
+    for env in ({}, {"BARK_B200_SAMPLE_FLAG_EVERY": "5"}, {"BARK_B200_SAMPLE": "host"}, {"BARK_B200_DECODE": "multi"}, {"BARK_B200_KV_REUSE": "0"},
+                {"BARK_B200_KV_REUSE": "0", "BARK_B200_SAMPLE": "host"}):
+        for k in ("BARK_B200_SAMPLE_FLAG_EVERY", "BARK_B200_SAMPLE", "BARK_B200_DECODE", "BARK_B200_KV_REUSE"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -114,6 +124,23 @@ def test_sampler_paths_agree(pkg, weights_file, monkeypatch):
         for i in range(3):
             assert np.array_equal(t1[i], runs[0][1][i]) and np.array_equal(t2[i], runs[0][3][i])
         assert np.array_equal(bits(a1), bits(runs[0][0])) and np.array_equal(bits(a2), bits(runs[0][2]))
+
+
+def test_coarse_prefix_reuse_on_a_long_clip(pkg, weights_file, monkeypatch):
+    """230 semantic tokens -> 690 coarse steps in 12 windows: the semantic window start moves (semantic_idx > 209) and the
+    coarse history saturates at 630, so window prompts stop being extensions of the cache.  Prefix reuse (default) must give
+    the tokens of the reference's full re-prefill (BARK_B200_KV_REUSE=0; that path is the one pinned against the oracle)."""
+    path = weights_file("tiny", "f16")
+    runs = []
+    for reuse in ("1", "0"):
+        monkeypatch.setenv("BARK_B200_KV_REUSE", reuse)
+        with pkg.Bark(path, seed=5, n_steps_text_encoder=230) as b:
+            a = b.generate("a long clip")
+            runs.append((a, [b.tokens(i).copy() for i in range(3)]))
+    assert runs[0][1][1].shape[0] == 345
+    for i in range(3):
+        assert np.array_equal(runs[0][1][i], runs[1][1][i])
+    assert np.array_equal(bits(runs[0][0]), bits(runs[1][0]))
 
 
 def test_semantic_early_stop_inside_a_batch(pkg, orc, weights_file):
