@@ -301,6 +301,7 @@ bool run_coarse(bark_context * ctx) {
     const bool dev = ctx->sample_on_device && P.sliding_window_size <= 1024 && P.semantic_vocab_size + 2 * P.codebook_size <= m.n_out_vocab;
     int step = 0;
     std::vector<int32_t> kv_ids;                                                  // ids whose K/V rows the coarse cache holds, by position
+    size_t kv_canon = 0;                                                          // leading rows of the cache known to be canonical (see below)
     for (int w = 0; w < n_windows; w++) {
         const int semantic_idx = (int) roundf(step / stc_ratio);
         // window input: semantic tokens from the history start TO THE END, cut/padded to 256 (quirk D.5), infer token, coarse history
@@ -309,19 +310,22 @@ bool run_coarse(bark_context * ctx) {
         in.push_back(P.coarse_infer_token);
         const size_t hist = std::min<size_t>((size_t) P.max_coarse_history, out.size());
         in.insert(in.end(), out.end() - (std::ptrdiff_t) hist, out.end());
-        // Prefix reuse.  The reference re-evaluates the whole window prompt from n_past = 0 (bark.cpp:1795-1812).  Every row of
-        // that evaluation depends only on the ids at positions <= its own (causal mask; each mat-mul / soft_max row is computed
-        // independently of the batch it is in), so a position whose id prefix is unchanged has bit-identical K/V rows to the ones
-        // already in the cache from the previous window.  While the prompt is [same 256 semantic ids, infer token, ALL coarse
-        // history] (clips up to max_coarse_history = 630 coarse tokens / 209 semantic tokens) that is every position but the
-        // last one: the window start costs one decode step instead of a <= 887-row prefill.  kv_ids records what the cache holds.
+        // Prefix reuse.  The reference re-evaluates the whole window prompt from n_past = 0 (bark.cpp:1795-1812).  Row p of
+        // that evaluation depends on the ids at positions <= p and on the call's n_kv — but only through WHERE the summation
+        // structure is cut: soft_max switches from the 8-wide polynomial to libm expf at column n_kv & ~7 and the P.V dot
+        // from lane chains to the scalar leftovers at column n_kv & ~31 (ggml.c:2845-2888, 2144-2170).  For p < (n_kv & ~31)
+        // every column beyond the cut is masked (an exact zero), so the row has ONE value whatever the call's n_kv:
+        // "canonical".  Rows [0, n_kv & ~31) of every evaluation here are canonical (by induction over the layers), so a
+        // window whose prompt starts with the ids the cache holds re-uses the canonical rows and evaluates the rest in one
+        // call with the reference's own n_kv — bit-identical K/V rows and logits, 60-91 rows instead of 257-887.
         int n_past = 0;
         if (ctx->kv_reuse) {
             size_t common = 0;
-            while (common < kv_ids.size() && common + 1 < in.size() && kv_ids[common] == in[common]) common++;   // keep >= 1 id to evaluate
-            n_past = (int) common;
-            ctx->n_kv_reused += common;
+            while (common < kv_ids.size() && common < in.size() && kv_ids[common] == in[common]) common++;
+            n_past = (int) std::min({common, kv_canon, in.size() & ~(size_t) 31, in.size() - 1});       // keep >= 1 id to evaluate
+            ctx->n_kv_reused += (unsigned long long) n_past;
         }
+        kv_canon = std::max((size_t) n_past, in.size() & ~(size_t) 31);
         std::vector<int32_t> in_eval(in.begin() + n_past, in.end());
         kv_ids = in;
         if (dev) {

@@ -5,15 +5,19 @@
 //
 // One CTA per SM, 512 threads.
 //  * Weights are a pure stream: each CTA owns a contiguous row range of every matrix (lane-interleaved rows), each warp a
-//    fixed subset of those rows.  As soon as a warp finishes a phase it starts cp.async copies of its rows of the NEXT
-//    phase into a private shared-memory staging area, so HBM latency hides behind the exchange + LayerNorm of that phase
-//    and no block-wide barrier is needed around the weight stream.  (A TMA bulk-copy ring was measured first: the
-//    elected thread's expect_tx + UBLKCP issue cost 1.3 us per phase on the critical path.)
+//    contiguous slice of that range.  As soon as a warp finishes a phase, its lane 0 issues ONE TMA bulk copy
+//    (cp.async.bulk + a per-warp mbarrier) of its rows of the phase after next into a private shared-memory staging area, so
+//    HBM latency hides behind two phases and no block-wide barrier surrounds the weight stream.  (Measured before: a
+//    CTA-wide TMA ring fed by one elected thread cost 1.3 us per phase on the critical path; per-lane 16-byte cp.async cost
+//    0.5-0.9 us of issue time per phase with 2 us tails.)  The copies carry an L2 evict-first policy: 188 MB of weights per
+//    token would otherwise flush the KV cache, the exchange words, local memory and the kernel's own code out of the 126 MB
+//    L2 on every token — the source of sporadic 2-4 us stragglers that every other CTA then waits for.
 //  * Activations cross CTAs as TAGGED words: every exchanged float travels in one 8-byte {value, epoch} store; consumers
 //    spin on the words they need until the epoch matches.  Data and "ready" flag arrive in the same L2 transaction, so a
 //    grid-wide dependency costs one store->load latency instead of store + fence + atomic + poll + load (a classic
 //    barrier measured 1.5-2 us here; 6 per layer).  Epochs are unique per use and never reset.
 //  * KV rows of older positions are prefetched into registers BEFORE waiting for q / the probabilities.
+//  * Nothing the phases need lives in local memory: block-wide state is in static shared memory (BlockCtx).
 //
 // Phases of a layer (each ends by publishing tagged outputs, the next begins by consuming them):
 //   P1  LN1 -> QKV rows          -> q, k_new, v_new (+ K/V appended to the f32 KV cache for later tokens)
@@ -40,16 +44,34 @@ struct SmemLayout {
     static constexpr int x = act + 4096 * 4;                        // residual stream, up to 1024 floats
     static constexpr int q = x + 1024 * 4;                          // q vector / probabilities row, up to 1024 floats
     static constexpr int part = q + 1024 * 4;                       // P.V lane partials [32][16] + chunk sums [128]
-    static constexpr int red = part + (32 * 16 + 128) * 4;          // reduction scratch: 2 x 16 doubles + 4 broadcast slots
-    static constexpr int sched = red + (2 * kWarps + 4) * 8;        // per-CTA row ranges: kMaxPhases x PhaseSched
+    static constexpr int red = part + (32 * 16 + 128) * 4;          // reduction scratch: 16 doubles + 16 floats + 16 doubles + 4 broadcast slots
+    static constexpr int sched = red + (kWarps + kWarps / 2 + kWarps + 4) * 8;   // per-CTA row ranges: kMaxPhases x PhaseSched
     static constexpr int total = sched + 128 * 32;
 };
 
 // ---- PTX helpers -------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void * p) { return (uint32_t) __cvta_generic_to_shared(p); }
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void * src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory"); }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all_but_newest() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+// one bulk copy global -> shared, completion counted on `bar`, L2 evict-first (the weight stream is read once per token)
+__device__ __forceinline__ void tma_bulk_g2s_stream(uint32_t dst, const void * src, uint32_t bytes, uint32_t bar, unsigned long long policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
+}
+__device__ __forceinline__ unsigned long long l2_evict_first_policy() {
+    unsigned long long pol; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
 
 // ---- tagged exchange -------------------------------------------------------------------------------------------------
 typedef unsigned long long tagged_t;                                // low 32 bits: float payload, high 32 bits: epoch
@@ -123,11 +145,16 @@ __device__ __forceinline__ double approx_rcp(double x) {
 
 // LayerNorm of xs[0..E) (ggml.c:11964-12013; order-independence argument in layernorm_act_kernel, gpt_kernels.cu) ->
 // activation operand (optionally f16-rounded) in two-plane LI order.  Block-wide: each thread owns <= 2 elements.
+// One block barrier per statistic: warps leave their partial sums in shared memory and EVERY thread adds the 16 partials and
+// takes the rounding decision itself (identical inputs, identical arithmetic -> identical result), instead of funnelling
+// through warp 0 and a second barrier.  red: [0,16) double mean partials, [16,24) 16 float |x| partials, [24,40) double
+// variance partials.
 template <bool ROUND16>
 __device__ __noinline__ void block_layernorm(const float * xs, int E, double inv_E, const float * __restrict__ g, const float * __restrict__ b, float * act,
-                                             double * scratch, float * bc, unsigned * fallback_counter, int sb) {
+                                             double * red, unsigned * fallback_counter, int sb) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float * fscratch = reinterpret_cast<float *>(scratch + kWarps);
+    double * sA = red, * sB = red + kWarps + kWarps / 2;
+    float * fA = reinterpret_cast<float *>(red + kWarps);
     const int i0 = tid, i1 = tid + kThreads;
     const bool h0 = i0 < E, h1 = i1 < E;
     // gains / biases are different vectors every layer (L2 or HBM latency): fetch them now, use them at the end
@@ -141,54 +168,47 @@ __device__ __noinline__ void block_layernorm(const float * xs, int E, double inv
     float a = fabsf(x0) + fabsf(x1);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); a += __shfl_xor_sync(0xffffffffu, a, o); }
-    if (lane == 0) { scratch[warp] = s; fscratch[warp] = a; }
+    if (lane == 0) { sA[warp] = s; fA[warp] = a; }
     __syncthreads();
-    if (warp == 0) {
-        s = lane < kWarps ? scratch[lane] : 0.0; a = lane < kWarps ? fscratch[lane] : 0.f;
+    float mean;
+    {
+        double S = 0.0; float A = 0.0f;
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); a += __shfl_xor_sync(0xffffffffu, a, o); }
-        if (lane == 0) {
-            const double c = s * inv_E;
-            const double w = (slack * (double) a * 1.001) * inv_E + fabs(c) * 0x1p-50;      // 1.001: the float abs-sum may be low by n*2^-24
-            float mean = __double2float_rn(c - w);
-            if (mean != __double2float_rn(c + w)) {                                         // rare: replay the reference's sequential sum
-                double ss = 0.0;
-                for (int i = 0; i < E; i++) ss = __dadd_rn(ss, (double) xs[i]);
-                mean = __double2float_rn(__ddiv_rn(ss, (double) E));
-                if (fallback_counter) atomicAdd(fallback_counter, 1u);
-            }
-            bc[0] = mean;
+        for (int w = 0; w < kWarps; w++) { S += sA[w]; A += fA[w]; }
+        const double c = S * inv_E;
+        const double hw = (slack * (double) A * 1.001) * inv_E + fabs(c) * 0x1p-50;     // 1.001: the float abs-sum may be low by n*2^-24
+        mean = __double2float_rn(c - hw);
+        if (mean != __double2float_rn(c + hw)) {                                        // rare: replay the reference's sequential sum (every thread, same result)
+            double ss = 0.0;
+            for (int i = 0; i < E; i++) ss = __dadd_rn(ss, (double) xs[i]);
+            mean = __double2float_rn(__ddiv_rn(ss, (double) E));
+            if (fallback_counter && tid == 0) atomicAdd(fallback_counter, 1u);
         }
     }
-    __syncthreads();
-    const float mean = bc[0];
     tstamp(sb);
     // ---- variance ----
     const float v0 = __fsub_rn(x0, mean), v1 = __fsub_rn(x1, mean);
     double s2 = (h0 ? (double) __fmul_rn(v0, v0) : 0.0) + (h1 ? (double) __fmul_rn(v1, v1) : 0.0);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-    if (lane == 0) scratch[warp] = s2;
+    if (lane == 0) sB[warp] = s2;
     __syncthreads();
-    if (warp == 0) {
-        s2 = lane < kWarps ? scratch[lane] : 0.0;
+    float scale;
+    {
+        double S2 = 0.0;
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-        if (lane == 0) {
-            const double c = s2 * inv_E;
-            const double w = (slack * s2) * inv_E + c * 0x1p-50;
-            float variance = __double2float_rn(c - w);
-            if (variance != __double2float_rn(c + w)) {
-                double ss = 0.0;
-                for (int i = 0; i < E; i++) { const float v = __fsub_rn(xs[i], mean); ss = __dadd_rn(ss, (double) __fmul_rn(v, v)); }
-                variance = __double2float_rn(__ddiv_rn(ss, (double) E));
-                if (fallback_counter) atomicAdd(fallback_counter, 1u);
-            }
-            bc[1] = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(variance, 1e-5f)));
+        for (int w = 0; w < kWarps; w++) S2 += sB[w];
+        const double c = S2 * inv_E;
+        const double hw = (slack * S2) * inv_E + c * 0x1p-50;
+        float variance = __double2float_rn(c - hw);
+        if (variance != __double2float_rn(c + hw)) {
+            double ss = 0.0;
+            for (int i = 0; i < E; i++) { const float v = __fsub_rn(xs[i], mean); ss = __dadd_rn(ss, (double) __fmul_rn(v, v)); }
+            variance = __double2float_rn(__ddiv_rn(ss, (double) E));
+            if (fallback_counter && tid == 0) atomicAdd(fallback_counter, 1u);
         }
+        scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(variance, 1e-5f)));
     }
-    __syncthreads();
-    const float scale = bc[1];
     if (h0) { float y = __fmul_rn(__fmul_rn(v0, scale), g0); if (b) y = __fadd_rn(y, b0); act[act_index(i0)] = ROUND16 ? round_f16(y) : y; }
     if (h1) { float y = __fmul_rn(__fmul_rn(v1, scale), g1); if (b) y = __fadd_rn(y, b1); act[act_index(i1)] = ROUND16 ? round_f16(y) : y; }
     __syncthreads();
@@ -196,7 +216,6 @@ __device__ __noinline__ void block_layernorm(const float * xs, int E, double inv
 
 // Per-CTA row ranges of every phase, built once per launch in shared memory (the divisions and table look-ups they replace
 // cost ~2 us of single-thread time per phase when done on the fly).
-constexpr int kMaxPhases = 128;
 struct PhaseSched { int r0, r1, K, row_bytes; const unsigned char * w; int pad[2]; };   // rows [r0, r1) of this phase belong to this CTA
 
 enum { EP_QKV = 0, EP_RESID = 1, EP_GELU = 2, EP_LOGITS = 3 };
@@ -257,79 +276,86 @@ __device__ __forceinline__ float row_dot(const unsigned char * row, const float 
 
 constexpr int kMaxTasks = 6;        // (h, k) score tasks per warp: H * block_size / (n_cta * kWarps) <= 16 * 1024 / (132 * 16) < 8
 
-// everything run_phase needs; lives in local memory of the kernel and is passed by reference
-struct PhaseCtx {
-    const PhaseSched * sched; int n_phases;
-    unsigned char * wslot;           // this warp's staging area
-    int staged_mask;                 // bit h: half h of wslot holds (or is receiving) the rows of the phase with parity h
-    const float * act; const float * xs;
+// Block-wide state of the phases, in static shared memory (a by-reference struct in local memory cost L1/L2 round trips on
+// the critical path: the 72 KB of per-thread stack frames do not fit the L1 left over next to 220 KB of shared memory).
+struct BlockCtx {
     tagged_t * gq, * gk, * gv, * gx, * gff;
     float * mem_k, * mem_v, * logits;
     const __half * gelu_tab;
-    int E, ctx, n_past;
-    unsigned long long * timing;     // debug stamps (CTA 0, thread 0)
+    unsigned long long policy;       // L2 evict-first descriptor of the weight stream
+    int E, ctx, n_past, n_phases;
 };
+__shared__ BlockCtx s_bc;
+__shared__ __align__(8) unsigned long long s_bar[kWarps][2];       // per warp, per staging half: "rows have landed"
+extern __shared__ __align__(128) unsigned char dsm[];
 
-// Start copying this warp's rows of `phase` (rows r0 + warp, r0 + warp + 16, ...) into half (phase & 1) of its staging area
-// with per-lane 16-byte cp.async: the lane-interleaved layout makes every instruction one coalesced 512-byte segment.
-// Always commits exactly one cp.async group (possibly empty) so that run_phase can wait for "all but the newest".
-// Returns immediately; bit (phase & 1) of pc.staged_mask says whether the rows will be in shared memory.
-__device__ __forceinline__ void stage_rows(PhaseCtx & pc, int phase) {
-    const int half = phase & 1;
-    pc.staged_mask &= ~(1 << half);
-    if (phase < pc.n_phases) {
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        const PhaseSched p = pc.sched[phase];
-        const int nrows = (p.r1 - p.r0 - warp + kWarps - 1) / kWarps;             // rows of this warp (may be <= 0)
-        if (nrows > 0 && nrows * p.row_bytes <= kHalfSlotBytes) {                 // else run_phase reads global memory directly
-            const uint32_t dst0 = smem_u32(pc.wslot) + half * kHalfSlotBytes + lane * 16;
-            const int vec_per_row = p.row_bytes >> 9;                              // 512-byte segments per row
-            for (int j = 0; j < nrows; j++) {
-                const unsigned char * src = p.w + (size_t)(p.r0 + warp + j * kWarps) * p.row_bytes + lane * 16;
-                for (int g = 0; g < vec_per_row; g++) cp_async16(dst0 + j * p.row_bytes + g * 512, src + g * 512);
-            }
-            pc.staged_mask |= 1 << half;
-        }
+__device__ __forceinline__ const PhaseSched * sched_tab() { return reinterpret_cast<const PhaseSched *>(dsm + SmemLayout::sched); }
+// rows [a, b) of this warp: the CTA's range cut into 16 contiguous slices (contiguous rows = one bulk copy)
+__device__ __forceinline__ void warp_rows(const PhaseSched & p, int warp, int & a, int & b) {
+    const int n = p.r1 - p.r0;
+    a = p.r0 + ((warp * n) >> 4); b = p.r0 + (((warp + 1) * n) >> 4);
+}
+
+// Lane 0: start the bulk copy of this warp's rows of `phase` into half (phase & 1) of its staging area and arm that half's
+// mbarrier.  The barrier is armed exactly once per phase (with or without bytes), so use k of a half completes barrier
+// phase k and run_phase waits on parity (phase >> 1) & 1.  Rows that do not fit (lm_head over the whole vocabulary, K = 4096
+// rows of bark-large) are read from global memory by run_phase instead.
+__device__ __forceinline__ void stage_rows(int phase) {
+    if (phase >= s_bc.n_phases || (threadIdx.x & 31) != 0) return;
+    const int warp = threadIdx.x >> 5, half = phase & 1;
+    const PhaseSched p = sched_tab()[phase];
+    int a, b; warp_rows(p, warp, a, b);
+    const uint32_t bytes = (uint32_t)((b - a) * p.row_bytes);
+    const uint32_t bar = smem_u32(&s_bar[warp][half]);
+    if (bytes != 0 && bytes <= (uint32_t) kHalfSlotBytes) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // this half was just read through the generic proxy
+        mbar_expect_tx(bar, bytes);
+        tma_bulk_g2s_stream(smem_u32(dsm + SmemLayout::wslot) + warp * kWarpSlotBytes + half * kHalfSlotBytes, p.w + (size_t) a * p.row_bytes, bytes, bar, s_bc.policy);
+    } else {
+        mbar_arrive(bar);
     }
-    cp_async_commit();
 }
 
 // This warp's rows of `phase`: lane-order dot against the shared activation operand; outputs are published with epoch
-// `otag` (or stored, for the logits).  Then the rows of the next phase start streaming in.  No block-wide synchronisation.
+// `otag` (or stored, for the logits).  Then the rows of the phase after next start streaming in.  No block-wide synchronisation.
 template <typename WT>
-__device__ __noinline__ void run_phase(PhaseCtx & pc, int phase, int ep, int layer, uint32_t otag, int sb) {
+__device__ __noinline__ void run_phase(int phase, int ep, int layer, uint32_t otag, int sb) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const PhaseSched p = pc.sched[phase];
-    const int E = pc.E;
+    const PhaseSched p = sched_tab()[phase];
+    const float * act = reinterpret_cast<const float *>(dsm + SmemLayout::act);
+    const float * xs = reinterpret_cast<const float *>(dsm + SmemLayout::x);
     const int half = phase & 1;
-    const bool staged = (pc.staged_mask >> half) & 1;
-    cp_async_wait_all_but_newest();                           // the group of `phase` is complete; `phase + 1` may still be in flight
-    __syncwarp();
+    int a, b; warp_rows(p, warp, a, b);
+    const uint32_t bytes = (uint32_t)((b - a) * p.row_bytes);
+    const bool staged = bytes != 0 && bytes <= (uint32_t) kHalfSlotBytes;
+    const unsigned char * slot = dsm + SmemLayout::wslot + (size_t) warp * kWarpSlotBytes + (size_t) half * kHalfSlotBytes;
+    mbar_wait(smem_u32(&s_bar[warp][half]), (uint32_t)(phase >> 1) & 1u);
     tstamp(sb);
+    const int E = s_bc.E;
     int j = 0;
-    for (int r = p.r0 + warp; r < p.r1; r += kWarps, j++) {
-        const unsigned char * row = staged ? pc.wslot + half * kHalfSlotBytes + (size_t) j * p.row_bytes : p.w + (size_t) r * p.row_bytes;
-        const float v = row_dot<WT>(row, pc.act, p.K, lane);
+    for (int r = a; r < b; r++, j++) {
+        const unsigned char * row = staged ? slot + (size_t) j * p.row_bytes : p.w + (size_t) r * p.row_bytes;
+        const float v = row_dot<WT>(row, act, p.K, lane);
         if (lane == 0) {
             if (ep == EP_QKV) {
-                const size_t slot_off = ((size_t) layer * pc.ctx + pc.n_past) * E;
-                if (r < E) publish(pc.gq + r, v, otag);
-                else if (r < 2 * E) { publish(pc.gk + (r - E), v, otag); pc.mem_k[slot_off + (r - E)] = v; }
-                else                { publish(pc.gv + (r - 2 * E), v, otag); pc.mem_v[slot_off + (r - 2 * E)] = v; }
+                const size_t slot_off = ((size_t) layer * s_bc.ctx + s_bc.n_past) * E;
+                if (r < E) publish(s_bc.gq + r, v, otag);
+                else if (r < 2 * E) { publish(s_bc.gk + (r - E), v, otag); s_bc.mem_k[slot_off + (r - E)] = v; }
+                else                { publish(s_bc.gv + (r - 2 * E), v, otag); s_bc.mem_v[slot_off + (r - 2 * E)] = v; }
             } else if (ep == EP_RESID) {
-                publish(pc.gx + r, __fadd_rn(v, pc.xs[r]), otag);
+                publish(s_bc.gx + r, __fadd_rn(v, xs[r]), otag);
             } else if (ep == EP_GELU) {
                 float gl;
-                if (v <= -10.0f) gl = 0.0f; else if (v >= 10.0f) gl = v; else gl = __half2float(pc.gelu_tab[__half_as_ushort(__float2half_rn(v))]);
-                publish(pc.gff + r, gl, otag);
+                if (v <= -10.0f) gl = 0.0f; else if (v >= 10.0f) gl = v; else gl = __half2float(s_bc.gelu_tab[__half_as_ushort(__float2half_rn(v))]);
+                publish(s_bc.gff + r, gl, otag);
             } else {
-                pc.logits[r] = v;
+                s_bc.logits[r] = v;
             }
         }
     }
     __syncwarp();                                             // all lanes are done reading this half
     tstamp(sb + 1);
-    stage_rows(pc, phase + 2);
+    stage_rows(phase + 2);
     tstamp(sb + 2);
 }
 
@@ -337,13 +363,12 @@ __device__ __noinline__ void run_phase(PhaseCtx & pc, int phase, int ep, int lay
 
 template <typename WT, int DSTEPS>
 __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs A) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    float * act = reinterpret_cast<float *>(smem + SmemLayout::act);
-    float * xs = reinterpret_cast<float *>(smem + SmemLayout::x);
-    float * qs = reinterpret_cast<float *>(smem + SmemLayout::q);
-    float * part = reinterpret_cast<float *>(smem + SmemLayout::part);
-    double * red = reinterpret_cast<double *>(smem + SmemLayout::red);
-    float * bc = reinterpret_cast<float *>(red + 2 * kWarps);
+    float * act = reinterpret_cast<float *>(dsm + SmemLayout::act);
+    float * xs = reinterpret_cast<float *>(dsm + SmemLayout::x);
+    float * qs = reinterpret_cast<float *>(dsm + SmemLayout::q);
+    float * part = reinterpret_cast<float *>(dsm + SmemLayout::part);
+    double * red = reinterpret_cast<double *>(dsm + SmemLayout::red);
+    float * bc = reinterpret_cast<float *>(red + kWarps + kWarps / 2 + kWarps);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int D = DSTEPS * 32;
     const int E = A.E, H = A.H, L = A.L, ctx = A.block_size, n_past = A.n_past, n_kv = n_past + 1;
@@ -352,8 +377,8 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
     tagged_t * const gq = (tagged_t *) A.gq, * const gk = (tagged_t *) A.gk, * const gv = (tagged_t *) A.gv, * const gatt = (tagged_t *) A.gatt,
              * const gx = (tagged_t *) A.gx, * const gff = (tagged_t *) A.gff, * const gscores = (tagged_t *) A.gscores;
 
-    // ---- per-CTA row ranges in shared memory ----
-    PhaseSched * sched = reinterpret_cast<PhaseSched *>(smem + SmemLayout::sched);
+    // ---- per-CTA row ranges, block context and the staging barriers in shared memory ----
+    PhaseSched * sched = reinterpret_cast<PhaseSched *>(dsm + SmemLayout::sched);
     const int n_phases = 4 * L + 1;
     if (tid < n_phases) {
         const DecodePhase ph = A.phases[tid];
@@ -365,17 +390,20 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
         e.K = ph.K; e.row_bytes = ph.row_bytes; e.w = (const unsigned char *) ph.w; e.pad[0] = e.pad[1] = 0;
         sched[tid] = e;
     }
+    if (tid == kThreads - 1) {
+        s_bc.gq = gq; s_bc.gk = gk; s_bc.gv = gv; s_bc.gx = gx; s_bc.gff = gff;
+        s_bc.mem_k = A.mem_k; s_bc.mem_v = A.mem_v; s_bc.logits = A.logits; s_bc.gelu_tab = A.gelu_tab;
+        s_bc.policy = l2_evict_first_policy();
+        s_bc.E = E; s_bc.ctx = ctx; s_bc.n_past = n_past; s_bc.n_phases = n_phases;
+        s_tim = A.timing; s_tim_layer = 0;
+    }
+    if (lane == 0) {
+        mbar_init(smem_u32(&s_bar[warp][0]), 1); mbar_init(smem_u32(&s_bar[warp][1]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
-
-    PhaseCtx pc;
-    pc.sched = sched; pc.n_phases = n_phases;
-    pc.wslot = smem + SmemLayout::wslot + (size_t) warp * kWarpSlotBytes; pc.staged_mask = 0;
-    pc.act = act; pc.xs = xs;
-    pc.gq = gq; pc.gk = gk; pc.gv = gv; pc.gx = gx; pc.gff = gff;
-    pc.mem_k = A.mem_k; pc.mem_v = A.mem_v; pc.logits = A.logits; pc.gelu_tab = A.gelu_tab;
-    pc.E = E; pc.ctx = ctx; pc.n_past = n_past; pc.timing = A.timing;
-    stage_rows(pc, 0);
-    stage_rows(pc, 1);
+    stage_rows(0);
+    stage_rows(1);
 
     // embedding of the one new token (bark.cpp:1226-1228, 1259): every CTA keeps its own copy of the residual stream
     const int token = A.token_ptr ? min(max(__ldcg(A.token_ptr), 0), A.n_vocab_in - 1) : A.token;
@@ -388,8 +416,6 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
     uint32_t tag = A.tag_base;                               // unique epoch per exchange; the host advances the base by 6 * L per launch
     const float scale = 1.0f / sqrtf((float) E / (float) H);
     const double inv_E = A.inv_E;
-    if (tid == 0) { s_tim = A.timing; s_tim_layer = 0; }
-    __syncthreads();
 
     const int parts = D >> 4;                                // P3: CTAs per head
     const bool pv_cta = (int) blockIdx.x < H * parts;
@@ -404,9 +430,21 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
         if (tid == 0) s_tim_layer = il;                       // (tid 0 is the only reader)
         tstamp(0);
         // ---- P1: LN1 -> QKV ----
-        block_layernorm<kRound>(xs, E, inv_E, lv.ln_1_g, lv.ln_1_b, act, red, bc, A.ln_fallbacks, 1);
+        block_layernorm<kRound>(xs, E, inv_E, lv.ln_1_g, lv.ln_1_b, act, red, A.ln_fallbacks, 1);
         tstamp(2);
-        run_phase<WT>(pc, 4 * il + 0, EP_QKV, il, t_qkv, 3);
+        run_phase<WT>(4 * il + 0, EP_QKV, il, t_qkv, 3);
+
+        // ---- P3 operands first: this thread's chain of V values of older positions (thread (v, dd): virtual lane v of output
+        // column dd) goes out before anything is waited for, so the loads drain while P2 runs ----
+        const int pv_v = tid >> 4, pv_dd = tid & 15;
+        const int col0 = pv_h * D + pv_c * 16;
+        float vreg[32]; float vl = 0.0f;
+        if (pv_cta) {
+            const float * Vc = A.mem_v + (size_t) il * ctx * E + col0;
+#pragma unroll
+            for (int c = 0; c < 32; c++) { const int k = pv_v + 32 * c; if (k < np && k < n_past) vreg[c] = __ldcg(Vc + (size_t) k * E + pv_dd); }
+            if (np + pv_v < n_past) vl = __ldcg(Vc + (size_t)(np + pv_v) * E + pv_dd);          // one element of the leftover rows k = np + v
+        }
 
         // ---- P2: scores.  K rows of older positions are fetched before q arrives. ----
         {
@@ -459,19 +497,11 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
 
         // ---- P3: soft_max + P.V, one CTA per (head, 16 columns of the head) ----
         if (pv_cta) {
-            const int h = pv_h, col0 = h * D + pv_c * 16;
-            const int v = tid >> 4, dd = tid & 15;              // thread (v, dd): virtual lane v of output column dd
-            const float * Vc = A.mem_v + (size_t) il * ctx * E + col0;
-            // prefetch this thread's chain of V values (older positions) ...
-            float vreg[32];
-#pragma unroll
-            for (int c = 0; c < 32; c++) { const int k = v + 32 * c; if (k < np && k < n_past) vreg[c] = __ldcg(Vc + (size_t) k * E + dd); }
-            // ... and one element of the leftover rows k = np + v (parked in shared memory later; `act` is idle in this phase)
-            const float vl = (np + v < n_past) ? __ldcg(Vc + (size_t)(np + v) * E + dd) : 0.0f;
+            const int h = pv_h, v = pv_v, dd = pv_dd;
             const float v_new = consume1(gv + col0 + dd, t_qkv);     // value row of the new position
+            __syncthreads();                                         // slower warps may still be reading q (in `qs`) for their score tasks
             tstamp(9);
-            float * p = qs;                                          // scores row -> probabilities
-            float * csum = part + 32 * 16;
+            float * p = qs;                                          // scores row -> exp(score - max); the 1/sum factor is applied on use
             consume_to_smem<2>(gscores + (size_t) h * ctx, n_kv, t_sc, p, SINK_PLAIN);
             tstamp(10);
             float mx = __int_as_float(0xff800000);
@@ -486,30 +516,36 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
 #pragma unroll
             for (int w = 1; w < kWarps; w++) mx = fmaxf(mx, fred[w]);
             tstamp(11);
-            const int nchunks = n_kv >> 3;
-            if (tid < nchunks) {
-                float * pc8 = p + tid * 8;
+            // exp: whole chunks of 8 through the vector polynomial (ggml.c:2706-2746), the n_kv % 8 tail through libm expf
+            // (ggml.c:2880-2884) — one element per thread, every element independent of the others
+            const int nchunks = n_kv >> 3, n8 = nchunks << 3;
 #pragma unroll 1
-                for (int l = 0; l < 8; l++) pc8[l] = ggml_v_expf_dev(__fsub_rn(pc8[l], mx));
-                const float t0 = __fadd_rn(pc8[4], pc8[0]), t1 = __fadd_rn(pc8[5], pc8[1]), t2 = __fadd_rn(pc8[6], pc8[2]), t3 = __fadd_rn(pc8[7], pc8[3]);
-                csum[tid] = __fadd_rn(__fadd_rn(t0, t2), __fadd_rn(t1, t3));
+            for (int i = tid; i < n_kv; i += kThreads) {
+                const float d = __fsub_rn(p[i], mx);
+                p[i] = i < n8 ? ggml_v_expf_dev(d) : glibc_expf_dev(d);
             }
             __syncthreads();
             tstamp(12);
-            // sum = sequential double accumulation of the chunk sums, then the libm-expf tail (ggml.c:2845-2888).  All terms are
-            // positive, so a tree sum S brackets the sequential one within +-2n*2^-53*S; if 1/sum rounds to the same float at both
-            // ends of the bracket the order cannot matter, else replay sequentially.  Done by warp 0, broadcast through bc[2].
+            // sum = sequential double accumulation of the chunk sums (in-chunk float tree of the 8-wide vector code), then the
+            // tail (ggml.c:2845-2888).  All terms are positive, so a tree sum S brackets the sequential one within
+            // +-2n*2^-53*S; if 1/sum rounds to the same float at both ends of the bracket the order cannot matter, else replay
+            // sequentially.  Done by warp 0, broadcast through bc[2].
             if (warp == 0) {
+                auto chunk_sum = [&](int c) {
+                    const float4 lo4 = *reinterpret_cast<const float4 *>(p + c * 8), hi4 = *reinterpret_cast<const float4 *>(p + c * 8 + 4);
+                    const float t0 = __fadd_rn(hi4.x, lo4.x), t1 = __fadd_rn(hi4.y, lo4.y), t2 = __fadd_rn(hi4.z, lo4.z), t3 = __fadd_rn(hi4.w, lo4.w);
+                    return __fadd_rn(__fadd_rn(t0, t2), __fadd_rn(t1, t3));
+                };
                 double s = 0.0;
 #pragma unroll 1
-                for (int c = lane; c < nchunks; c += 32) s += (double) csum[c];
+                for (int c = lane; c < nchunks; c += 32) s += (double) chunk_sum(c);
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
                 if (lane == 0) {
                     const double dl = 2.0 * (double)(nchunks + 8) * 0x1p-53 * s * (1.0 + 1e-6);
                     double lo = s - dl, hi = s + dl;
 #pragma unroll 1
-                    for (int i = nchunks * 8; i < n_kv; i++) { const float tl = glibc_expf_dev(__fsub_rn(p[i], mx)); p[i] = tl; lo = __dadd_rn(lo, (double) tl); hi = __dadd_rn(hi, (double) tl); }
+                    for (int i = n8; i < n_kv; i++) { const double tl = (double) p[i]; lo = __dadd_rn(lo, tl); hi = __dadd_rn(hi, tl); }
                     // 1/sum without a double division: y ~ 1/mid to 2^-50, the bracket [lo, hi] and that error go into the half-width
                     const double mid = 0.5 * (lo + hi), y = approx_rcp(mid);
                     const double rw = (hi - lo) * y * 0.5 + 0x1p-48;                       // relative half-width
@@ -518,9 +554,9 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
                     if (f_lo != f_hi) {
                         double q2 = 0.0;
 #pragma unroll 1
-                        for (int c = 0; c < nchunks; c++) q2 = __dadd_rn(q2, (double) csum[c]);
+                        for (int c = 0; c < nchunks; c++) q2 = __dadd_rn(q2, (double) chunk_sum(c));
 #pragma unroll 1
-                        for (int i = nchunks * 8; i < n_kv; i++) q2 = __dadd_rn(q2, (double) p[i]);
+                        for (int i = n8; i < n_kv; i++) q2 = __dadd_rn(q2, (double) p[i]);
                         f_lo = __double2float_rn(__ddiv_rn(1.0, q2));
                         if (A.ln_fallbacks) atomicAdd(A.ln_fallbacks + 1, 1u);
                     }
@@ -529,19 +565,23 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
             }
             __syncthreads();
             tstamp(13);
-            const float sc_f = bc[2];
-#pragma unroll 1
-            for (int i = tid; i < n_kv; i += kThreads) p[i] = __fmul_rn(p[i], sc_f);
-            __syncthreads();
-            tstamp(14);
+            const float sc_f = bc[2];                                // probabilities = p[k] * sc_f (ggml_vec_scale_f32), formed where they are used
             float acc = 0.0f;
 #pragma unroll
             for (int c = 0; c < 32; c++) {
                 const int k = v + 32 * c;
-                if (k < np) acc = __fmaf_rn(k < n_past ? vreg[c] : v_new, p[k], acc);
+                if (k < np) acc = __fmaf_rn(k < n_past ? vreg[c] : v_new, __fmul_rn(p[k], sc_f), acc);
             }
             part[v * 16 + dd] = acc;
-            act[v * 16 + dd] = vl;
+            // leftovers k = np .. n_kv-1 as the pinned build compiles them (oracle orc_vec_dot_f32): 8-groups and a 4-group of
+            // rounded multiply + add, then <= 3 fused multiply-adds.  Thread (v, dd) prepares term v: the rounded product where
+            // the chain adds one, the bare value where it fuses.
+            const int r = n_kv - np;
+            const int r8 = r & ~7, n4 = r8 + ((r - r8) >= 4 ? 4 : 0);
+            if (v < r) {
+                const float vv = (np + v < n_past) ? vl : v_new;
+                act[v * 16 + dd] = v < n4 ? __fmul_rn(vv, __fmul_rn(p[np + v], sc_f)) : vv;
+            }
             __syncthreads();
             tstamp(15);
             if (tid < 16) {
@@ -549,14 +589,10 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
 #pragma unroll
                 for (int l = 0; l < 32; l++) a32[l] = part[l * 16 + tid];
                 float sum = lane_tree_reduce_local(a32);
-                // leftovers k = np .. n_kv-1 as the pinned build compiles them (oracle orc_vec_dot_f32): 8-groups and a 4-group of
-                // rounded multiply + add, then <= 3 fused multiply-adds
-                const int r = n_kv - np;
-                const int n8 = r & ~7, n4 = n8 + ((r - n8) >= 4 ? 4 : 0);
-#pragma unroll 1
+#pragma unroll 4
                 for (int j = 0; j < r; j++) {
-                    const float vv = (np + j < n_past) ? act[j * 16 + tid] : v_new;
-                    if (j < n4) sum = __fadd_rn(sum, __fmul_rn(vv, p[np + j])); else sum = __fmaf_rn(vv, p[np + j], sum);
+                    const float tj = act[j * 16 + tid];
+                    if (j < n4) sum = __fadd_rn(sum, tj); else sum = __fmaf_rn(tj, __fmul_rn(p[np + j], sc_f), sum);
                 }
                 publish(gatt + col0 + tid, sum, t_att);
             }
@@ -567,30 +603,30 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
         // ---- P4: c_proj + residual ----
         consume_to_smem<2>(gatt, E, t_att, act, kSinkAct);
         tstamp(17);
-        run_phase<WT>(pc, 4 * il + 1, EP_RESID, il, t_x1, 18);
+        run_phase<WT>(4 * il + 1, EP_RESID, il, t_x1, 18);
 
         // ---- P5: LN2 -> c_fc -> GELU ----
         consume_to_smem<2>(gx, E, t_x1, xs, SINK_PLAIN);
         tstamp(21);
-        block_layernorm<kRound>(xs, E, inv_E, lv.ln_2_g, lv.ln_2_b, act, red, bc, A.ln_fallbacks, 22);
+        block_layernorm<kRound>(xs, E, inv_E, lv.ln_2_g, lv.ln_2_b, act, red, A.ln_fallbacks, 22);
         tstamp(23);
-        run_phase<WT>(pc, 4 * il + 2, EP_GELU, il, t_ff, 24);
+        run_phase<WT>(4 * il + 2, EP_GELU, il, t_ff, 24);
         __syncthreads();                                         // the ff vector lands in `act`, which slower warps may still be reading
         tstamp(27);
 
         // ---- P6: mlp/c_proj + residual ----
         consume_to_smem<8>(gff, 4 * E, t_ff, act, kSinkAct);
         tstamp(28);
-        run_phase<WT>(pc, 4 * il + 3, EP_RESID, il, t_x2, 29);
+        run_phase<WT>(4 * il + 3, EP_RESID, il, t_x2, 29);
 
         consume_to_smem<2>(gx, E, t_x2, xs, SINK_PLAIN);
     }
     if (tid == 0) s_tim_layer = L;                            // row L: start of the final norm
     // ---- final norm + lm_head window ----
     tstamp(0);
-    block_layernorm<kRound>(xs, E, inv_E, A.ln_f_g, A.ln_f_b, act, red, bc, A.ln_fallbacks, 1);
+    block_layernorm<kRound>(xs, E, inv_E, A.ln_f_g, A.ln_f_b, act, red, A.ln_fallbacks, 1);
     tstamp(2);
-    run_phase<WT>(pc, 4 * L, EP_LOGITS, 0, 0, 3);
+    run_phase<WT>(4 * L, EP_LOGITS, 0, 0, 3);
 }
 
 static size_t decode_smem_bytes() { return (size_t) SmemLayout::total + 128; }

@@ -558,11 +558,9 @@ int orc_gpt_eval(orc_ctx * c, int which, const int32_t * tokens, int n, int * n_
     const int E = m->n_embd;
     int N = n;
     float * x;
-    if (*n_past > 0) {
-        if (N != 1) return 0;
-        x = malloc((size_t) E * 4);
-        get_row(&m->wte[0], tokens[0], x);
-    } else if (merge_ctx) {                                                    /* bark.cpp:1230-1248 */
+    if (*n_past > 0 && merge_ctx) return 0;
+    if (*n_past + (merge_ctx ? 257 : N) > m->block_size) return 0;
+    if (merge_ctx) {                                                    /* bark.cpp:1230-1248 */
         if (N != 513) return 0;
         N = 257;
         x = malloc((size_t) N * E * 4);
