@@ -558,7 +558,7 @@ int orc_gpt_eval(orc_ctx * c, int which, const int32_t * tokens, int n, int * n_
     const int E = m->n_embd;
     int N = n;
     float * x;
-    if (*n_past > 0 && merge_ctx) return 0;
+    merge_ctx = merge_ctx && *n_past == 0;                                     /* bark.cpp:1230: the merged prompt only exists at n_past == 0 */
     if (*n_past + (merge_ctx ? 257 : N) > m->block_size) return 0;
     if (merge_ctx) {                                                    /* bark.cpp:1230-1248 */
         if (N != 513) return 0;
