@@ -562,13 +562,6 @@ extern "C" int64_t bark_get_eval_time(struct bark_context * ctx) {
     return ctx->stats.t_eval_us;
 }
 
-extern "C" bool bark_model_quantize(const char * fname_inp, const char * fname_out, enum ggml_ftype ftype) {
-    (void) fname_inp; (void) fname_out;
-    fprintf(stderr, "%s: re-quantising model files (ftype %d) is not part of this library's scope; use the reference `quantize` tool "
-                    "(examples/quantize) to produce the file\n", __func__, (int) ftype);
-    return false;
-}
-
 extern "C" void bark_free(struct bark_context * ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
