@@ -57,6 +57,12 @@ void permute_to_gm(const void * src, void * dst, int n_out, int o_pad, int K, WT
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float wte_value(const void * wte, int wt, int E, int row, int i) {
     if (wt == W_F16) return __half2float(((const __half *) wte)[(size_t) row * E + i]);
+    if (wt == W_Q4_0) {                                      // dequantize_row_q4_0 (ggml-quants.c:1515-1533): (nibble - 8) * d on the file's 18-byte blocks
+        const unsigned char * blk = (const unsigned char *) wte + ((size_t) row * (E >> 5) + (i >> 5)) * 18;
+        const float d = __half2float(__ushort_as_half((unsigned short)(blk[0] | (blk[1] << 8))));
+        const int j = i & 31, q = j < 16 ? (blk[2 + j] & 0x0f) : (blk[2 + j - 16] >> 4);
+        return __fmul_rn((float)(q - 8), d);
+    }
     return ((const float *) wte)[(size_t) row * E + i];
 }
 
@@ -218,6 +224,7 @@ __global__ void __launch_bounds__(256) lane_matmul_kernel(const T * __restrict__
 static bool use_tiled() { static const bool t = [] { const char * e = getenv("BARK_B200_GEMM"); return !(e && !strcmp(e, "simple")); }(); return t; }
 
 void lane_matmul(const DMat & W, const void * act, int act_gs, int rows, const MatmulEpilogue & ep, cudaStream_t s) {
+    if (W.type == W_Q4_0) { q4_matmul(W, act, act_gs, rows, ep, s); return; }      // act_gs = f32 row stride for this type
     const int gx = (W.n_out + 7) / 8;
     {   // roofline annotation: algorithmic HBM bytes (weights once + operands) and flops of this mat-mul
         const double es = W.type == W_F16 ? 2.0 : 4.0;

@@ -29,6 +29,11 @@ void lane_matmul(const DMat & W, const void * act, int act_gs, int rows, const M
 void attention(const float * Q, const float * Kc, const float * Vc, int N, int n_kv, int n_past, int E, int H, bool causal,
                float * scores, void * act, WType wt, int Kp, cudaStream_t s);
 
+// ---- q4_0 weights (q4_kernels.cu) ---------------------------------------------------------------------------------
+void q4_split(const void * raw_blocks, size_t n_blocks, void * qs, void * scales, cudaStream_t s);
+void q4_set_scratch(void * q8, void * q8_scales);      // int8 [rows][K] + f32 [rows][K/32] for the activation operand, owned by the context
+void q4_matmul(const DMat & W, const void * act_f32, int ld_act, int rows, const MatmulEpilogue & ep, cudaStream_t s);
+
 // ---- register-tiled multi-row kernels (gemm_kernels.cu) ------------------------------------------------------------
 void lane_gemm_tiled(const DMat & W, const void * act, int act_gs, int rows, const MatmulEpilogue & ep, cudaStream_t s);
 void attention_tiled_scores(const float * Q, const float * Kc, int N, int n_kv, int n_past, int E, int H, float scale, bool causal, float * scores, cudaStream_t s);

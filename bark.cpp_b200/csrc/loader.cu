@@ -82,8 +82,8 @@ bool load_gpt(bark_context * ctx, std::ifstream & f, GPTModel & m, const char * 
         printf("%s: %s model: n_layer=%d n_head=%d n_embd=%d block_size=%d bias=%d n_in_vocab=%d n_out_vocab=%d n_lm_heads=%d n_wtes=%d ftype=%d\n",
                __func__, what, m.n_layer, m.n_head, m.n_embd, m.block_size, m.bias, m.n_in_vocab, m.n_out_vocab, m.n_lm_heads, m.n_wtes, m.ftype);
     m.ftype %= 1000;                                                          // GGML_QNT_VERSION_FACTOR, bark.cpp:727
-    if (m.ftype != W_F32 && m.ftype != W_F16) {
-        fprintf(stderr, "%s: unsupported weight type (ftype %d) in %s model: this build reads f32 and f16 GPT weights\n", __func__, m.ftype, what);
+    if (m.ftype != W_F32 && m.ftype != W_F16 && m.ftype != W_Q4_0) {
+        fprintf(stderr, "%s: unsupported weight type (ftype %d) in %s model: this build reads f32, f16 and q4_0 GPT weights\n", __func__, m.ftype, what);
         return false;
     }
     m.wtype = (WType) m.ftype;
@@ -136,6 +136,16 @@ bool load_gpt(bark_context * ctx, std::ifstream & f, GPTModel & m, const char * 
             void * raw = upload_raw(ctx, f, bytes, host, false);
             if (!raw) return false;
             DMat & d = *s.mat;
+            if (m.wtype == W_Q4_0) {                         // 18-byte blocks -> aligned nibble words + f16 scales (q4_kernels.cu)
+                const size_t n_blocks = h.nel / 32;
+                d.n_out = s.ne1; d.K = s.ne0; d.Kp = d.K; d.type = W_Q4_0;
+                d.p = ctx_alloc(ctx, n_blocks * 16); d.scales = ctx_alloc(ctx, n_blocks * 2);
+                q4_split(raw, n_blocks, d.p, d.scales, ctx->stream);
+                BARK_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+                BARK_CUDA_CHECK(cudaFree(raw));
+                if (ctx->params.verbosity == HIGH) printf("%48s - [%5d, %5d], type = %d, %6.2f MB\n", h.name.c_str(), h.ne[0], h.ne[1], h.ttype, bytes / 1024.0 / 1024.0);
+                continue;
+            }
             d.n_out = s.ne1; d.K = s.ne0; d.type = m.wtype; d.Kp = li_padded_k(d.K, m.wtype == W_F16 ? 2 : 4);
             d.p = ctx_alloc(ctx, (size_t) d.n_out * d.Kp * (m.wtype == W_F16 ? 2 : 4));
             permute_to_li(raw, d.p, d.n_out, d.K, m.wtype, ctx->stream);
@@ -319,8 +329,8 @@ bool load_model_file(const std::string & path, bark_context * ctx) {
     }
     ctx->d_ln_fallbacks = (unsigned *) ctx_alloc(ctx, 4 * sizeof(unsigned));
     BARK_CUDA_CHECK(cudaMemset(ctx->d_ln_fallbacks, 0, 4 * sizeof(unsigned)));
-    build_decode_tables(ctx, ctx->semantic);
-    build_decode_tables(ctx, ctx->coarse);
+    if (ctx->semantic.wtype != W_Q4_0) build_decode_tables(ctx, ctx->semantic);   // q4_0 models step through the per-op kernels
+    if (ctx->coarse.wtype != W_Q4_0) build_decode_tables(ctx, ctx->coarse);
     return true;
 }
 

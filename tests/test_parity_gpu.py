@@ -210,3 +210,49 @@ def test_full_size_against_the_reference_itself(pkg, orc, weights_file):
         assert np.array_equal(b.tokens(1), ref["coarse"])
         assert np.array_equal(b.tokens(2), ref["fine"])
         assert wav_rel(audio, ref["audio"]) < WAV_RTOL
+
+
+# ---- q4_0 GPT weights (BASELINE configs[3]: q4_0 GPT + f16 codec) --------------------------------------------------------
+def _q4_path(pkg, weights_file, config, src_ftype):
+    import os
+    from conftest import FIXTURE_DIR
+    src = weights_file(config, src_ftype)
+    dst = os.path.join(FIXTURE_DIR, f"{config}_{src_ftype}_1234_q4_0.bin")
+    if not os.path.exists(dst):
+        assert pkg.lib().bark_model_quantize(src.encode(), (dst + ".tmp").encode(), 2)      # the library's own quantizer (tests/test_quantize.py pins it)
+        os.replace(dst + ".tmp", dst)
+    return dst
+
+
+@pytest.mark.parametrize("config,src_ftype,n_steps", [("tiny", "f16", 16), ("mini", "f32", 30)])
+def test_q4_0_logits_tokens_and_waveform(pkg, orc, weights_file, config, src_ftype, n_steps):
+    """q4_0 mul_mat (q8_0 activation blocks, 8 int lanes per block, hsum_float_8) and q4_0 get_rows against the oracle, whose
+    q4_0 path is pinned bit-exactly against the unmodified reference (tests/test_quantize.py)."""
+    path = _q4_path(pkg, weights_file, config, src_ftype)
+    o = orc.Oracle(path, seed=0, n_steps=n_steps)
+    rng = np.random.default_rng(19)
+    with pkg.Bark(path, seed=0, n_steps_text_encoder=n_steps) as b:
+        assert int(b.hparams(0)[9]) % 1000 == 2
+        toks, pg, po = o.tokenize("Hello, world"), 0, 0
+        for step in range(6):
+            lg, pg = b.gpt_eval(0, toks, pg, True)
+            lo, po = o.gpt_eval(0, toks, po, True)
+            assert np.array_equal(bits(lg), bits(lo)), f"semantic step {step}: {int((lg != lo).sum())} logits differ, max {np.abs(lg - lo).max():.3e}"
+            toks = np.array([int(np.argmax(lo[:10000]))], np.int32)
+        toks = np.concatenate([rng.integers(0, 10000, 256), [12050], rng.integers(10000, 12048, 37)]).astype(np.int32)
+        pg = po = 0
+        for step in range(8):
+            lg, pg = b.gpt_eval(1, toks, pg, False)
+            lo, po = o.gpt_eval(1, toks, po, False)
+            assert np.array_equal(bits(lg), bits(lo)), f"coarse step {step}: {int((lg != lo).sum())} logits differ"
+            toks = np.array([10000 + int(np.argmax(lo[10000:12048]))], np.int32)
+        buf = rng.integers(0, 1024, (8, 1024)).astype(np.int32); buf[:, 500:] = 1024
+        for nn in (2, 6):
+            x = buf.copy(); x[nn:, :] = 1024
+            assert np.array_equal(bits(b.fine_eval(x, nn)), bits(o.fine_eval(x, nn))), f"fine nn={nn}"
+        ref = o.generate("hello world")
+        audio = b.generate("hello world")
+        assert np.array_equal(b.tokens(0), ref["semantic"])
+        assert np.array_equal(b.tokens(1), ref["coarse"])
+        assert np.array_equal(b.tokens(2), ref["fine"])
+        assert wav_rel(audio, ref["audio"]) < WAV_RTOL
