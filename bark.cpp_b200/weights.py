@@ -70,7 +70,14 @@ def mini(ftype=F16):
     return Config("mini", GPTDims(3, 4, 256), GPTDims(2, 4, 256), GPTDims(2, 4, 256), gpt_ftype=ftype)
 
 
-CONFIGS = {"tiny": tiny, "mini": mini, "small": small, "large": large}
+def wide(ftype=F16):
+    """bark-large widths (E=1024, 16 heads of 64, K=4096 MLP rows) at 2 layers: the shapes of BASELINE configs[2] at a depth the
+    CPU oracle finishes in seconds."""
+    d = GPTDims(2, 16, 1024)
+    return Config("wide", d, d, d, gpt_ftype=ftype)
+
+
+CONFIGS = {"tiny": tiny, "mini": mini, "small": small, "large": large, "wide": wide}
 
 
 def synth_vocab(cfg: Config):

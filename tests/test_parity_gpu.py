@@ -256,3 +256,27 @@ def test_q4_0_logits_tokens_and_waveform(pkg, orc, weights_file, config, src_fty
         assert np.array_equal(b.tokens(1), ref["coarse"])
         assert np.array_equal(b.tokens(2), ref["fine"])
         assert wav_rel(audio, ref["audio"]) < WAV_RTOL
+
+
+def test_bark_large_widths(pkg, orc, weights_file):
+    """E=1024 / 16 heads / K=4096 (bark-large widths, BASELINE configs[2]) at 2 layers: decode rows too long for the staging
+    area are streamed from global memory, 64 soft_max CTAs, two LayerNorm elements per thread — all against the oracle."""
+    path = weights_file("wide", "f16")
+    o = orc.Oracle(path, seed=0, n_steps=8)
+    rng = np.random.default_rng(23)
+    with pkg.Bark(path, seed=0, n_steps_text_encoder=8) as b:
+        toks, pg, po = o.tokenize("hello world"), 0, 0
+        for step in range(12):
+            lg, pg = b.gpt_eval(0, toks, pg, True)
+            lo, po = o.gpt_eval(0, toks, po, True)
+            assert np.array_equal(bits(lg), bits(lo)), f"semantic step {step}: {int((lg != lo).sum())} logits differ, max {np.abs(lg - lo).max():.3e}"
+            toks = np.array([int(np.argmax(lo[:10000]))], np.int32)
+        toks = np.concatenate([rng.integers(0, 10000, 256), [12050], rng.integers(10000, 12048, 45)]).astype(np.int32)
+        pg = po = 0
+        for step in range(12):
+            lg, pg = b.gpt_eval(1, toks, pg, False)
+            lo, po = o.gpt_eval(1, toks, po, False)
+            assert np.array_equal(bits(lg), bits(lo)), f"coarse step {step}: {int((lg != lo).sum())} logits differ"
+            toks = np.array([10000 + int(np.argmax(lo[10000:12048]))], np.int32)
+        buf = rng.integers(0, 1024, (8, 1024)).astype(np.int32); buf[:, 600:] = 1024; buf[3:, :] = 1024
+        assert np.array_equal(bits(b.fine_eval(buf, 3)), bits(o.fine_eval(buf, 3)))      # one 1024-row pass (a whole generation costs the CPU oracle a minute)
