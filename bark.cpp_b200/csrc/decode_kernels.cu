@@ -84,9 +84,10 @@ __device__ __forceinline__ tagged_t peek(const tagged_t * p) {
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
     return w;
 }
+__shared__ unsigned s_poll_ns;                                       // back-off between polls (DecodeArgs::poll_ns, default 40)
 __device__ __forceinline__ float consume1(const tagged_t * p, uint32_t tag) {
     tagged_t w = peek(p);
-    while ((uint32_t)(w >> 32) != tag) { __nanosleep(40); w = peek(p); }       // back off: thousands of pollers share a few L2 lines
+    while ((uint32_t)(w >> 32) != tag) { __nanosleep(s_poll_ns); w = peek(p); }       // back off: thousands of pollers share a few L2 lines
     return __uint_as_float((uint32_t) w);
 }
 // two-plane LI index of column k in the shared activation operand: LDS.128 of one plane is contiguous across lanes
@@ -98,9 +99,9 @@ __device__ __forceinline__ int act_index(int k) {
 // debug stamps (BARK_B200_DECODE_TIMING=1): thread 0 of CTA 0 stamps every layer (rows 0..L-1 of the buffer), thread 0 of
 // every CTA stamps layer 5 (rows 64 + cta); 32 slots per row, %globaltimer nanoseconds.  s_tim is null in normal runs.
 __shared__ unsigned long long * s_tim;
-__shared__ int s_tim_layer;
+__shared__ int s_tim_layer, s_tim_tid;                               // s_tim_tid: the stamping thread (0, or lane 0 of another warp: BARK_B200_DECODE_TIMING_TID)
 __device__ __forceinline__ void tstamp(int i) {
-    if (threadIdx.x == 0 && s_tim) {
+    if (s_tim && (int) threadIdx.x == s_tim_tid) {
         unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         const int layer = s_tim_layer;
         if (blockIdx.x == 0) s_tim[layer * 32 + i] = t;
@@ -121,7 +122,7 @@ __device__ __noinline__ void consume_to_smem(const tagged_t * g, int n, uint32_t
     for (int j = 0; j < MAXJ; j++) {
         const int i = threadIdx.x + j * kThreads;
         if (i < n) {
-            while ((uint32_t)(w[j] >> 32) != tag) { __nanosleep(40); w[j] = peek(g + i); }
+            while ((uint32_t)(w[j] >> 32) != tag) { __nanosleep(s_poll_ns); w[j] = peek(g + i); }
             const float v = __uint_as_float((uint32_t) w[j]);
             if (mode == SINK_PLAIN) dst[i] = v; else dst[act_index(i)] = mode == SINK_ACT_R16 ? round_f16(v) : v;
         }
@@ -395,7 +396,7 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
         s_bc.mem_k = A.mem_k; s_bc.mem_v = A.mem_v; s_bc.logits = A.logits; s_bc.gelu_tab = A.gelu_tab;
         s_bc.policy = l2_evict_first_policy();
         s_bc.E = E; s_bc.ctx = ctx; s_bc.n_past = n_past; s_bc.n_phases = n_phases;
-        s_tim = A.timing; s_tim_layer = 0;
+        s_tim = A.timing; s_tim_layer = 0; s_tim_tid = A.timing_tid; s_poll_ns = A.poll_ns;
     }
     if (lane == 0) {
         mbar_init(smem_u32(&s_bar[warp][0]), 1); mbar_init(smem_u32(&s_bar[warp][1]), 1);
@@ -427,7 +428,7 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
         const DecodeLayerVec lv = A.layer_vecs[il];
         const uint32_t t_qkv = tag + 1, t_sc = tag + 2, t_att = tag + 3, t_x1 = tag + 4, t_ff = tag + 5, t_x2 = tag + 6;
         tag += 6;
-        if (tid == 0) s_tim_layer = il;                       // (tid 0 is the only reader)
+        if (tid == A.timing_tid) s_tim_layer = il;           // (the stamping thread is the only reader)
         tstamp(0);
         // ---- P1: LN1 -> QKV ----
         block_layernorm<kRound>(xs, E, inv_E, lv.ln_1_g, lv.ln_1_b, act, red, A.ln_fallbacks, 1);
@@ -621,7 +622,7 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
 
         consume_to_smem<2>(gx, E, t_x2, xs, SINK_PLAIN);
     }
-    if (tid == 0) s_tim_layer = L;                            // row L: start of the final norm
+    if (tid == A.timing_tid) s_tim_layer = L;                 // row L: start of the final norm
     // ---- final norm + lm_head window ----
     tstamp(0);
     block_layernorm<kRound>(xs, E, inv_E, A.ln_f_g, A.ln_f_b, act, red, A.ln_fallbacks, 1);

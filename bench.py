@@ -48,6 +48,16 @@ def peaks():
     return dict(hbm_gbs=6650.0, tflops=1400.0, tflops_burst=1590.0, source="fallback")
 
 
+def measured_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture (profiles/, tools/summarize_ncu.py traffic); None if not captured"""
+    p = os.path.join(ROOT, "profiles", "r01_decode_traffic.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        if d.get("kernel", "").split("<")[0] == kernel.split("<")[0]:
+            return int(d["traffic_bytes"])
+    return None
+
+
 def weights_path(config="small", ftype="f16", seed=1234):
     import importlib
     graft.load_package()
@@ -124,7 +134,7 @@ def algorithmic_work(pkg_bark):
     out = {}
     for which, name in ((0, "semantic"), (1, "coarse"), (2, "fine")):
         L, H, E, ctx, bias, n_in, n_out, n_heads, n_wtes, ftype = [int(v) for v in pkg_bark.hparams(which)]
-        bpw = 2 if ftype == 1 else 4
+        bpw = {0: 4, 1: 2, 2: 18 / 32}[ftype % 1000]
         out[name] = dict(L=L, E=E, n_out=n_out, bpw=bpw,
                          decode_weight_bytes=(12 * L * E * E + n_out * E) * bpw,
                          dense_flops=lambda N, rows_out, L=L, E=E, n_out=n_out: 2 * N * 12 * L * E * E + 4 * N * N * E * L + 2 * rows_out * E * n_out)
@@ -200,8 +210,8 @@ def run_ours(args):
             gbs = v["bytes"] / sec / 1e9 if sec else 0.0
             tfs = v["flops"] / sec / 1e12 if sec else 0.0
             f_h, f_t = gbs / P["hbm_gbs"], tfs / P["tflops"]
-            common = dict(kernel=name, launches=v["launches"], avg_launch_us=round(sec * 1e6 / max(v["launches"], 1), 2), share=round(v["ms"] / tot_ms, 4), traffic=None,
-                          peak_source=P["source"])
+            common = dict(kernel=name, launches=v["launches"], avg_launch_us=round(sec * 1e6 / max(v["launches"], 1), 2), share=round(v["ms"] / tot_ms, 4),
+                          traffic=measured_traffic(name), algorithmic_bytes_per_launch=int(v["bytes"] / max(v["launches"], 1)), peak_source=P["source"])
             if f_h >= f_t:
                 return dict(bound="hbm", achieved=round(gbs, 1), peak=P["hbm_gbs"], unit="GB/s", frac=round(f_h, 4), **common)
             return dict(bound="tensor", achieved=round(tfs, 2), peak=P["tflops"], unit="TFLOP/s", frac=round(f_t, 4),
@@ -222,7 +232,7 @@ def run_ours(args):
         "ms_per_step": round(elapsed_max / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16 weights/operands, f32 accumulate (reference arithmetic)", "data": "synthetic (seeded random weights in ggml_weights.bin format, prompt 'hello world')",
         "config": {"workload": "bark-small f16, batch=1 per GPU, n_steps_text_encoder=138 -> 2.76 s clip (BASELINE configs[1])", "parallelism": f"replica x{world} (one prompt per GPU, no collective)",
-                   "mode": "parity (token ids bit-identical to the CPU reference)", "l2": "inputs larger than L2: 0.84 GB of weights streamed per clip vs 126 MB L2; no flush needed"},
+                   "mode": "parity (token ids bit-identical to the CPU reference); coarse windows start from the cached canonical K/V rows (exact, DESIGN.md §6)", "l2": "inputs larger than L2: 0.84 GB of weights streamed per clip vs 126 MB L2; no flush needed"},
         "e2e": {"value": round(e2e_value, 4), "unit": UNIT, "h2d_bytes_per_step": int(h2d / args.steps), "d2h_bytes_per_step": int(d2h / args.steps),
                 "note": "wall clock around bark_generate_audio (C-ABI, host text in / host waveform out): prompt ids, uniforms and codes H2D, sampled tokens and waveform D2H inside the timed region"},
         "gpu_launches": int(launches),

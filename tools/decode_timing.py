@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Per-phase globaltimer stamps of the persistent decode kernel (BARK_B200_DECODE_TIMING=1), GPU box only.
 
-usage: python tools/decode_timing.py [n_past ...]      (coarse model of the bark-small f16 bench file)
+usage: [BARK_B200_DECODE_TIMING_TID=480] [BARK_B200_POLL_NS=200] python tools/decode_timing.py [n_past ...]   (coarse model, bark-small f16 bench file)
 Prints, per n_past: the time between consecutive stamps on CTA 0 (median over layers) and, at layer 5, the spread over CTAs
 of each stamp.  The raw [256][32] dump is saved to gpurun_out/decode_timing_<n_kv>.npy.  Stamp ids: decode_kernels.cu tstamp().
 """
@@ -40,9 +40,10 @@ def main():
             t = np.zeros(256 * 32, np.uint64)
             pkg.lib().bark_b200_decode_timing(b.ctx, t.ctypes.data_as(C.c_void_p), t.size)
             t = t.reshape(256, 32).astype(np.int64)
-            np.save(os.path.join(ROOT, "gpurun_out", f"decode_timing_{p}.npy"), t)
+            tag = f"tid{os.environ.get('BARK_B200_DECODE_TIMING_TID', '0')}_poll{os.environ.get('BARK_B200_POLL_NS', '40')}"
+            np.save(os.path.join(ROOT, "gpurun_out", f"decode_timing_{p}_{tag}.npy"), t)
             lay = t[:L + 1]
-            print(f"== n_kv {p}: {(lay[L, 0] - lay[0, 0]) / 1e3:.1f} us for {L} layers on CTA 0 ({(lay[L, 0] - lay[0, 0]) / 1e3 / L:.2f} us per layer)")
+            print(f"== [{tag}] n_kv {p}: {(lay[L, 0] - lay[0, 0]) / 1e3:.1f} us for {L} layers on CTA 0 ({(lay[L, 0] - lay[0, 0]) / 1e3 / L:.2f} us per layer)")
             used = [i for i in range(32) if lay[1, i] != 0]
             for a, c in zip(used[:-1], used[1:]):
                 d = (lay[:L, c] - lay[:L, a]) / 1e3

@@ -51,5 +51,21 @@ def full(path, out):
                 if k in idx: f.write(f"| {k} | {r[idx[k]]} | {units[idx[k]]} |\n")
             f.write("\n")
 
+def traffic(path, out):
+    """dram bytes per launch of the first kernel in a `--set full` report -> small JSON that bench.py reports as roofline.traffic"""
+    import json
+    txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rd = list(csv.reader(io.StringIO(txt)))
+    hdr, units, r = rd[0], rd[1], rd[2]
+    idx = {h: i for i, h in enumerate(hdr)}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    def val(k): return float(r[idx[k]].replace(",", "")) * scale[units[idx[k]]]
+    d = {"kernel": short(r[idx["Kernel Name"]]), "dram_bytes_read": val("dram__bytes_read.sum"), "dram_bytes_write": val("dram__bytes_write.sum"),
+         "duration_us_under_ncu": float(r[idx["gpu__time_duration.sum"]].replace(",", "")), "source": path,
+         "how": "ncu --set full --clock-control none, one launch inside `bench.py --steps 1 --warmup 1` (tools/ncu_one.sh)"}
+    d["traffic_bytes"] = d["dram_bytes_read"] + d["dram_bytes_write"]
+    json.dump(d, open(out, "w"), indent=1)
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
