@@ -84,7 +84,7 @@ __device__ __forceinline__ tagged_t peek(const tagged_t * p) {
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
     return w;
 }
-__shared__ unsigned s_poll_ns;                                       // back-off between polls (DecodeArgs::poll_ns, default 40)
+__shared__ unsigned s_poll_ns, s_first_ns;                           // back-off between polls (DecodeArgs::poll_ns, default 40); head start given to the two residual exchanges
 __device__ __forceinline__ float consume1(const tagged_t * p, uint32_t tag) {
     tagged_t w = peek(p);
     while ((uint32_t)(w >> 32) != tag) { __nanosleep(s_poll_ns); w = peek(p); }       // back off: thousands of pollers share a few L2 lines
@@ -114,8 +114,9 @@ __device__ __forceinline__ void tstamp(int i) {
 // footprint (a 100 KB body re-fetched from L2 every layer cost 5-10x), so shared pieces are real calls.
 enum { SINK_PLAIN = 0, SINK_ACT = 1, SINK_ACT_R16 = 2 };
 template <int MAXJ>
-__device__ __noinline__ void consume_to_smem(const tagged_t * g, int n, uint32_t tag, float * dst, int mode) {
+__device__ __noinline__ void consume_to_smem(const tagged_t * g, int n, uint32_t tag, float * dst, int mode, unsigned first_ns = 0) {
     tagged_t w[MAXJ];
+    if (first_ns) __nanosleep(first_ns);                     // the producers are known to need at least this long: do not hammer their lines meanwhile
 #pragma unroll
     for (int j = 0; j < MAXJ; j++) { const int i = threadIdx.x + j * kThreads; if (i < n) w[j] = peek(g + i); }
 #pragma unroll
@@ -396,7 +397,7 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
         s_bc.mem_k = A.mem_k; s_bc.mem_v = A.mem_v; s_bc.logits = A.logits; s_bc.gelu_tab = A.gelu_tab;
         s_bc.policy = l2_evict_first_policy();
         s_bc.E = E; s_bc.ctx = ctx; s_bc.n_past = n_past; s_bc.n_phases = n_phases;
-        s_tim = A.timing; s_tim_layer = 0; s_tim_tid = A.timing_tid; s_poll_ns = A.poll_ns;
+        s_tim = A.timing; s_tim_layer = 0; s_tim_tid = A.timing_tid; s_poll_ns = A.poll_ns; s_first_ns = A.first_ns;
     }
     if (lane == 0) {
         mbar_init(smem_u32(&s_bar[warp][0]), 1); mbar_init(smem_u32(&s_bar[warp][1]), 1);
@@ -607,7 +608,7 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
         run_phase<WT>(4 * il + 1, EP_RESID, il, t_x1, 18);
 
         // ---- P5: LN2 -> c_fc -> GELU ----
-        consume_to_smem<2>(gx, E, t_x1, xs, SINK_PLAIN);
+        consume_to_smem<2>(gx, E, t_x1, xs, SINK_PLAIN, s_first_ns);
         tstamp(21);
         block_layernorm<kRound>(xs, E, inv_E, lv.ln_2_g, lv.ln_2_b, act, red, A.ln_fallbacks, 22);
         tstamp(23);
@@ -620,7 +621,7 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
         tstamp(28);
         run_phase<WT>(4 * il + 3, EP_RESID, il, t_x2, 29);
 
-        consume_to_smem<2>(gx, E, t_x2, xs, SINK_PLAIN);
+        consume_to_smem<2>(gx, E, t_x2, xs, SINK_PLAIN, s_first_ns);
     }
     if (tid == A.timing_tid) s_tim_layer = L;                 // row L: start of the final norm
     // ---- final norm + lm_head window ----

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Per-phase globaltimer stamps of the persistent decode kernel (BARK_B200_DECODE_TIMING=1), GPU box only.
 
-usage: [BARK_B200_DECODE_TIMING_TID=480] [BARK_B200_POLL_NS=200] python tools/decode_timing.py [n_past ...]   (coarse model, bark-small f16 bench file)
+usage: python tools/decode_timing.py [--sweep tid:poll_ns[:first_ns],...] [n_past ...]   (coarse model, bark-small f16 bench file;
+       tid = stamping thread (lane 0 of a warp), poll_ns = back-off between polls of the tagged exchange words)
 Prints, per n_past: the time between consecutive stamps on CTA 0 (median over layers) and, at layer 5, the spread over CTAs
 of each stamp.  The raw [256][32] dump is saved to gpurun_out/decode_timing_<n_kv>.npy.  Stamp ids: decode_kernels.cu tstamp().
 """
@@ -24,12 +25,14 @@ NAMES = {0: "layer start", 1: "LN1 mean", 2: "LN1 done", 3: "QKV rows ready (cp.
          24: "fc rows ready", 25: "fc rows done", 26: "fc next issued", 27: "fc block sync", 28: "ff arrived", 29: "proj rows ready", 30: "proj rows done", 31: "proj next issued"}
 
 
-def main():
-    pkg = graft.load_package()
-    path = bench.weights_path()
-    pasts = [int(a) for a in sys.argv[1:]] or [300, 900]
+SUMMARY = []
+
+
+def measure(pkg, path, pasts, tid, poll, first=0):
+    os.environ["BARK_B200_DECODE_TIMING_TID"] = str(tid)
+    os.environ["BARK_B200_POLL_NS"] = str(poll)
+    os.environ["BARK_B200_POLL_FIRST_NS"] = str(first)
     rng = np.random.default_rng(0)
-    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with pkg.Bark(path) as b:
         L = int(b.hparams(1)[0])
         for n_past in pasts:
@@ -40,9 +43,10 @@ def main():
             t = np.zeros(256 * 32, np.uint64)
             pkg.lib().bark_b200_decode_timing(b.ctx, t.ctypes.data_as(C.c_void_p), t.size)
             t = t.reshape(256, 32).astype(np.int64)
-            tag = f"tid{os.environ.get('BARK_B200_DECODE_TIMING_TID', '0')}_poll{os.environ.get('BARK_B200_POLL_NS', '40')}"
+            tag = f"tid{tid}_poll{poll}_first{first}"
             np.save(os.path.join(ROOT, "gpurun_out", f"decode_timing_{p}_{tag}.npy"), t)
             lay = t[:L + 1]
+            SUMMARY.append(dict(tid=tid, poll_ns=poll, first_ns=first, n_kv=int(p), us_per_layer=float((lay[L, 0] - lay[0, 0]) / 1e3 / L)))
             print(f"== [{tag}] n_kv {p}: {(lay[L, 0] - lay[0, 0]) / 1e3:.1f} us for {L} layers on CTA 0 ({(lay[L, 0] - lay[0, 0]) / 1e3 / L:.2f} us per layer)")
             used = [i for i in range(32) if lay[1, i] != 0]
             for a, c in zip(used[:-1], used[1:]):
@@ -56,6 +60,22 @@ def main():
                 col = cta[:, c]; col = col[col != 0]
                 v = (col - base) / 1e3
                 print(f"   layer5 stamp {c:2d} over {len(v):3d} CTAs: min {v.min():7.2f}  median {np.median(v):7.2f}  max {v.max():7.2f} us   {NAMES[c]}")
+
+
+def main():
+    pkg = graft.load_package()
+    path = bench.weights_path()
+    args = sys.argv[1:]
+    sweep = [(int(os.environ.get("BARK_B200_DECODE_TIMING_TID", "0")), int(os.environ.get("BARK_B200_POLL_NS", "40")))]
+    if args and args[0] == "--sweep":                        # --sweep tid:poll,tid:poll,...   one context per setting
+        sweep = [tuple(int(v) for v in item.split(":")) for item in args[1].split(",")]
+        args = args[2:]
+    pasts = [int(a) for a in args] or [300, 900]
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    for item in sweep:
+        measure(pkg, path, pasts, *item)
+    import json
+    json.dump(SUMMARY, open(os.path.join(ROOT, "gpurun_out", "decode_sweep.json"), "w"), indent=1)
 
 
 if __name__ == "__main__":
