@@ -114,7 +114,7 @@ __device__ __forceinline__ void tstamp(int i) {
 // footprint (a 100 KB body re-fetched from L2 every layer cost 5-10x), so shared pieces are real calls.
 enum { SINK_PLAIN = 0, SINK_ACT = 1, SINK_ACT_R16 = 2 };
 template <int MAXJ>
-__device__ __noinline__ void consume_to_smem(const tagged_t * g, int n, uint32_t tag, float * dst, int mode, unsigned first_ns = 0) {
+__device__ __forceinline__ void consume_to_smem_inl(const tagged_t * g, int n, uint32_t tag, float * dst, int mode, unsigned first_ns = 0) {
     tagged_t w[MAXJ];
     if (first_ns) __nanosleep(first_ns);                     // the producers are known to need at least this long: do not hammer their lines meanwhile
 #pragma unroll
@@ -129,6 +129,11 @@ __device__ __noinline__ void consume_to_smem(const tagged_t * g, int n, uint32_t
         }
     }
     __syncthreads();
+}
+// out-of-line copy: the kernel lives or dies by its instruction-cache footprint, so shared pieces are real calls
+template <int MAXJ>
+__device__ __noinline__ void consume_to_smem(const tagged_t * g, int n, uint32_t tag, float * dst, int mode, unsigned first_ns = 0) {
+    consume_to_smem_inl<MAXJ>(g, n, tag, dst, mode, first_ns);
 }
 
 // FP64 is scarce on this part (a double division is ~2400 cycles of dependent latency — measured: it dominated the whole
@@ -236,44 +241,73 @@ template <> struct Unpack<float> {
     __device__ static void w(const uint4 & u, float (&f)[4]) { f[0] = __uint_as_float(u.x); f[1] = __uint_as_float(u.y); f[2] = __uint_as_float(u.z); f[3] = __uint_as_float(u.w); }
 };
 
-// one weight row (in the ring) against the shared activation operand, lane order
-template <typename WT>
-__device__ __forceinline__ float row_dot(const unsigned char * row, const float * act, int K, int lane) {
+// NR adjacent weight rows against the shared activation operand, lane order.  SH: the rows sit in this warp's staging area and
+// are read with ld.shared (a generic-pointer load of shared memory is tracked like a global load and costs several times the
+// latency: ncu showed the unpack instructions behind it waiting on the long scoreboard); otherwise they stream from global
+// memory.  The NR chains are independent, so two rows cost barely more than one.
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+template <typename WT, bool SH, int NR>
+__device__ __forceinline__ void row_dot(const unsigned char * row, int row_bytes, const float * act, int K, int lane, float (&out)[NR]) {
     constexpr int G = Unpack<WT>::G;
     const int nsteps = K >> 5;
     const uint4 * wv = reinterpret_cast<const uint4 *>(row) + lane;
-    float acc = 0.0f;
+    const uint32_t sw = SH ? smem_u32(row) + lane * 16 : 0u;
+    const int rstride = row_bytes >> 4;                        // uint4 words between adjacent rows
+    auto fetch = [&](int n, int i) -> uint4 { return SH ? lds128(sw + n * row_bytes + i * 512) : wv[n * rstride + i * 32]; };
+    float acc[NR];
+#pragma unroll
+    for (int n = 0; n < NR; n++) acc[n] = 0.0f;
     if constexpr (G == 8) {
         const int ng = nsteps >> 3, tail = nsteps & 7;
         for (int g = 0; g < ng; g++) {
-            float w[8]; Unpack<WT>::w(wv[g * 32], w);
             const float4 a0 = *reinterpret_cast<const float4 *>(act + ((g * 2) * 32 + lane) * 4);
             const float4 a1 = *reinterpret_cast<const float4 *>(act + ((g * 2 + 1) * 32 + lane) * 4);
-            acc = __fmaf_rn(w[0], a0.x, acc); acc = __fmaf_rn(w[1], a0.y, acc); acc = __fmaf_rn(w[2], a0.z, acc); acc = __fmaf_rn(w[3], a0.w, acc);
-            acc = __fmaf_rn(w[4], a1.x, acc); acc = __fmaf_rn(w[5], a1.y, acc); acc = __fmaf_rn(w[6], a1.z, acc); acc = __fmaf_rn(w[7], a1.w, acc);
+#pragma unroll
+            for (int n = 0; n < NR; n++) {
+                float w[8]; Unpack<WT>::w(fetch(n, g), w);
+                float c = acc[n];
+                c = __fmaf_rn(w[0], a0.x, c); c = __fmaf_rn(w[1], a0.y, c); c = __fmaf_rn(w[2], a0.z, c); c = __fmaf_rn(w[3], a0.w, c);
+                c = __fmaf_rn(w[4], a1.x, c); c = __fmaf_rn(w[5], a1.y, c); c = __fmaf_rn(w[6], a1.z, c); c = __fmaf_rn(w[7], a1.w, c);
+                acc[n] = c;
+            }
         }
         if (tail) {
-            float w[8]; Unpack<WT>::w(wv[ng * 32], w);
             const float * a0 = act + ((ng * 2) * 32 + lane) * 4, * a1 = act + ((ng * 2 + 1) * 32 + lane) * 4;
 #pragma unroll
-            for (int e = 0; e < 8; e++) if (e < tail) acc = __fmaf_rn(w[e], e < 4 ? a0[e] : a1[e - 4], acc);
+            for (int n = 0; n < NR; n++) {
+                float w[8]; Unpack<WT>::w(fetch(n, ng), w);
+#pragma unroll
+                for (int e = 0; e < 8; e++) if (e < tail) acc[n] = __fmaf_rn(w[e], e < 4 ? a0[e] : a1[e - 4], acc[n]);
+            }
         }
     } else {
         // f32 rows: 4 chain steps per 16 bytes = one quad of the two-plane operand (quad index = chain step / 4)
         const int nq = nsteps >> 2, tail = nsteps & 3;
         for (int qd = 0; qd < nq; qd++) {
-            float w[4]; Unpack<WT>::w(wv[qd * 32], w);
             const float4 a = *reinterpret_cast<const float4 *>(act + (qd * 32 + lane) * 4);
-            acc = __fmaf_rn(w[0], a.x, acc); acc = __fmaf_rn(w[1], a.y, acc); acc = __fmaf_rn(w[2], a.z, acc); acc = __fmaf_rn(w[3], a.w, acc);
+#pragma unroll
+            for (int n = 0; n < NR; n++) {
+                float w[4]; Unpack<WT>::w(fetch(n, qd), w);
+                float c = acc[n];
+                c = __fmaf_rn(w[0], a.x, c); c = __fmaf_rn(w[1], a.y, c); c = __fmaf_rn(w[2], a.z, c); c = __fmaf_rn(w[3], a.w, c);
+                acc[n] = c;
+            }
         }
         if (tail) {
-            float w[4]; Unpack<WT>::w(wv[nq * 32], w);
             const float * a = act + (nq * 32 + lane) * 4;
 #pragma unroll
-            for (int e = 0; e < 4; e++) if (e < tail) acc = __fmaf_rn(w[e], a[e], acc);
+            for (int n = 0; n < NR; n++) {
+                float w[4]; Unpack<WT>::w(fetch(n, nq), w);
+#pragma unroll
+                for (int e = 0; e < 4; e++) if (e < tail) acc[n] = __fmaf_rn(w[e], a[e], acc[n]);
+            }
         }
     }
-    return lane_tree_reduce(acc);
+#pragma unroll
+    for (int n = 0; n < NR; n++) out[n] = lane_tree_reduce(acc[n]);
 }
 
 constexpr int kMaxTasks = 6;        // (h, k) score tasks per warp: H * block_size / (n_cta * kWarps) <= 16 * 1024 / (132 * 16) < 8
@@ -281,7 +315,7 @@ constexpr int kMaxTasks = 6;        // (h, k) score tasks per warp: H * block_si
 // Block-wide state of the phases, in static shared memory (a by-reference struct in local memory cost L1/L2 round trips on
 // the critical path: the 72 KB of per-thread stack frames do not fit the L1 left over next to 220 KB of shared memory).
 struct BlockCtx {
-    tagged_t * gq, * gk, * gv, * gx, * gff;
+    tagged_t * gq, * gk, * gv, * gx, * gff, * gatt, * gscores;
     float * mem_k, * mem_v, * logits;
     const __half * gelu_tab;
     unsigned long long policy;       // L2 evict-first descriptor of the weight stream
@@ -334,25 +368,42 @@ __device__ __noinline__ void run_phase(int phase, int ep, int layer, uint32_t ot
     mbar_wait(smem_u32(&s_bar[warp][half]), (uint32_t)(phase >> 1) & 1u);
     tstamp(sb);
     const int E = s_bc.E;
+    // one output row: lane 0 publishes / stores it in the form the consumer of this phase expects
+    auto emit = [&](int r, float v) {
+        if (ep == EP_QKV) {
+            const size_t slot_off = ((size_t) layer * s_bc.ctx + s_bc.n_past) * E;
+            if (r < E) publish(s_bc.gq + r, v, otag);
+            else if (r < 2 * E) { publish(s_bc.gk + (r - E), v, otag); s_bc.mem_k[slot_off + (r - E)] = v; }
+            else                { publish(s_bc.gv + (r - 2 * E), v, otag); s_bc.mem_v[slot_off + (r - 2 * E)] = v; }
+        } else if (ep == EP_RESID) {
+            publish(s_bc.gx + r, __fadd_rn(v, xs[r]), otag);
+        } else {
+            s_bc.logits[r] = v;
+        }
+    };
+    auto gelu_sel = [](float v, __half t) { return v <= -10.0f ? 0.0f : v >= 10.0f ? v : __half2float(t); };   // ggml_vec_gelu_f32, ggml.c:2557-2571
     int j = 0;
-    for (int r = a; r < b; r++, j++) {
+    for (int r = a; r < b;) {
         const unsigned char * row = staged ? slot + (size_t) j * p.row_bytes : p.w + (size_t) r * p.row_bytes;
-        const float v = row_dot<WT>(row, act, p.K, lane);
-        if (lane == 0) {
-            if (ep == EP_QKV) {
-                const size_t slot_off = ((size_t) layer * s_bc.ctx + s_bc.n_past) * E;
-                if (r < E) publish(s_bc.gq + r, v, otag);
-                else if (r < 2 * E) { publish(s_bc.gk + (r - E), v, otag); s_bc.mem_k[slot_off + (r - E)] = v; }
-                else                { publish(s_bc.gv + (r - 2 * E), v, otag); s_bc.mem_v[slot_off + (r - 2 * E)] = v; }
-            } else if (ep == EP_RESID) {
-                publish(s_bc.gx + r, __fadd_rn(v, xs[r]), otag);
-            } else if (ep == EP_GELU) {
-                float gl;
-                if (v <= -10.0f) gl = 0.0f; else if (v >= 10.0f) gl = v; else gl = __half2float(s_bc.gelu_tab[__half_as_ushort(__float2half_rn(v))]);
-                publish(s_bc.gff + r, gl, otag);
-            } else {
-                s_bc.logits[r] = v;
+        if (r + 1 < b) {                                      // two adjacent rows at once: independent chains, and both table look-ups in flight together
+            float v[2];
+            if (staged) row_dot<WT, true, 2>(row, p.row_bytes, act, p.K, lane, v);
+            else { float u[1]; row_dot<WT, false, 1>(row, p.row_bytes, act, p.K, lane, u); v[0] = u[0]; row_dot<WT, false, 1>(row + p.row_bytes, p.row_bytes, act, p.K, lane, u); v[1] = u[0]; }
+            if (lane == 0) {
+                if (ep == EP_GELU) {
+                    const __half t0 = s_bc.gelu_tab[__half_as_ushort(__float2half_rn(v[0]))], t1 = s_bc.gelu_tab[__half_as_ushort(__float2half_rn(v[1]))];
+                    publish(s_bc.gff + r, gelu_sel(v[0], t0), otag); publish(s_bc.gff + r + 1, gelu_sel(v[1], t1), otag);
+                } else { emit(r, v[0]); emit(r + 1, v[1]); }
             }
+            r += 2; j += 2;
+        } else {
+            float v[1];
+            if (staged) row_dot<WT, true, 1>(row, p.row_bytes, act, p.K, lane, v); else row_dot<WT, false, 1>(row, p.row_bytes, act, p.K, lane, v);
+            if (lane == 0) {
+                if (ep == EP_GELU) publish(s_bc.gff + r, gelu_sel(v[0], s_bc.gelu_tab[__half_as_ushort(__float2half_rn(v[0]))]), otag);
+                else emit(r, v[0]);
+            }
+            r += 1; j += 1;
         }
     }
     __syncwarp();                                             // all lanes are done reading this half
@@ -376,8 +427,6 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
     const int E = A.E, H = A.H, L = A.L, ctx = A.block_size, n_past = A.n_past, n_kv = n_past + 1;
     constexpr bool kRound = sizeof(WT) == 2;
     constexpr int kSinkAct = kRound ? SINK_ACT_R16 : SINK_ACT;
-    tagged_t * const gq = (tagged_t *) A.gq, * const gk = (tagged_t *) A.gk, * const gv = (tagged_t *) A.gv, * const gatt = (tagged_t *) A.gatt,
-             * const gx = (tagged_t *) A.gx, * const gff = (tagged_t *) A.gff, * const gscores = (tagged_t *) A.gscores;
 
     // ---- per-CTA row ranges, block context and the staging barriers in shared memory ----
     PhaseSched * sched = reinterpret_cast<PhaseSched *>(dsm + SmemLayout::sched);
@@ -393,7 +442,8 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
         sched[tid] = e;
     }
     if (tid == kThreads - 1) {
-        s_bc.gq = gq; s_bc.gk = gk; s_bc.gv = gv; s_bc.gx = gx; s_bc.gff = gff;
+        s_bc.gq = (tagged_t *) A.gq; s_bc.gk = (tagged_t *) A.gk; s_bc.gv = (tagged_t *) A.gv; s_bc.gx = (tagged_t *) A.gx; s_bc.gff = (tagged_t *) A.gff;
+        s_bc.gatt = (tagged_t *) A.gatt; s_bc.gscores = (tagged_t *) A.gscores;
         s_bc.mem_k = A.mem_k; s_bc.mem_v = A.mem_v; s_bc.logits = A.logits; s_bc.gelu_tab = A.gelu_tab;
         s_bc.policy = l2_evict_first_policy();
         s_bc.E = E; s_bc.ctx = ctx; s_bc.n_past = n_past; s_bc.n_phases = n_phases;
@@ -440,11 +490,11 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
         // column dd) goes out before anything is waited for, so the loads drain while P2 runs ----
         const int pv_v = tid >> 4, pv_dd = tid & 15;
         const int col0 = pv_h * D + pv_c * 16;
-        float vreg[32]; float vl = 0.0f;
+        float vlo[16], vhi[16]; float vl = 0.0f;              // chain steps 0..15 (positions < 512) now; 16..31 at the start of P3 (registers)
         if (pv_cta) {
             const float * Vc = A.mem_v + (size_t) il * ctx * E + col0;
 #pragma unroll
-            for (int c = 0; c < 32; c++) { const int k = pv_v + 32 * c; if (k < np && k < n_past) vreg[c] = __ldcg(Vc + (size_t) k * E + pv_dd); }
+            for (int c = 0; c < 16; c++) { const int k = pv_v + 32 * c; if (k < np && k < n_past) vlo[c] = __ldcg(Vc + (size_t) k * E + pv_dd); }
             if (np + pv_v < n_past) vl = __ldcg(Vc + (size_t)(np + pv_v) * E + pv_dd);          // one element of the leftover rows k = np + v
         }
 
@@ -465,7 +515,7 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
                 }
             }
             tstamp(6);
-            consume_to_smem<2>(gq, E, t_qkv, qs, SINK_PLAIN);
+            consume_to_smem<2>(s_bc.gq, E, t_qkv, qs, SINK_PLAIN);
             tstamp(7);
 #pragma unroll
             for (int i = 0; i < kMaxTasks; i++) {
@@ -475,11 +525,11 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
                     float acc = 0.0f;
 #pragma unroll
                     for (int c = 0; c < DSTEPS; c++) {
-                        const float kv = (k < n_past) ? kf[i][c] : consume1(gk + h * D + c * 32 + lane, t_qkv);   // the new position's key comes through the exchange
+                        const float kv = (k < n_past) ? kf[i][c] : consume1(s_bc.gk + h * D + c * 32 + lane, t_qkv);   // the new position's key comes through the exchange
                         acc = __fmaf_rn(kv, qs[h * D + c * 32 + lane], acc);
                     }
                     const float r = lane_tree_reduce(acc);
-                    if (lane == 0) publish(gscores + (size_t) h * ctx + k, __fmul_rn(r, scale), t_sc);
+                    if (lane == 0) publish(s_bc.gscores + (size_t) h * ctx + k, __fmul_rn(r, scale), t_sc);
                 }
             }
 #pragma unroll 1
@@ -488,11 +538,11 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
                 float acc = 0.0f;
 #pragma unroll
                 for (int c = 0; c < DSTEPS; c++) {
-                    const float kv = (k < n_past) ? __ldcg(Kc + (size_t) k * E + h * D + c * 32 + lane) : consume1(gk + h * D + c * 32 + lane, t_qkv);
+                    const float kv = (k < n_past) ? __ldcg(Kc + (size_t) k * E + h * D + c * 32 + lane) : consume1(s_bc.gk + h * D + c * 32 + lane, t_qkv);
                     acc = __fmaf_rn(kv, qs[h * D + c * 32 + lane], acc);
                 }
                 const float r = lane_tree_reduce(acc);
-                if (lane == 0) publish(gscores + (size_t) h * ctx + k, __fmul_rn(r, scale), t_sc);
+                if (lane == 0) publish(s_bc.gscores + (size_t) h * ctx + k, __fmul_rn(r, scale), t_sc);
             }
         }
         tstamp(8);
@@ -500,11 +550,16 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
         // ---- P3: soft_max + P.V, one CTA per (head, 16 columns of the head) ----
         if (pv_cta) {
             const int h = pv_h, v = pv_v, dd = pv_dd;
-            const float v_new = consume1(gv + col0 + dd, t_qkv);     // value row of the new position
+            {
+                const float * Vc = A.mem_v + (size_t) il * ctx * E + col0;
+#pragma unroll
+                for (int c = 0; c < 16; c++) { const int k = v + 32 * (c + 16); if (k < np && k < n_past) vhi[c] = __ldcg(Vc + (size_t) k * E + dd); }
+            }
+            const float v_new = consume1(s_bc.gv + col0 + dd, t_qkv);     // value row of the new position
             __syncthreads();                                         // slower warps may still be reading q (in `qs`) for their score tasks
             tstamp(9);
             float * p = qs;                                          // scores row -> exp(score - max); the 1/sum factor is applied on use
-            consume_to_smem<2>(gscores + (size_t) h * ctx, n_kv, t_sc, p, SINK_PLAIN);
+            consume_to_smem<2>(s_bc.gscores + (size_t) h * ctx, n_kv, t_sc, p, SINK_PLAIN);
             tstamp(10);
             float mx = __int_as_float(0xff800000);
 #pragma unroll 1
@@ -572,7 +627,7 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
 #pragma unroll
             for (int c = 0; c < 32; c++) {
                 const int k = v + 32 * c;
-                if (k < np) acc = __fmaf_rn(k < n_past ? vreg[c] : v_new, __fmul_rn(p[k], sc_f), acc);
+                if (k < np) acc = __fmaf_rn(k < n_past ? (c < 16 ? vlo[c & 15] : vhi[c & 15]) : v_new, __fmul_rn(p[k], sc_f), acc);
             }
             part[v * 16 + dd] = acc;
             // leftovers k = np .. n_kv-1 as the pinned build compiles them (oracle orc_vec_dot_f32): 8-groups and a 4-group of
@@ -596,19 +651,19 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
                     const float tj = act[j * 16 + tid];
                     if (j < n4) sum = __fadd_rn(sum, tj); else sum = __fmaf_rn(tj, __fmul_rn(p[np + j], sc_f), sum);
                 }
-                publish(gatt + col0 + tid, sum, t_att);
+                publish(s_bc.gatt + col0 + tid, sum, t_att);
             }
             __syncthreads();                                     // `act` / `qs` are reused by the next phase
         }
         tstamp(16);
 
         // ---- P4: c_proj + residual ----
-        consume_to_smem<2>(gatt, E, t_att, act, kSinkAct);
+        consume_to_smem<2>(s_bc.gatt, E, t_att, act, kSinkAct);
         tstamp(17);
         run_phase<WT>(4 * il + 1, EP_RESID, il, t_x1, 18);
 
         // ---- P5: LN2 -> c_fc -> GELU ----
-        consume_to_smem<2>(gx, E, t_x1, xs, SINK_PLAIN, s_first_ns);
+        consume_to_smem<2>(s_bc.gx, E, t_x1, xs, SINK_PLAIN, s_first_ns);
         tstamp(21);
         block_layernorm<kRound>(xs, E, inv_E, lv.ln_2_g, lv.ln_2_b, act, red, A.ln_fallbacks, 22);
         tstamp(23);
@@ -617,11 +672,11 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
         tstamp(27);
 
         // ---- P6: mlp/c_proj + residual ----
-        consume_to_smem<8>(gff, 4 * E, t_ff, act, kSinkAct);
+        consume_to_smem<8>(s_bc.gff, 4 * E, t_ff, act, kSinkAct);
         tstamp(28);
         run_phase<WT>(4 * il + 3, EP_RESID, il, t_x2, 29);
 
-        consume_to_smem<2>(gx, E, t_x2, xs, SINK_PLAIN, s_first_ns);
+        consume_to_smem<2>(s_bc.gx, E, t_x2, xs, SINK_PLAIN, s_first_ns);
     }
     if (tid == A.timing_tid) s_tim_layer = L;                 // row L: start of the final norm
     // ---- final norm + lm_head window ----
