@@ -22,7 +22,9 @@ struct bark_context {
     unsigned tag_base = 0;                           // epoch counter of the decode kernel's tagged exchanges (advances 6*L per token)
     int n_sm = 0; bool use_decode_kernel = true;
     bool kv_reuse = true; unsigned long long n_kv_reused = 0;   // coarse windows start from the cached prefix (bark_api.cu run_coarse)
-    int timing_tid = 0; unsigned poll_ns = 40, first_ns = 0;       // BARK_B200_DECODE_TIMING_TID / BARK_B200_POLL_NS (experiment knobs of the decode kernel)
+    // decode-kernel knobs (BARK_B200_DECODE_TIMING_TID / BARK_B200_POLL_NS / BARK_B200_POLL_FIRST_NS); defaults from the measured sweep
+    // in profiles/r01_decode_knob_sweep.md: 40 ns back-off between polls, 500 ns head start for the two residual exchanges
+    int timing_tid = 0; unsigned poll_ns = 40, first_ns = 500;
     unsigned long long * d_timing = nullptr;         // optional phase timestamps of the decode kernel (BARK_B200_DECODE_TIMING=1)
 
     bark::Workspace ws;
