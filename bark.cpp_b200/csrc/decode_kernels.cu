@@ -84,7 +84,7 @@ __device__ __forceinline__ tagged_t peek(const tagged_t * p) {
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
     return w;
 }
-__shared__ unsigned s_poll_ns, s_first_ns;                           // back-off between polls (DecodeArgs::poll_ns, default 40); head start given to the two residual exchanges
+__shared__ unsigned s_poll_ns, s_first_ns, s_att_ns;                           // back-off between polls (DecodeArgs::poll_ns, default 40); head start given to the two residual exchanges
 __device__ __forceinline__ float consume1(const tagged_t * p, uint32_t tag) {
     tagged_t w = peek(p);
     while ((uint32_t)(w >> 32) != tag) { __nanosleep(s_poll_ns); w = peek(p); }       // back off: thousands of pollers share a few L2 lines
@@ -100,8 +100,11 @@ __device__ __forceinline__ int act_index(int k) {
 // every CTA stamps layer 5 (rows 64 + cta); 32 slots per row, %globaltimer nanoseconds.  s_tim is null in normal runs.
 __shared__ unsigned long long * s_tim;
 __shared__ int s_tim_layer, s_tim_tid;                               // s_tim_tid: the stamping thread (0, or lane 0 of another warp: BARK_B200_DECODE_TIMING_TID)
+// TM = false (every normal run) compiles the stamps away: even a not-taken stamp is two shared-memory loads and a branch on
+// the critical path of a single warp, ~30 times per layer.
+template <bool TM>
 __device__ __forceinline__ void tstamp(int i) {
-    if (s_tim && (int) threadIdx.x == s_tim_tid) {
+    if (TM && s_tim && (int) threadIdx.x == s_tim_tid) {
         unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         const int layer = s_tim_layer;
         if (blockIdx.x == 0) s_tim[layer * 32 + i] = t;
@@ -156,7 +159,7 @@ __device__ __forceinline__ double approx_rcp(double x) {
 // takes the rounding decision itself (identical inputs, identical arithmetic -> identical result), instead of funnelling
 // through warp 0 and a second barrier.  red: [0,16) double mean partials, [16,24) 16 float |x| partials, [24,40) double
 // variance partials.
-template <bool ROUND16>
+template <bool ROUND16, bool TM>
 __device__ __noinline__ void block_layernorm(const float * xs, int E, double inv_E, const float * __restrict__ g, const float * __restrict__ b, float * act,
                                              double * red, unsigned * fallback_counter, int sb) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -192,7 +195,7 @@ __device__ __noinline__ void block_layernorm(const float * xs, int E, double inv
             if (fallback_counter && tid == 0) atomicAdd(fallback_counter, 1u);
         }
     }
-    tstamp(sb);
+    tstamp<TM>(sb);
     // ---- variance ----
     const float v0 = __fsub_rn(x0, mean), v1 = __fsub_rn(x1, mean);
     double s2 = (h0 ? (double) __fmul_rn(v0, v0) : 0.0) + (h1 ? (double) __fmul_rn(v1, v1) : 0.0);
@@ -354,7 +357,7 @@ __device__ __forceinline__ void stage_rows(int phase) {
 
 // This warp's rows of `phase`: lane-order dot against the shared activation operand; outputs are published with epoch
 // `otag` (or stored, for the logits).  Then the rows of the phase after next start streaming in.  No block-wide synchronisation.
-template <typename WT>
+template <typename WT, bool TM>
 __device__ __noinline__ void run_phase(int phase, int ep, int layer, uint32_t otag, int sb) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const PhaseSched p = sched_tab()[phase];
@@ -366,7 +369,7 @@ __device__ __noinline__ void run_phase(int phase, int ep, int layer, uint32_t ot
     const bool staged = bytes != 0 && bytes <= (uint32_t) kHalfSlotBytes;
     const unsigned char * slot = dsm + SmemLayout::wslot + (size_t) warp * kWarpSlotBytes + (size_t) half * kHalfSlotBytes;
     mbar_wait(smem_u32(&s_bar[warp][half]), (uint32_t)(phase >> 1) & 1u);
-    tstamp(sb);
+    tstamp<TM>(sb);
     const int E = s_bc.E;
     // one output row: lane 0 publishes / stores it in the form the consumer of this phase expects
     auto emit = [&](int r, float v) {
@@ -407,14 +410,14 @@ __device__ __noinline__ void run_phase(int phase, int ep, int layer, uint32_t ot
         }
     }
     __syncwarp();                                             // all lanes are done reading this half
-    tstamp(sb + 1);
+    tstamp<TM>(sb + 1);
     stage_rows(phase + 2);
-    tstamp(sb + 2);
+    tstamp<TM>(sb + 2);
 }
 
 }  // namespace
 
-template <typename WT, int DSTEPS>
+template <typename WT, int DSTEPS, bool TM>
 __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs A) {
     float * act = reinterpret_cast<float *>(dsm + SmemLayout::act);
     float * xs = reinterpret_cast<float *>(dsm + SmemLayout::x);
@@ -447,7 +450,7 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
         s_bc.mem_k = A.mem_k; s_bc.mem_v = A.mem_v; s_bc.logits = A.logits; s_bc.gelu_tab = A.gelu_tab;
         s_bc.policy = l2_evict_first_policy();
         s_bc.E = E; s_bc.ctx = ctx; s_bc.n_past = n_past; s_bc.n_phases = n_phases;
-        s_tim = A.timing; s_tim_layer = 0; s_tim_tid = A.timing_tid; s_poll_ns = A.poll_ns; s_first_ns = A.first_ns;
+        s_tim = A.timing; s_tim_layer = 0; s_tim_tid = A.timing_tid; s_poll_ns = A.poll_ns; s_first_ns = A.first_ns; s_att_ns = A.att_ns;
     }
     if (lane == 0) {
         mbar_init(smem_u32(&s_bar[warp][0]), 1); mbar_init(smem_u32(&s_bar[warp][1]), 1);
@@ -480,11 +483,11 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
         const uint32_t t_qkv = tag + 1, t_sc = tag + 2, t_att = tag + 3, t_x1 = tag + 4, t_ff = tag + 5, t_x2 = tag + 6;
         tag += 6;
         if (tid == A.timing_tid) s_tim_layer = il;           // (the stamping thread is the only reader)
-        tstamp(0);
+        tstamp<TM>(0);
         // ---- P1: LN1 -> QKV ----
-        block_layernorm<kRound>(xs, E, inv_E, lv.ln_1_g, lv.ln_1_b, act, red, A.ln_fallbacks, 1);
-        tstamp(2);
-        run_phase<WT>(4 * il + 0, EP_QKV, il, t_qkv, 3);
+        block_layernorm<kRound, TM>(xs, E, inv_E, lv.ln_1_g, lv.ln_1_b, act, red, A.ln_fallbacks, 1);
+        tstamp<TM>(2);
+        run_phase<WT, TM>(4 * il + 0, EP_QKV, il, t_qkv, 3);
 
         // ---- P3 operands first: this thread's chain of V values of older positions (thread (v, dd): virtual lane v of output
         // column dd) goes out before anything is waited for, so the loads drain while P2 runs ----
@@ -514,9 +517,9 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
                     }
                 }
             }
-            tstamp(6);
+            tstamp<TM>(6);
             consume_to_smem<2>(s_bc.gq, E, t_qkv, qs, SINK_PLAIN);
-            tstamp(7);
+            tstamp<TM>(7);
 #pragma unroll
             for (int i = 0; i < kMaxTasks; i++) {
                 const int t = gw + i * nw;
@@ -545,7 +548,7 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
                 if (lane == 0) publish(s_bc.gscores + (size_t) h * ctx + k, __fmul_rn(r, scale), t_sc);
             }
         }
-        tstamp(8);
+        tstamp<TM>(8);
 
         // ---- P3: soft_max + P.V, one CTA per (head, 16 columns of the head) ----
         if (pv_cta) {
@@ -557,10 +560,10 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
             }
             const float v_new = consume1(s_bc.gv + col0 + dd, t_qkv);     // value row of the new position
             __syncthreads();                                         // slower warps may still be reading q (in `qs`) for their score tasks
-            tstamp(9);
+            tstamp<TM>(9);
             float * p = qs;                                          // scores row -> exp(score - max); the 1/sum factor is applied on use
             consume_to_smem<2>(s_bc.gscores + (size_t) h * ctx, n_kv, t_sc, p, SINK_PLAIN);
-            tstamp(10);
+            tstamp<TM>(10);
             float mx = __int_as_float(0xff800000);
 #pragma unroll 1
             for (int i = tid; i < n_kv; i += kThreads) mx = fmaxf(mx, p[i]);
@@ -572,7 +575,7 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
             mx = fred[0];
 #pragma unroll
             for (int w = 1; w < kWarps; w++) mx = fmaxf(mx, fred[w]);
-            tstamp(11);
+            tstamp<TM>(11);
             // exp: whole chunks of 8 through the vector polynomial (ggml.c:2706-2746), the n_kv % 8 tail through libm expf
             // (ggml.c:2880-2884) — one element per thread, every element independent of the others
             const int nchunks = n_kv >> 3, n8 = nchunks << 3;
@@ -582,7 +585,7 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
                 p[i] = i < n8 ? ggml_v_expf_dev(d) : glibc_expf_dev(d);
             }
             __syncthreads();
-            tstamp(12);
+            tstamp<TM>(12);
             // sum = sequential double accumulation of the chunk sums (in-chunk float tree of the 8-wide vector code), then the
             // tail (ggml.c:2845-2888).  All terms are positive, so a tree sum S brackets the sequential one within
             // +-2n*2^-53*S; if 1/sum rounds to the same float at both ends of the bracket the order cannot matter, else replay
@@ -621,7 +624,7 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
                 }
             }
             __syncthreads();
-            tstamp(13);
+            tstamp<TM>(13);
             const float sc_f = bc[2];                                // probabilities = p[k] * sc_f (ggml_vec_scale_f32), formed where they are used
             float acc = 0.0f;
 #pragma unroll
@@ -640,7 +643,7 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
                 act[v * 16 + dd] = v < n4 ? __fmul_rn(vv, __fmul_rn(p[np + v], sc_f)) : vv;
             }
             __syncthreads();
-            tstamp(15);
+            tstamp<TM>(15);
             if (tid < 16) {
                 float a32[32];
 #pragma unroll
@@ -655,50 +658,54 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
             }
             __syncthreads();                                     // `act` / `qs` are reused by the next phase
         }
-        tstamp(16);
+        tstamp<TM>(16);
 
         // ---- P4: c_proj + residual ----
-        consume_to_smem<2>(s_bc.gatt, E, t_att, act, kSinkAct);
-        tstamp(17);
-        run_phase<WT>(4 * il + 1, EP_RESID, il, t_x1, 18);
+        consume_to_smem<2>(s_bc.gatt, E, t_att, act, kSinkAct, pv_cta ? 0u : s_att_ns);   // CTAs without a soft_max tile would poll for the whole of P3
+        tstamp<TM>(17);
+        run_phase<WT, TM>(4 * il + 1, EP_RESID, il, t_x1, 18);
 
         // ---- P5: LN2 -> c_fc -> GELU ----
         consume_to_smem<2>(s_bc.gx, E, t_x1, xs, SINK_PLAIN, s_first_ns);
-        tstamp(21);
-        block_layernorm<kRound>(xs, E, inv_E, lv.ln_2_g, lv.ln_2_b, act, red, A.ln_fallbacks, 22);
-        tstamp(23);
-        run_phase<WT>(4 * il + 2, EP_GELU, il, t_ff, 24);
+        tstamp<TM>(21);
+        block_layernorm<kRound, TM>(xs, E, inv_E, lv.ln_2_g, lv.ln_2_b, act, red, A.ln_fallbacks, 22);
+        tstamp<TM>(23);
+        run_phase<WT, TM>(4 * il + 2, EP_GELU, il, t_ff, 24);
         __syncthreads();                                         // the ff vector lands in `act`, which slower warps may still be reading
-        tstamp(27);
+        tstamp<TM>(27);
 
         // ---- P6: mlp/c_proj + residual ----
         consume_to_smem<8>(s_bc.gff, 4 * E, t_ff, act, kSinkAct);
-        tstamp(28);
-        run_phase<WT>(4 * il + 3, EP_RESID, il, t_x2, 29);
+        tstamp<TM>(28);
+        run_phase<WT, TM>(4 * il + 3, EP_RESID, il, t_x2, 29);
 
         consume_to_smem<2>(s_bc.gx, E, t_x2, xs, SINK_PLAIN, s_first_ns);
     }
     if (tid == A.timing_tid) s_tim_layer = L;                 // row L: start of the final norm
     // ---- final norm + lm_head window ----
-    tstamp(0);
-    block_layernorm<kRound>(xs, E, inv_E, A.ln_f_g, A.ln_f_b, act, red, A.ln_fallbacks, 1);
-    tstamp(2);
-    run_phase<WT>(4 * L, EP_LOGITS, 0, 0, 3);
+    tstamp<TM>(0);
+    block_layernorm<kRound, TM>(xs, E, inv_E, A.ln_f_g, A.ln_f_b, act, red, A.ln_fallbacks, 1);
+    tstamp<TM>(2);
+    run_phase<WT, TM>(4 * L, EP_LOGITS, 0, 0, 3);
 }
 
 static size_t decode_smem_bytes() { return (size_t) SmemLayout::total + 128; }
 
 int decode_tags_per_step(int n_layer) { return 6 * n_layer; }
 
-template <typename WT, int DSTEPS>
-static void launch_one(DecodeArgs a, int n_sm, cudaStream_t s) {
+template <typename WT, int DSTEPS, bool TM>
+static void launch_variant(DecodeArgs a, int n_sm, cudaStream_t s) {
     static bool configured = false;
     if (!configured) {
-        BARK_CUDA_CHECK(cudaFuncSetAttribute(gpt_decode_step_kernel<WT, DSTEPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) decode_smem_bytes()));
+        BARK_CUDA_CHECK(cudaFuncSetAttribute(gpt_decode_step_kernel<WT, DSTEPS, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) decode_smem_bytes()));
         configured = true;
     }
     void * kargs[] = {(void *) &a};
-    BARK_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *) gpt_decode_step_kernel<WT, DSTEPS>, dim3(n_sm), dim3(kThreads), kargs, decode_smem_bytes(), s));
+    BARK_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *) gpt_decode_step_kernel<WT, DSTEPS, TM>, dim3(n_sm), dim3(kThreads), kargs, decode_smem_bytes(), s));
+}
+template <typename WT, int DSTEPS>
+static void launch_one(DecodeArgs a, int n_sm, cudaStream_t s) {
+    if (a.timing) launch_variant<WT, DSTEPS, true>(a, n_sm, s); else launch_variant<WT, DSTEPS, false>(a, n_sm, s);   // stamps exist only in the BARK_B200_DECODE_TIMING build of the kernel
 }
 
 void launch_decode_step(const DecodeArgs & args, WType wt, int n_sm, cudaStream_t s) {

@@ -84,7 +84,7 @@ static void decode_step(bark_context * ctx, GPTModel & m, int token, const int32
     a.E = m.n_embd; a.H = m.n_head; a.L = m.n_layer; a.block_size = m.block_size; a.n_past = n_past; a.token = token; a.lm_lo = lm_lo; a.lm_hi = lm_hi;
     a.token_ptr = d_token; a.n_vocab_in = m.n_in_vocab;
     a.inv_E = 1.0 / (double) m.n_embd;
-    a.timing_tid = ctx->timing_tid; a.poll_ns = ctx->poll_ns; a.first_ns = ctx->first_ns;
+    a.timing_tid = ctx->timing_tid; a.poll_ns = ctx->poll_ns; a.first_ns = ctx->first_ns; a.att_ns = ctx->att_ns;
     const double es = m.wtype == W_F16 ? 2.0 : 4.0;
     const double E = m.n_embd, L = m.n_layer;
     g_next_bytes = (12.0 * L * E * E + (double)(lm_hi - lm_lo) * E) * es + 2.0 * L * (double)(n_past + 1) * E * 4.0 + 2.0 * L * E * 4.0 + (double)(lm_hi - lm_lo) * 4.0;   // SURVEY §8d B_tok
