@@ -442,6 +442,8 @@ void alloc_workspace(bark_context * ctx) {
 // ---------------------------------------------------------------------------------------------
 // ggml.h shim
 // ---------------------------------------------------------------------------------------------
+extern "C" struct ggml_context * ggml_init(struct ggml_init_params) { static int token; return reinterpret_cast<struct ggml_context *>(&token); }   // nothing to initialise: f16 conversions are hardware instructions here
+extern "C" void    ggml_free(struct ggml_context *) {}
 extern "C" void    ggml_time_init(void) {}
 extern "C" int64_t ggml_time_us(void) { return now_us(); }
 extern "C" int64_t ggml_time_ms(void) { return now_us() / 1000; }

@@ -212,7 +212,8 @@ def run_ours(args):
             f_h, f_t = gbs / P["hbm_gbs"], tfs / P["tflops"]
             common = dict(kernel=name, launches=v["launches"], avg_launch_us=round(sec * 1e6 / max(v["launches"], 1), 2), share=round(v["ms"] / tot_ms, 4),
                           traffic=measured_traffic(name), algorithmic_bytes_per_launch=int(v["bytes"] / max(v["launches"], 1)), peak_source=P["source"])
-            if f_h >= f_t:
+            ridge = P["tflops"] * 1e12 / (P["hbm_gbs"] * 1e9)                       # flop per byte where the two roofs meet
+            if v["bytes"] > 0 and (v["flops"] <= 0 or v["flops"] / v["bytes"] < ridge):   # the roof that bounds this kernel's arithmetic intensity
                 return dict(bound="hbm", achieved=round(gbs, 1), peak=P["hbm_gbs"], unit="GB/s", frac=round(f_h, 4), **common)
             return dict(bound="tensor", achieved=round(tfs, 2), peak=P["tflops"], unit="TFLOP/s", frac=round(f_t, 4),
                         note="parity path: f16 operands, fp32 FMA chains in the reference's lane order on CUDA cores; bf16 cuBLAS peak is the ceiling of the contraction without the bit-exactness constraint", **common)

@@ -54,7 +54,8 @@ BARK_API unsigned bark_b200_layernorm_fallbacks(struct bark_context * ctx); /* L
 BARK_API void bark_b200_profile_enable(int on);                            /* CUDA-event timing of every kernel launch; clears previous records */
 BARK_API int  bark_b200_profile_report(char * buf, int cap);               /* JSON {kernel: {launches, ms, work}}; returns bytes needed */
 BARK_API void bark_b200_io_counters(unsigned long long * h2d_bytes, unsigned long long * d2h_bytes, int reset);
-/* with BARK_B200_DECODE_TIMING=1 in the environment at load: globaltimer stamps [layer][16] of the last decode step (CTA 0) */
+/* with BARK_B200_DECODE_TIMING=1 in the environment at load: %globaltimer stamps [256][32] of the last decode step (rows 0..L: the
+ * stamping thread of CTA 0 per layer; rows 64 + cta: every CTA at layer 5; slot meaning in tools/decode_timing.py) */
 BARK_API int  bark_b200_decode_timing(struct bark_context * ctx, unsigned long long * out, int n);
 
 #ifdef __cplusplus

@@ -16,7 +16,7 @@ def header_symbols():
         src = open(os.path.join(ROOT, "include", h)).read()
         syms |= set(re.findall(r"BARK_API[^;(]*?\b(bark_\w+)\s*\(", src))
     src = open(os.path.join(ROOT, "include", "ggml.h")).read()
-    syms |= set(re.findall(r"\b(ggml_time_\w+)\s*\(", src))
+    syms |= set(re.findall(r"\b(ggml_time_\w+|ggml_init|ggml_free)\s*\(", src))
     return syms
 
 
@@ -105,3 +105,20 @@ int main(int argc, char ** argv) {
                            "-Wl,-rpath," + libdir])
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 3 and "load failed as expected" in r.stdout
+
+
+def test_reference_quantize_tool_builds_and_runs_against_this_library(pkg, weights_file, tmp_path):
+    """The reference's own examples/quantize/main.cpp, unchanged, compiled against include/ and linked with -lbark_b200:
+    its output must equal the library call's (which tests/test_quantize.py pins byte for byte against the reference tool)."""
+    src = "/root/reference/examples/quantize/main.cpp"
+    if not os.path.exists(src):
+        pytest.skip("reference tree not present (GPU box)")
+    exe = tmp_path / "quantize"
+    libdir = os.path.dirname(pkg.LIB_PATH)
+    subprocess.check_call(["g++", "-std=c++17", "-I", os.path.join(ROOT, "include"), src, "-o", str(exe), "-L", libdir, "-lbark_b200", "-Wl,-rpath," + libdir])
+    inp = weights_file("tiny", "f16")
+    out_tool, out_lib = tmp_path / "tool_q4.bin", tmp_path / "lib_q4.bin"
+    r = subprocess.run([str(exe), inp, str(out_tool), "q4_0"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-500:]
+    assert pkg.lib().bark_model_quantize(inp.encode(), str(out_lib).encode(), 2)
+    assert open(out_tool, "rb").read() == open(out_lib, "rb").read()
