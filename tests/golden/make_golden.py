@@ -18,10 +18,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 import __graft_entry__ as graft  # noqa: E402
 
-CASES = [  # (config, ftype, weight seed, rng seed, n_steps_text_encoder, prompt)
-    ("tiny", "f16", 1234, 0, 20, "hello world"),
-    ("mini", "f32", 1234, 0, 45, "hello world"),       # BASELINE config 1 shape: f32 GPT + f16 codec; 67 frames, 3 coarse windows
-    ("mini", "f16", 1234, 7, 30, "The quick brown fox, 42!"),
+CASES = [  # (config, ftype, weight seed, rng seed, n_steps_text_encoder, prompt, quant)
+    ("tiny", "f16", 1234, 0, 20, "hello world", ""),
+    ("mini", "f32", 1234, 0, 45, "hello world", ""),       # BASELINE config 1 shape: f32 GPT + f16 codec; 67 frames, 3 coarse windows
+    ("mini", "f16", 1234, 7, 30, "The quick brown fox, 42!", ""),
+    ("tiny", "f16", 1234, 0, 16, "hello world", "q4_0"),   # BASELINE config 4 shape: q4_0 GPT (the reference's own bark_model_quantize) + f16 codec
+    ("mini", "f32", 1234, 3, 24, "Quantised, 7 times.", "q4_0"),
 ]
 
 
@@ -37,10 +39,19 @@ def main():
     out_dir = os.path.dirname(os.path.abspath(__file__))
     tmp = "/tmp/bark_b200_fixtures"
     os.makedirs(tmp, exist_ok=True)
-    for config, ftype, wseed, seed, n_steps, prompt in CASES:
+    import ctypes as C
+    for config, ftype, wseed, seed, n_steps, prompt, quant in CASES:
         path = os.path.join(tmp, f"{config}_{ftype}_{wseed}.bin")
         if not os.path.exists(path):
             weights.write_weights(path, weights.CONFIGS[config](weights.F16 if ftype == "f16" else weights.F32), wseed)
+        if quant:                                            # the REFERENCE's quantizer makes the file (ggml_init first: f16 tables, examples/quantize/main.cpp:67-72)
+            orc.Ref(path)
+            R = C.CDLL(orc.REF_SO)
+            R.bark_model_quantize.restype = C.c_bool
+            R.bark_model_quantize.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
+            qpath = os.path.join(tmp, f"{config}_{ftype}_{wseed}_{quant}_ref.bin")
+            assert quant == "q4_0" and R.bark_model_quantize(path.encode(), qpath.encode(), 2)
+            path = qpath
         r = orc.Ref(path, seed=seed, n_steps=n_steps)
         prompt_ids = r.tokenize(prompt)
         # teacher-forced traces: semantic prefill + 3 decode steps, one fine pass
@@ -55,8 +66,8 @@ def main():
         r.reseed(seed)
         g = r.generate(prompt)
         np.savez_compressed(
-            os.path.join(out_dir, f"{config}_{ftype}.npz"),
-            config=config, ftype=ftype, weight_seed=wseed, seed=seed, n_steps=n_steps, prompt=prompt,
+            os.path.join(out_dir, f"{config}_{ftype}{'_' + quant if quant else ''}.npz"),
+            config=config, ftype=ftype, quant=quant, weight_seed=wseed, seed=seed, n_steps=n_steps, prompt=prompt,
             reference_build=r.build_info(), weights_sha1=hashlib.sha1(open(path, "rb").read()).hexdigest(),
             prompt_ids=prompt_ids, semantic=g["semantic"], coarse=g["coarse"], fine=g["fine"], audio=g["audio"],
             sem_logits_head=np.stack([l[:256] for l in sem_logits]), sem_logits_sha1=np.array([sha(l) for l in sem_logits]),
