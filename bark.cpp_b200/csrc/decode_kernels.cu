@@ -39,7 +39,7 @@ constexpr int kWarpSlotBytes = 12 * 1024;       // per-warp staging area: two ha
 constexpr int kHalfSlotBytes = kWarpSlotBytes / 2;
 
 struct SmemLayout {
-    static constexpr int wslot = 0;                                 // kWarps x 12 KB: each warp's weight rows of its next phase (cp.async)
+    static constexpr int wslot = 0;                                 // kWarps x 12 KB: each warp's weight rows of its next two phases (TMA bulk copies)
     static constexpr int act = wslot + kWarps * kWarpSlotBytes;     // two-plane LI activation operand, up to 4096 floats
     static constexpr int x = act + 4096 * 4;                        // residual stream, up to 1024 floats
     static constexpr int q = x + 1024 * 4;                          // q vector / probabilities row, up to 1024 floats

@@ -19,7 +19,7 @@ os.environ.setdefault("BARK_B200_QUIET", "1")
 import bench  # noqa: E402
 import __graft_entry__ as graft  # noqa: E402
 
-NAMES = {0: "layer start", 1: "LN1 mean", 2: "LN1 done", 3: "QKV rows ready (cp.async)", 4: "QKV rows done", 5: "QKV next rows issued", 6: "K prefetched",
+NAMES = {0: "layer start", 1: "LN1 mean", 2: "LN1 done", 3: "QKV rows ready (mbarrier)", 4: "QKV rows done", 5: "QKV next rows issued", 6: "K prefetched",
          7: "q arrived", 8: "scores done", 9: "V prefetched + v_new", 10: "scores arrived", 11: "max", 12: "exp", 13: "sum", 14: "probabilities", 15: "PV partials",
          16: "P3 done", 17: "att arrived", 18: "c_proj rows ready", 19: "c_proj rows done", 20: "c_proj next issued", 21: "x arrived", 22: "LN2 mean", 23: "LN2 done",
          24: "fc rows ready", 25: "fc rows done", 26: "fc next issued", 27: "fc block sync", 28: "ff arrived", 29: "proj rows ready", 30: "proj rows done", 31: "proj next issued"}
