@@ -136,7 +136,7 @@ extern "C" bool bark_model_quantize(const char * fname_inp, const char * fname_o
     static const char * names[3] = {"text", "coarse", "fine"};
     for (int s = 0; s < 3; s++)
         if (!quantize_gpt_section(fin, fout, (int) ftype, names[s])) { fprintf(stderr, "%s: failed to quantize %s model\n", __func__, names[s]); return false; }
-    fout << fin.rdbuf();                                                                                // codec section: not quantised, copied verbatim (bark.cpp:2366-2371)
+    if (fin.peek() != std::ifstream::traits_type::eof()) fout << fin.rdbuf();                           // codec section: not quantised, copied verbatim (bark.cpp:2366-2371)
     fout.flush();
     return (bool) fout;
 }
