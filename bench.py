@@ -58,7 +58,12 @@ def measured_traffic(kernel):
     return None
 
 
-def weights_path(config="small", ftype="f16", seed=1234):
+# tests/test_bench_contract.py sets this to "tiny" to exercise the reference arm's plumbing in seconds; every real run uses bark-small
+BENCH_CONFIG = os.environ.get("BARK_B200_BENCH_CONFIG", "small")
+
+
+def weights_path(config=None, ftype="f16", seed=1234):
+    config = config or BENCH_CONFIG
     import importlib
     graft.load_package()
     weights = importlib.import_module("bark_cpp_b200.weights")
@@ -334,7 +339,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": round(value, 5), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(total / len(times) * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16 weights/operands, f32 accumulate", "data": "synthetic (same file as the CUDA arm)",
-        "config": {"workload": f"bark-small f16, batch=1, bounded sample n_steps_text_encoder={n} ({audio_s:.2f} s clip) of BASELINE configs[1]", "parallelism": f"host CPU, {cores} threads"},
+        "config": {"workload": f"bark-{BENCH_CONFIG} f16, batch=1, bounded sample n_steps_text_encoder={n} ({audio_s:.2f} s clip) of BASELINE configs[1]", "parallelism": f"host CPU, {cores} threads"},
         "cpu_baseline": base, "e2e": {"value": round(value, 5), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     })
 
