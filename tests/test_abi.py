@@ -122,3 +122,20 @@ def test_reference_quantize_tool_builds_and_runs_against_this_library(pkg, weigh
     assert r.returncode == 0, r.stderr[-500:]
     assert pkg.lib().bark_model_quantize(inp.encode(), str(out_lib).encode(), 2)
     assert open(out_tool, "rb").read() == open(out_lib, "rb").read()
+
+
+@pytest.mark.parametrize("example", ["main", "server"])
+def test_reference_examples_build_unchanged_against_this_library(pkg, tmp_path, example):
+    """examples/main/main.cpp and examples/server/server.cpp of the reference, byte for byte, compile against include/ and link with
+    -lbark_b200 alone (no ggml, no encodec); without a model file (and, here, without a GPU) they fail the way the reference's do."""
+    ref = "/root/reference/examples"
+    if not os.path.isdir(ref):
+        pytest.skip("reference tree not present (GPU box)")
+    exe = tmp_path / example
+    libdir = os.path.dirname(pkg.LIB_PATH)
+    subprocess.check_call(["g++", "-std=c++17", "-I", os.path.join(ROOT, "include"), "-I", ref, "-I", os.path.join(ref, "server"),
+                           os.path.join(ref, example, example + ".cpp"), os.path.join(ref, "common.cpp"), "-o", str(exe),
+                           "-L", libdir, "-lbark_b200", "-Wl,-rpath," + libdir, "-pthread"])
+    if example == "main":
+        r = subprocess.run([str(exe), "-m", "/nonexistent/ggml_weights.bin", "-p", "hi"], capture_output=True, text=True, timeout=60)
+        assert r.returncode != 0 and "Could not load model" in (r.stdout + r.stderr)
