@@ -22,20 +22,35 @@ def q4_file(pkg, weights_file, config, src_ftype):
     return src, dst
 
 
+_REF_KEEPALIVE = []
+
+
+def ensure_reference_tables(orc, any_model_path):
+    """ggml_init fills the f16 tables the reference's quantizer relies on (examples/quantize/main.cpp:67-72); loading one model does
+    that.  Once per process: the reference never frees its ggml contexts and runs out of them after 64 loads."""
+    if not _REF_KEEPALIVE:
+        _REF_KEEPALIVE.append(orc.Ref(any_model_path))
+
+
+FTYPES = {"q4_0": 2, "q4_1": 3, "q8_0": 7, "q5_0": 8, "q5_1": 9}      # enum ggml_ftype (ggml.h:388-417), the five types the reference tool's README lists
+
+
+@pytest.mark.parametrize("qname", sorted(FTYPES))
 @pytest.mark.parametrize("config,src_ftype", [("tiny", "f16"), ("mini", "f32")])
-def test_quantized_file_is_byte_identical_to_the_reference_tool(pkg, orc, weights_file, tmp_path, config, src_ftype):
+def test_quantized_file_is_byte_identical_to_the_reference_tool(pkg, orc, weights_file, tmp_path, config, src_ftype, qname):
     if not orc.have_ref():
         pytest.skip("oracle/_ref/libbark_ref.so did not travel with this snapshot")
-    src, ours = q4_file(pkg, weights_file, config, src_ftype)
-    ref_out = str(tmp_path / "ref_q4_0.bin")
-    orc.Ref(src)                                             # ggml_init fills the f16 tables the tool relies on (examples/quantize/main.cpp:67-72)
+    src = weights_file(config, src_ftype)
+    ours, ref_out = str(tmp_path / "ours.bin"), str(tmp_path / "ref.bin")
+    assert pkg.lib().bark_model_quantize(src.encode(), ours.encode(), FTYPES[qname])
+    ensure_reference_tables(orc, src)
     R = C.CDLL(orc.REF_SO)
     R.bark_model_quantize.restype = C.c_bool
     R.bark_model_quantize.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
     devnull, saved = os.open(os.devnull, os.O_WRONLY), os.dup(1)
     os.dup2(devnull, 1)                                      # the reference prints one line per tensor
     try:
-        assert R.bark_model_quantize(src.encode(), ref_out.encode(), GGML_FTYPE_MOSTLY_Q4_0)
+        assert R.bark_model_quantize(src.encode(), ref_out.encode(), FTYPES[qname])
     finally:
         os.dup2(saved, 1); os.close(devnull); os.close(saved)
     a, b = open(ours, "rb").read(), open(ref_out, "rb").read()
@@ -46,7 +61,7 @@ def test_quantized_file_is_byte_identical_to_the_reference_tool(pkg, orc, weight
 def test_quantize_rejects_what_it_cannot_do(pkg, weights_file, tmp_path):
     src = weights_file("tiny", "f16")
     L = pkg.lib()
-    assert not L.bark_model_quantize(src.encode(), str(tmp_path / "x.bin").encode(), 8)           # q5_0: not implemented here
+    assert not L.bark_model_quantize(src.encode(), str(tmp_path / "x.bin").encode(), 12)          # q4_K: k-quants are not implemented here
     assert not L.bark_model_quantize(b"/nonexistent/in.bin", str(tmp_path / "y.bin").encode(), GGML_FTYPE_MOSTLY_Q4_0)
     bad = tmp_path / "bad.bin"; bad.write_bytes(b"\x00" * 64)
     assert not L.bark_model_quantize(str(bad).encode(), str(tmp_path / "z.bin").encode(), GGML_FTYPE_MOSTLY_Q4_0)
