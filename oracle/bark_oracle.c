@@ -272,7 +272,11 @@ static int rd(FILE * f, void * p, size_t n) { return fread(p, 1, n, f) == n; }
 static size_t tensor_bytes(int type, size_t nel) {
     if (type == 0) return nel * 4;
     if (type == 1) return nel * 2;
-    if (type == 2) return nel / 32 * 18;
+    if (type == 2) return nel / 32 * 18;      /* q4_0 */
+    if (type == 3) return nel / 32 * 20;      /* q4_1 */
+    if (type == 6) return nel / 32 * 22;      /* q5_0 */
+    if (type == 7) return nel / 32 * 24;      /* q5_1 */
+    if (type == 8) return nel / 32 * 34;      /* q8_0 */
     return 0;
 }
 
@@ -436,6 +440,96 @@ static float vec_dot_q4_0_q8_0(int n, const uint8_t * vx, const q8_0_t * y) {
     return s0 + s1;
 }
 
+/* q8_1 activation blocks (quantize_row_q8_1, AVX2 branch, ggml-quants.c:1305-1345): q as q8_0, plus s = f16(d * sum(q)) */
+typedef struct { uint16_t d, s; int8_t qs[32]; } q8_1_t;
+static void quantize_row_q8_1(const float * x, q8_1_t * y, int k) {
+    for (int b = 0; b < k / 32; b++) {
+        float amax = 0.0f;
+        for (int j = 0; j < 32; j++) { float a = fabsf(x[b * 32 + j]); amax = a > amax ? a : amax; }
+        const float d = amax / 127.0f;
+        const float id = (amax != 0.0f) ? 127.0f / amax : 0.0f;
+        y[b].d = orc_f32_to_f16(d);
+        int sum = 0;
+        for (int j = 0; j < 32; j++) { float v = x[b * 32 + j] * id; int q = (int) nearbyintf(v); y[b].qs[j] = (int8_t) q; sum += q; }
+        y[b].s = orc_f32_to_f16(d * (float) sum);
+    }
+}
+
+static float hsum8(const float * acc) {      /* hsum_float_8 (ggml-quants.c:48-54) */
+    float t0 = acc[4] + acc[0], t1 = acc[5] + acc[1], t2 = acc[6] + acc[2], t3 = acc[7] + acc[3];
+    float s0 = t0 + t2, s1 = t1 + t3;
+    return s0 + s1;
+}
+/* the 8 int32 lanes of mul_sum_*_pairs_float: lane l = sum of products 4l..4l+3 */
+static void lanes8(const int * qx, const int8_t * qy, float scale, float * acc) {
+    for (int l = 0; l < 8; l++) {
+        int sm = 0;
+        for (int k = 0; k < 4; k++) sm += qx[4 * l + k] * (int) qy[4 * l + k];
+        acc[l] = fmaf(scale, (float) sm, acc[l]);
+    }
+}
+static uint32_t rd_u32(const uint8_t * p) { uint32_t v; memcpy(&v, p, 4); return v; }
+static uint16_t rd_u16(const uint8_t * p) { uint16_t v; memcpy(&v, p, 2); return v; }
+
+/* ggml_vec_dot_q4_1_q8_1, AVX2 branch (ggml-quants.c:4635-4667); `summs += m*s` is a fused multiply-add in the pinned build */
+static float vec_dot_q4_1_q8_1(int n, const uint8_t * vx, const q8_1_t * y) {
+    float acc[8] = {0}, summs = 0.0f;
+    for (int b = 0; b < n / 32; b++) {
+        const uint8_t * blk = vx + (size_t) b * 20;
+        const float d0 = f16_lut[rd_u16(blk)], d1 = f16_lut[y[b].d];
+        summs = fmaf(f16_lut[rd_u16(blk + 2)], f16_lut[y[b].s], summs);
+        int q[32];
+        for (int j = 0; j < 16; j++) { q[j] = blk[4 + j] & 0x0f; q[j + 16] = blk[4 + j] >> 4; }
+        lanes8(q, y[b].qs, d0 * d1, acc);
+    }
+    return hsum8(acc) + summs;
+}
+/* ggml_vec_dot_q5_0_q8_0, AVX2 branch (ggml-quants.c:4935-4957): code = (nibble | fifth bit << 4) - 16 */
+static float vec_dot_q5_0_q8_0(int n, const uint8_t * vx, const q8_0_t * y) {
+    float acc[8] = {0};
+    for (int b = 0; b < n / 32; b++) {
+        const uint8_t * blk = vx + (size_t) b * 22;
+        const float d = f16_lut[rd_u16(blk)] * f16_lut[y[b].d];
+        const uint32_t qh = rd_u32(blk + 2);
+        int q[32];
+        for (int j = 0; j < 16; j++) {
+            q[j]      = ((blk[6 + j] & 0x0f) | (((qh >> j) & 1) << 4)) - 16;
+            q[j + 16] = ((blk[6 + j] >> 4)   | (((qh >> (j + 16)) & 1) << 4)) - 16;
+        }
+        lanes8(q, y[b].qs, d, acc);
+    }
+    return hsum8(acc);
+}
+/* ggml_vec_dot_q5_1_q8_1, AVX2 branch (ggml-quants.c:5300-5325) */
+static float vec_dot_q5_1_q8_1(int n, const uint8_t * vx, const q8_1_t * y) {
+    float acc[8] = {0}, summs = 0.0f;
+    for (int b = 0; b < n / 32; b++) {
+        const uint8_t * blk = vx + (size_t) b * 24;
+        const float dx = f16_lut[rd_u16(blk)], dy = f16_lut[y[b].d];
+        summs = fmaf(f16_lut[rd_u16(blk + 2)], f16_lut[y[b].s], summs);
+        const uint32_t qh = rd_u32(blk + 4);
+        int q[32];
+        for (int j = 0; j < 16; j++) {
+            q[j]      = (blk[8 + j] & 0x0f) | (((qh >> j) & 1) << 4);
+            q[j + 16] = (blk[8 + j] >> 4)   | (((qh >> (j + 16)) & 1) << 4);
+        }
+        lanes8(q, y[b].qs, dx * dy, acc);
+    }
+    return hsum8(acc) + summs;
+}
+/* ggml_vec_dot_q8_0_q8_0, AVX2 branch (ggml-quants.c:5747-5768) */
+static float vec_dot_q8_0_q8_0(int n, const uint8_t * vx, const q8_0_t * y) {
+    float acc[8] = {0};
+    for (int b = 0; b < n / 32; b++) {
+        const uint8_t * blk = vx + (size_t) b * 34;
+        const float d = f16_lut[rd_u16(blk)] * f16_lut[y[b].d];
+        int q[32];
+        for (int j = 0; j < 32; j++) q[j] = (int8_t) blk[2 + j];
+        lanes8(q, y[b].qs, d, acc);
+    }
+    return hsum8(acc);
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* mul_mat: dst[r][o] = vec_dot(W[o][:], act[r][:]) (ggml.c:12369-12457, 12530-12558)          */
 /* ------------------------------------------------------------------------------------------ */
@@ -455,13 +549,31 @@ static void mul_mat(const tensor_t * W, const float * act, int rows, float * dst
         for (int r = 0; r < rows; r++)
             for (int o = 0; o < O; o++) dst[(size_t) r * O + o] = orc_vec_dot_f16(K, w + (size_t) o * K, a16 + (size_t) r * K);
         free(a16);
-    } else {
-        q8_0_t * a8 = malloc((size_t) rows * (K / 32) * sizeof(q8_0_t));
-        for (int r = 0; r < rows; r++) quantize_row_q8_0(act + (size_t) r * K, a8 + (size_t) r * (K / 32), K);
+    } else if (W->type == 2 || W->type == 6 || W->type == 8) {          /* vec_dot_type q8_0 (ggml.c type_traits) */
+        const int nbk = K / 32, bb = W->type == 2 ? 18 : W->type == 6 ? 22 : 34;
+        q8_0_t * a8 = malloc((size_t) rows * nbk * sizeof(q8_0_t));
+        for (int r = 0; r < rows; r++) quantize_row_q8_0(act + (size_t) r * K, a8 + (size_t) r * nbk, K);
         const uint8_t * w = W->data;
+        const int wt = W->type;
         #pragma omp parallel for schedule(static) collapse(2)
         for (int r = 0; r < rows; r++)
-            for (int o = 0; o < O; o++) dst[(size_t) r * O + o] = vec_dot_q4_0_q8_0(K, w + (size_t) o * (K / 32) * 18, a8 + (size_t) r * (K / 32));
+            for (int o = 0; o < O; o++) {
+                const uint8_t * wr = w + (size_t) o * nbk * bb; const q8_0_t * ar = a8 + (size_t) r * nbk;
+                dst[(size_t) r * O + o] = wt == 2 ? vec_dot_q4_0_q8_0(K, wr, ar) : wt == 6 ? vec_dot_q5_0_q8_0(K, wr, ar) : vec_dot_q8_0_q8_0(K, wr, ar);
+            }
+        free(a8);
+    } else {                                                               /* q4_1, q5_1: vec_dot_type q8_1 */
+        const int nbk = K / 32, bb = W->type == 3 ? 20 : 24;
+        q8_1_t * a8 = malloc((size_t) rows * nbk * sizeof(q8_1_t));
+        for (int r = 0; r < rows; r++) quantize_row_q8_1(act + (size_t) r * K, a8 + (size_t) r * nbk, K);
+        const uint8_t * w = W->data;
+        const int wt = W->type;
+        #pragma omp parallel for schedule(static) collapse(2)
+        for (int r = 0; r < rows; r++)
+            for (int o = 0; o < O; o++) {
+                const uint8_t * wr = w + (size_t) o * nbk * bb; const q8_1_t * ar = a8 + (size_t) r * nbk;
+                dst[(size_t) r * O + o] = wt == 3 ? vec_dot_q4_1_q8_1(K, wr, ar) : vec_dot_q5_1_q8_1(K, wr, ar);
+            }
         free(a8);
     }
 }
@@ -471,6 +583,24 @@ static void get_row(const tensor_t * T, int row, float * out) {
     const int K = T->ne[0];
     if (T->type == 0) memcpy(out, (const float *) T->data + (size_t) row * K, (size_t) K * 4);
     else if (T->type == 1) { const uint16_t * p = (const uint16_t *) T->data + (size_t) row * K; for (int i = 0; i < K; i++) out[i] = f16_lut[p[i]]; }
+    else if (T->type != 2) {   /* dequantize_row_q4_1 / q5_0 / q5_1 / q8_0 (ggml-quants.c:1542-1630); x*d + m is one fused multiply-add in the pinned build */
+        const int bb = T->type == 3 ? 20 : T->type == 6 ? 22 : T->type == 7 ? 24 : 34;
+        const uint8_t * p = (const uint8_t *) T->data + (size_t) row * (K / 32) * bb;
+        for (int b = 0; b < K / 32; b++) {
+            const uint8_t * blk = p + (size_t) b * bb;
+            const float d = f16_lut[rd_u16(blk)];
+            float * o = out + b * 32;
+            if (T->type == 8) { for (int j = 0; j < 32; j++) o[j] = (float)(int8_t) blk[2 + j] * d; continue; }
+            const float m = (T->type == 3 || T->type == 7) ? f16_lut[rd_u16(blk + 2)] : 0.0f;
+            const uint8_t * qs = blk + (T->type == 3 ? 4 : T->type == 6 ? 6 : 8);
+            const uint32_t qh = T->type == 3 ? 0u : rd_u32(blk + (T->type == 6 ? 2 : 4));
+            for (int j = 0; j < 16; j++) {
+                int x0 = (qs[j] & 0x0f) | (int)(((qh >> j) & 1) << 4), x1 = (qs[j] >> 4) | (int)(((qh >> (j + 16)) & 1) << 4);
+                if (T->type == 6) { o[j] = (float)(x0 - 16) * d; o[j + 16] = (float)(x1 - 16) * d; }
+                else              { o[j] = fmaf((float) x0, d, m); o[j + 16] = fmaf((float) x1, d, m); }
+            }
+        }
+    }
     else {   /* dequantize_row_q4_0 (ggml-quants.c:1515): (nibble-8)*d */
         const uint8_t * p = (const uint8_t *) T->data + (size_t) row * (K / 32) * 18;
         for (int b = 0; b < K / 32; b++) {

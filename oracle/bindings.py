@@ -142,6 +142,13 @@ class Ref:
             raise RuntimeError(f"reference failed to load {path}")
         L.ref_set_params(self.ctx, temp, fine_temp, min_eos_p)
 
+    def close(self):
+        """bark_free: the reference has a fixed pool of ggml contexts (64), so long test sessions must give them back"""
+        if getattr(self, "ctx", None):
+            self.L.ref_free.argtypes = [vp]
+            self.L.ref_free(self.ctx)
+            self.ctx = None
+
     def build_info(self): return self.L.ref_build_info().decode()
 
     def hparams(self, which):

@@ -67,32 +67,39 @@ def test_quantize_rejects_what_it_cannot_do(pkg, weights_file, tmp_path):
     assert not L.bark_model_quantize(str(bad).encode(), str(tmp_path / "z.bin").encode(), GGML_FTYPE_MOSTLY_Q4_0)
 
 
+@pytest.mark.parametrize("qname", sorted(FTYPES))
 @pytest.mark.parametrize("config,src_ftype", [("tiny", "f16"), ("mini", "f32")])
-def test_q4_oracle_matches_the_reference(pkg, orc, weights_file, config, src_ftype):
-    """Pins the oracle's q4_0 path: teacher-forced logits (merged prompt, decode, ragged coarse prefill), a fine pass and a
-    whole generation, oracle vs the unmodified reference on the same q4_0 file."""
+def test_quantised_oracle_matches_the_reference(pkg, orc, weights_file, tmp_path, config, src_ftype, qname):
+    """Pins the oracle's quantised paths (q8_0 / q8_1 activation blocks, the 8-lane integer dots, hsum_float_8, get_rows
+    dequantisation): teacher-forced logits (merged prompt, decode, ragged coarse prefill), a fine pass and a whole generation,
+    oracle vs the unmodified reference on the same quantised file."""
     if not orc.have_ref():
         pytest.skip("oracle/_ref/libbark_ref.so did not travel with this snapshot")
-    _, path = q4_file(pkg, weights_file, config, src_ftype)
+    src = weights_file(config, src_ftype)
+    path = str(tmp_path / f"{qname}.bin")
+    assert pkg.lib().bark_model_quantize(src.encode(), path.encode(), FTYPES[qname])
     o, r = orc.Oracle(path, seed=0, n_steps=10), orc.Ref(path, seed=0, n_steps=10)
-    assert int(o.hparams(0)[9]) % 1000 == 2
-    rng = np.random.default_rng(17)
-    toks, po, pr = o.tokenize("Hello, world"), 0, 0
-    for step in range(4):
-        lo, po = o.gpt_eval(0, toks, po, True)
-        lr, pr = r.gpt_eval(0, toks, pr, True)
-        assert np.array_equal(bits(lo), bits(lr)), f"semantic step {step}: {int((lo != lr).sum())} logits differ, max {np.abs(lo - lr).max():.3e}"
-        toks = np.array([int(np.argmax(lr[:10000]))], np.int32)
-    toks = np.concatenate([rng.integers(0, 10000, 256), [12050], rng.integers(10000, 12048, 21)]).astype(np.int32)
-    po = pr = 0
-    for step in range(3):
-        lo, po = o.gpt_eval(1, toks, po, False)
-        lr, pr = r.gpt_eval(1, toks, pr, False)
-        assert np.array_equal(bits(lo), bits(lr)), f"coarse step {step}: {int((lo != lr).sum())} logits differ"
-        toks = np.array([10000 + int(np.argmax(lr[10000:12048]))], np.int32)
-    buf = rng.integers(0, 1024, (8, 1024)).astype(np.int32); buf[:, 300:] = 1024; buf[4:, :] = 1024
-    assert np.array_equal(bits(o.fine_eval(buf, 4)), bits(r.fine_eval(buf, 4)))
-    go, gr = o.generate("hello world"), r.generate("hello world")
-    for k in ("semantic", "coarse", "fine"):
-        assert np.array_equal(go[k], gr[k]), k
-    assert np.array_equal(bits(go["audio"]), bits(gr["audio"]))
+    try:
+        assert int(o.hparams(0)[9]) % 1000 == FTYPES[qname]
+        rng = np.random.default_rng(17)
+        toks, po, pr = o.tokenize("Hello, world"), 0, 0
+        for step in range(4):
+            lo, po = o.gpt_eval(0, toks, po, True)
+            lr, pr = r.gpt_eval(0, toks, pr, True)
+            assert np.array_equal(bits(lo), bits(lr)), f"semantic step {step}: {int((lo != lr).sum())} logits differ, max {np.abs(lo - lr).max():.3e}"
+            toks = np.array([int(np.argmax(lr[:10000]))], np.int32)
+        toks = np.concatenate([rng.integers(0, 10000, 256), [12050], rng.integers(10000, 12048, 21)]).astype(np.int32)
+        po = pr = 0
+        for step in range(3):
+            lo, po = o.gpt_eval(1, toks, po, False)
+            lr, pr = r.gpt_eval(1, toks, pr, False)
+            assert np.array_equal(bits(lo), bits(lr)), f"coarse step {step}: {int((lo != lr).sum())} logits differ"
+            toks = np.array([10000 + int(np.argmax(lr[10000:12048]))], np.int32)
+        buf = rng.integers(0, 1024, (8, 1024)).astype(np.int32); buf[:, 300:] = 1024; buf[4:, :] = 1024
+        assert np.array_equal(bits(o.fine_eval(buf, 4)), bits(r.fine_eval(buf, 4)))
+        go, gr = o.generate("hello world"), r.generate("hello world")
+        for k in ("semantic", "coarse", "fine"):
+            assert np.array_equal(go[k], gr[k]), k
+        assert np.array_equal(bits(go["audio"]), bits(gr["audio"]))
+    finally:
+        r.close()
