@@ -280,3 +280,32 @@ def test_bark_large_widths(pkg, orc, weights_file):
             toks = np.array([10000 + int(np.argmax(lo[10000:12048]))], np.int32)
         buf = rng.integers(0, 1024, (8, 1024)).astype(np.int32); buf[:, 600:] = 1024; buf[3:, :] = 1024
         assert np.array_equal(bits(b.fine_eval(buf, 3)), bits(o.fine_eval(buf, 3)))      # one 1024-row pass (a whole generation costs the CPU oracle a minute)
+
+
+@pytest.mark.skipif(__import__("os").environ.get("BARK_B200_TEST_EXPERIMENTAL") != "1", reason="opt-in: BARK_B200_TEST_EXPERIMENTAL=1 (code paths not yet validated on a B200)")
+@pytest.mark.parametrize("config,ftype", [("tiny", "f16"), ("mini", "f32"), ("mini", "f16")])
+def test_packed_fma_variants_are_bit_identical(pkg, orc, weights_file, monkeypatch, config, ftype):
+    """BARK_B200_FFMA2=1: the tiled mat-mul / scores / P.V kernels with the 64 FMAs of a chain step issued as 32 packed FFMA2
+    (fma.rn.f32x2).  Per component the arithmetic is __fmaf_rn's, so prefill logits, fine passes and a whole generation must not
+    move by a bit — against the default kernels and against the oracle."""
+    path = weights_file(config, ftype)
+    o = orc.Oracle(path, seed=0, n_steps=24)
+    rng = np.random.default_rng(29)
+    toks = np.concatenate([rng.integers(0, 10000, 256), [12050], rng.integers(10000, 12048, 53)]).astype(np.int32)
+    buf = rng.integers(0, 1024, (8, 1024)).astype(np.int32); buf[:, 640:] = 1024; buf[5:, :] = 1024
+    res = {}
+    for f2 in ("0", "1"):
+        monkeypatch.setenv("BARK_B200_FFMA2", f2)
+        with pkg.Bark(path, seed=0, n_steps_text_encoder=24) as b:
+            lg, _ = b.gpt_eval(1, toks, 0, False)
+            sem, _ = b.gpt_eval(0, o.tokenize("packed"), 0, True)
+            fl = b.fine_eval(buf, 5)
+            audio = b.generate("hello world")
+            res[f2] = (lg, sem, fl, audio, [b.tokens(i).copy() for i in range(3)])
+    for a, c in zip(res["0"][:4], res["1"][:4]):
+        assert np.array_equal(bits(a), bits(c))
+    for a, c in zip(res["0"][4], res["1"][4]):
+        assert np.array_equal(a, c)
+    lo, _ = o.gpt_eval(1, toks, 0, False)
+    assert np.array_equal(bits(res["1"][0]), bits(lo))
+    assert np.array_equal(bits(res["1"][2]), bits(o.fine_eval(buf, 5)))
