@@ -912,10 +912,26 @@ static void elu_inplace(float * x, size_t n) { for (size_t i = 0; i < n; i++) x[
 
 /* strided_conv_1d, stride 1 (ops.cpp:59-75): reflect-pad left by k-1, im2col to f16 (ggml.c:14954),
  * f16 x f16 vec_dot over [Cin][k], bias added in f32 */
+/* ggml_conv_1d core (ggml.c:6641-6660 = im2col to f16 + mul_mat): xp is the already padded f16 input [Cin][Tp], T = Tp - k + 1 outputs */
+static void conv1d_core(const uint16_t * xp, int Cin, int Tp, int k, const uint16_t * w, int Cout, const float * bias, float * y) {
+    const int T = Tp - k + 1;
+    #pragma omp parallel
+    {
+        uint16_t * col = malloc((size_t) Cin * k * 2);
+        #pragma omp for schedule(static)
+        for (int t = 0; t < T; t++) {
+            for (int c = 0; c < Cin; c++) for (int j = 0; j < k; j++) col[c * k + j] = xp[(size_t) c * Tp + t + j];
+            for (int o = 0; o < Cout; o++) {
+                float v = orc_vec_dot_f16(Cin * k, col, w + (size_t) o * Cin * k);
+                y[(size_t) o * T + t] = bias ? bias[o] + v : v;                  /* ops.cpp:72 add(repeat(b), dst) */
+            }
+        }
+        free(col);
+    }
+}
 static float * conv1d(const float * x, int Cin, int T, const conv_t * cv) {
     const int k = cv->w.ne[0], Cout = cv->w.ne[2], pad = k - 1;
     assert(cv->w.ne[1] == Cin && T > pad);
-    const uint16_t * w = cv->w.data; const float * bias = cv->b.data;
     uint16_t * xp = malloc((size_t) Cin * (T + pad) * 2);           /* padded, f16 */
     for (int c = 0; c < Cin; c++) {
         uint16_t * row = xp + (size_t) c * (T + pad);
@@ -923,28 +939,14 @@ static float * conv1d(const float * x, int Cin, int T, const conv_t * cv) {
         for (int i = 1; i <= pad; i++) row[pad - i] = row[pad + i];            /* ggml.c:15589 */
     }
     float * y = malloc((size_t) Cout * T * 4);
-    #pragma omp parallel
-    {
-        uint16_t * col = malloc((size_t) Cin * k * 2);
-        #pragma omp for schedule(static)
-        for (int t = 0; t < T; t++) {
-            for (int c = 0; c < Cin; c++) for (int j = 0; j < k; j++) col[c * k + j] = xp[(size_t) c * (T + pad) + t + j];
-            for (int o = 0; o < Cout; o++) {
-                float v = orc_vec_dot_f16(Cin * k, col, w + (size_t) o * Cin * k);
-                y[(size_t) o * T + t] = bias[o] + v;                           /* ops.cpp:72 add(repeat(b), dst) */
-            }
-        }
-        free(col);
-    }
+    conv1d_core(xp, Cin, T + pad, k, cv->w.data, Cout, cv->b.data, y);
     free(xp);
     return y;
 }
 
 /* strided_conv_transpose_1d (ops.cpp:77-98, ggml.c:14614-14700): kernel [k][Cout][Cin] f16 */
-static float * convtr1d(const float * x, int Cin, int T, const conv_t * cv, int stride, int * T_out) {
-    const int k = cv->w.ne[0], Cout = cv->w.ne[1];
-    assert(cv->w.ne[2] == Cin);
-    const uint16_t * w = cv->w.data; const float * bias = cv->b.data;
+/* ggml_conv_transpose_1d core (ggml.c:14614-14700): full-length output [(T-1)*stride + k] per channel, kernel [Cin][Cout][k] f16 */
+static float * convtr1d_full(const float * x, int Cin, int T, const uint16_t * w, int k, int Cout, int stride) {
     const int Lfull = (T - 1) * stride + k;
     uint16_t * xs = malloc((size_t) T * Cin * 2);                   /* [T][Cin] f16 */
     for (int c = 0; c < Cin; c++) for (int t = 0; t < T; t++) xs[(size_t) t * Cin + c] = orc_f32_to_f16(x[(size_t) c * T + t]);
@@ -962,12 +964,40 @@ static float * convtr1d(const float * x, int Cin, int T, const conv_t * cv, int 
         }
         free(wk);
     }
+    free(xs);
+    return full;
+}
+static float * convtr1d(const float * x, int Cin, int T, const conv_t * cv, int stride, int * T_out) {
+    const int k = cv->w.ne[0], Cout = cv->w.ne[1];
+    assert(cv->w.ne[2] == Cin);
+    const float * bias = cv->b.data;
+    const int Lfull = (T - 1) * stride + k;
+    float * full = convtr1d_full(x, Cin, T, cv->w.data, k, Cout, stride);
     const int L = Lfull - (k - stride);                             /* unpad right (ops.cpp:89-95) */
     float * y = malloc((size_t) Cout * L * 4);
     for (int o = 0; o < Cout; o++) for (int t = 0; t < L; t++) y[(size_t) o * L + t] = bias[o] + full[(size_t) o * Lfull + t];
-    free(full); free(xs);
+    free(full);
     *T_out = L;
     return y;
+}
+
+/* Test hooks for the known-answer vectors of the reference's own op tests (ggml/tests/test-conv1d.cpp:233-281,
+ * test-conv-transpose-1d.cpp:415-560).  Kernels arrive as f32 and are rounded to f16 like the codec's weights; the vectors are
+ * small integers / halves, exact in f16.  conv1d: ggml_conv_1d(a, b, s0 = 1, p0, d0 = 1), zero padding p0 on both sides. */
+void orc_test_conv1d(const float * w, int k, int Cin, int Cout, const float * x, int T, int p0, float * y /*[Cout][T + 2 p0 - k + 1]*/) {
+    const int Tp = T + 2 * p0;
+    uint16_t * w16 = malloc((size_t) k * Cin * Cout * 2), * xp = calloc((size_t) Cin * Tp, 2);
+    for (int i = 0; i < k * Cin * Cout; i++) w16[i] = orc_f32_to_f16(w[i]);
+    for (int c = 0; c < Cin; c++) for (int t = 0; t < T; t++) xp[(size_t) c * Tp + p0 + t] = orc_f32_to_f16(x[(size_t) c * T + t]);
+    conv1d_core(xp, Cin, Tp, k, w16, Cout, NULL, y);
+    free(w16); free(xp);
+}
+void orc_test_convtr1d(const float * w /*[Cin][Cout][k]*/, int k, int Cout, int Cin, const float * x /*[Cin][T]*/, int T, int stride, float * y /*[Cout][(T-1)*stride + k]*/) {
+    uint16_t * w16 = malloc((size_t) k * Cin * Cout * 2);
+    for (int i = 0; i < k * Cin * Cout; i++) w16[i] = orc_f32_to_f16(w[i]);
+    float * full = convtr1d_full(x, Cin, T, w16, k, Cout, stride);
+    memcpy(y, full, (size_t) Cout * ((T - 1) * stride + k) * 4);
+    free(full); free(w16);
 }
 
 /* forward_pass_lstm_unilayer (lstm.h:22-78).  x: [C][T] -> returns [H][T] */

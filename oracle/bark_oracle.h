@@ -62,6 +62,9 @@ void     orc_soft_max(int n, const float * x, float * y);   /* row soft_max as g
 float    orc_v_expf(float x);
 void     orc_mt_seed(uint32_t * state625, uint32_t seed);
 uint32_t orc_mt_next(uint32_t * state625);
+/* known-answer hooks: the reference's own op tests (ggml/tests/test-conv1d.cpp, test-conv-transpose-1d.cpp) through the codec's conv cores */
+void     orc_test_conv1d(const float * w, int k, int Cin, int Cout, const float * x, int T, int p0, float * y);
+void     orc_test_convtr1d(const float * w, int k, int Cout, int Cin, const float * x, int T, int stride, float * y);
 
 #ifdef __cplusplus
 }
