@@ -199,7 +199,7 @@ bool run_chain(bark_context * ctx, GPTModel & m, const std::vector<int32_t> & fi
         for (int j = 0; j < n; j++) ctx->h_u[j] = std::generate_canonical<double, 53>(ctx->rng);     // one draw per sample, as discrete_distribution::operator() makes
         BARK_CUDA_CHECK(cudaMemcpyAsync(ctx->d_u, ctx->h_u, (size_t) n * sizeof(double), cudaMemcpyHostToDevice, s)); bark::g_h2d_bytes += (size_t) n * sizeof(double);
     }
-    const bool chain = ctx->use_decode_kernel && m.wtype != W_Q4_0;
+    const bool chain = ctx->use_decode_kernel && !is_quant(m.wtype);
     std::vector<int> past_before((size_t) n);
     std::vector<int32_t> cur_in = first_in;
     std::vector<float> host_logits;
@@ -424,8 +424,9 @@ void alloc_workspace(bark_context * ctx) {
     ws.scores = (float *) ctx_alloc(ctx, (size_t) H * R * R * 4);
     ws.logits = (float *) ctx_alloc(ctx, n_logits * 4);
     ws.tok  = (int32_t *) ctx_alloc(ctx, 8 * 1024 * 4);
-    if (ctx->semantic.wtype == W_Q4_0 || ctx->coarse.wtype == W_Q4_0 || ctx->fine.wtype == W_Q4_0) {
+    if (is_quant(ctx->semantic.wtype) || is_quant(ctx->coarse.wtype) || is_quant(ctx->fine.wtype)) {
         ctx->d_q8 = ctx_alloc(ctx, R * (size_t) 4 * E); ctx->d_q8_scales = ctx_alloc(ctx, R * (size_t)(4 * E / 32) * 4);
+        ctx->d_q8_sums = ctx_alloc(ctx, R * (size_t)(4 * E / 32) * 4);
     }
     BARK_CUDA_CHECK(cudaMallocHost(&ctx->h_logits, n_logits * 4));
     BARK_CUDA_CHECK(cudaMallocHost(&ctx->h_tok, 8 * 1024 * 4));

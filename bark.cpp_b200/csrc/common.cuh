@@ -46,7 +46,8 @@ extern double g_next_bytes, g_next_flops;
     } while (0)
 
 // weight element types as stored in ggml_weights.bin (ggml_type values)
-enum WType : int { W_F32 = 0, W_F16 = 1, W_Q4_0 = 2 };
+enum WType : int { W_F32 = 0, W_F16 = 1, W_Q4_0 = 2, W_Q4_1 = 3, W_Q5_0 = 6, W_Q5_1 = 7, W_Q8_0 = 8 };   // 3..8: experimental (qx_kernels.cu)
+inline bool is_quant(WType t) { return t != W_F32 && t != W_F16; }
 
 // ---------------------------------------------------------------------------------------------
 // Lane-interleaved ("LI") matrix layout.

@@ -28,6 +28,7 @@ struct bark_context {
     unsigned long long * d_timing = nullptr;         // optional phase timestamps of the decode kernel (BARK_B200_DECODE_TIMING=1)
 
     bark::Workspace ws;
+    void * d_q8_sums = nullptr;                       // experimental q4_1 / q5_1: q8_1 block sums s = f16(d * sum(q))
     void * d_q8 = nullptr, * d_q8_scales = nullptr;  // q4_0 models: q8_0 activation operand (int8 [rows][4E], f32 scales [rows][4E/32])
     const float * last_logits = nullptr;             // device logits of the latest gpt_eval / fine_eval
     double * d_u = nullptr, * h_u = nullptr;         // device sampling: uniforms, tokens, flags, eos probabilities (1024 rows)

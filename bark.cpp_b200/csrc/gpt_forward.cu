@@ -25,12 +25,13 @@ static void run_layers(bark_context * ctx, GPTModel & m, int N, int n_past, bool
     Workspace & ws = ctx->ws;
     cudaStream_t s = ctx->stream;
     const int E = m.n_embd, H = m.n_head;
-    const bool q4 = m.wtype == W_Q4_0;
+    const bool q4 = is_quant(m.wtype);                       // quantised weights: f32 activation rows, quantised to q8 blocks in front of each mat-mul
+    const WType awt = q4 ? W_Q4_0 : m.wtype;                 // what the activation producers are told (store_act)
     const int kpE = q4 ? E : ws.max_rows * kGmGroup, kp4E = q4 ? 4 * E : kpE;      // group stride of the group-major activation operands; q4_0: f32 row stride
-    if (q4) q4_set_scratch(ctx->d_q8, ctx->d_q8_scales);
+    if (q4) { q4_set_scratch(ctx->d_q8, ctx->d_q8_scales); qx_set_scratch(ctx->d_q8, ctx->d_q8_scales, ctx->d_q8_sums); }
     for (int il = 0; il < m.n_layer; il++) {
         const GPTLayer & L = m.layers[(size_t) il];
-        layernorm_act(ws.x, N, E, L.ln_1_g, L.ln_1_b, ws.act, m.wtype, kpE, ctx->d_ln_fallbacks, s);
+        layernorm_act(ws.x, N, E, L.ln_1_g, L.ln_1_b, ws.act, awt, kpE, ctx->d_ln_fallbacks, s);
         float * k_all, * v_all, * k_dst, * v_dst; int n_kv;
         if (causal) {
             k_all = m.mem_k + (size_t) il * m.block_size * E; v_all = m.mem_v + (size_t) il * m.block_size * E;
@@ -40,11 +41,11 @@ static void run_layers(bark_context * ctx, GPTModel & m, int N, int n_past, bool
         }
         MatmulEpilogue qkv; qkv.mode = EPI_QKV; qkv.out = ws.q; qkv.ldo = E; qkv.k_out = k_dst; qkv.v_out = v_dst;
         lane_matmul(L.c_attn, ws.act, kpE, N, qkv, s);
-        attention(ws.q, k_all, v_all, N, n_kv, n_past, E, H, causal, ws.scores, ws.act, m.wtype, kpE, s);
+        attention(ws.q, k_all, v_all, N, n_kv, n_past, E, H, causal, ws.scores, ws.act, awt, kpE, s);
         MatmulEpilogue res; res.mode = EPI_RESID; res.out = ws.x; res.ldo = E;
         lane_matmul(L.c_proj, ws.act, kpE, N, res, s);                                                              // + inpL
-        layernorm_act(ws.x, N, E, L.ln_2_g, L.ln_2_b, ws.act, m.wtype, kpE, ctx->d_ln_fallbacks, s);
-        MatmulEpilogue ge; ge.mode = EPI_GELU_ACT; ge.act_out = ws.act2; ge.act_wt = (int) m.wtype; ge.act_Kp = kp4E; ge.gelu_tab = ctx->d_gelu_tab;
+        layernorm_act(ws.x, N, E, L.ln_2_g, L.ln_2_b, ws.act, awt, kpE, ctx->d_ln_fallbacks, s);
+        MatmulEpilogue ge; ge.mode = EPI_GELU_ACT; ge.act_out = ws.act2; ge.act_wt = (int) awt; ge.act_Kp = kp4E; ge.gelu_tab = ctx->d_gelu_tab;
         lane_matmul(L.fc, ws.act, kpE, N, ge, s);
         lane_matmul(L.proj, ws.act2, kp4E, N, res, s);                                                                // + inpFF
     }
@@ -103,7 +104,7 @@ bool gpt_eval(bark_context * ctx, GPTModel & m, const int32_t * tokens, int n, i
     bool merge = false;
     if (lm_hi <= 0 || lm_hi > m.n_out_vocab || lm_lo < 0 || lm_lo >= lm_hi) { lm_lo = 0; lm_hi = m.n_out_vocab; }
     if (*n_past > 0 && N == 1) {
-        if (ctx->use_decode_kernel && m.wtype != W_Q4_0 && *n_past + 1 <= m.block_size && tokens[0] >= 0 && tokens[0] < m.n_in_vocab) {
+        if (ctx->use_decode_kernel && !is_quant(m.wtype) && *n_past + 1 <= m.block_size && tokens[0] >= 0 && tokens[0] < m.n_in_vocab) {
             decode_step(ctx, m, tokens[0], nullptr, *n_past, lm_lo, lm_hi);
             ctx->last_logits = m.glogits;
             if (logits_host) {
@@ -126,8 +127,8 @@ bool gpt_eval(bark_context * ctx, GPTModel & m, const int32_t * tokens, int n, i
     gpt_embed_causal(m, ws.tok, N, *n_past, merge, ws.x, s);
     run_layers(ctx, m, N, *n_past, true);
     // final norm + lm_head on the last position only (bark.cpp:1391-1405)
-    const int kpE = m.wtype == W_Q4_0 ? E : ws.max_rows * kGmGroup;
-    layernorm_act(ws.x + (size_t)(N - 1) * E, 1, E, m.ln_f_g, m.ln_f_b, ws.act, m.wtype, kpE, ctx->d_ln_fallbacks, s);
+    const int kpE = is_quant(m.wtype) ? E : ws.max_rows * kGmGroup;
+    layernorm_act(ws.x + (size_t)(N - 1) * E, 1, E, m.ln_f_g, m.ln_f_b, ws.act, is_quant(m.wtype) ? W_Q4_0 : m.wtype, kpE, ctx->d_ln_fallbacks, s);
     MatmulEpilogue st; st.mode = EPI_STORE; st.out = ws.logits; st.ldo = m.n_out_vocab;
     lane_matmul(m.lm_head[0], ws.act, kpE, 1, st, s);
     ctx->last_logits = ws.logits;
@@ -144,7 +145,7 @@ bool gpt_eval(bark_context * ctx, GPTModel & m, const int32_t * tokens, int n, i
 // One decode step whose input token is read from device memory (the previous step's sample): nothing to wait for on the
 // host, so a whole window of steps is enqueued back to back.
 bool gpt_decode_chained(bark_context * ctx, GPTModel & m, const int32_t * d_token, int * n_past, int lm_lo, int lm_hi) {
-    if (!ctx->use_decode_kernel || m.wtype == W_Q4_0 || *n_past < 1) { fprintf(stderr, "%s: needs the persistent decode kernel and a filled KV cache\n", __func__); return false; }
+    if (!ctx->use_decode_kernel || is_quant(m.wtype) || *n_past < 1) { fprintf(stderr, "%s: needs the persistent decode kernel and a filled KV cache\n", __func__); return false; }
     if (*n_past + 1 > m.block_size) { fprintf(stderr, "%s: context overflow (n_past %d + 1 > %d)\n", __func__, *n_past, m.block_size); return false; }
     if (lm_hi <= 0 || lm_hi > m.n_out_vocab || lm_lo < 0 || lm_lo >= lm_hi) { lm_lo = 0; lm_hi = m.n_out_vocab; }
     decode_step(ctx, m, 0, d_token, *n_past, lm_lo, lm_hi);
@@ -164,8 +165,8 @@ bool fine_eval(bark_context * ctx, const int32_t * in_buffer, int nn, float * lo
     BARK_CUDA_CHECK(cudaMemcpyAsync(ws.tok, ctx->h_tok, (size_t) 8 * 1024 * sizeof(int32_t), cudaMemcpyHostToDevice, s)); g_h2d_bytes += (size_t) 8 * 1024 * sizeof(int32_t);
     gpt_embed_fine(m, ws.tok, nn, ws.x, s);
     run_layers(ctx, m, N, 0, false);
-    const int kpE = m.wtype == W_Q4_0 ? E : ws.max_rows * kGmGroup;
-    layernorm_act(ws.x, N, E, m.ln_f_g, m.ln_f_b, ws.act, m.wtype, kpE, ctx->d_ln_fallbacks, s);
+    const int kpE = is_quant(m.wtype) ? E : ws.max_rows * kGmGroup;
+    layernorm_act(ws.x, N, E, m.ln_f_g, m.ln_f_b, ws.act, is_quant(m.wtype) ? W_Q4_0 : m.wtype, kpE, ctx->d_ln_fallbacks, s);
     MatmulEpilogue st; st.mode = EPI_STORE; st.out = ws.logits; st.ldo = m.n_out_vocab;
     lane_matmul(m.lm_head[nn - 1], ws.act, kpE, N, st, s);                                                           // n_codes_given = 1 (bark.cpp:61,1573)
     ctx->last_logits = ws.logits;

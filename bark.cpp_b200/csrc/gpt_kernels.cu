@@ -95,9 +95,11 @@ __global__ void embed_fine_kernel(FineTables tabs, int wt, const float * __restr
 }
 
 void gpt_embed_causal(const GPTModel & m, const int32_t * d_tok, int N, int n_past, bool merge, float * x, cudaStream_t s) {
+    if (qx_supported(m.wtype)) { qx_embed_causal(m, d_tok, N, n_past, merge, x, s); return; }
     BARK_LAUNCH(embed_causal_kernel, N, 256, 0, s, m.wte[0], (int) m.wtype, m.wpe, d_tok, N, n_past, merge ? 1 : 0, m.n_embd, x);
 }
 void gpt_embed_fine(const GPTModel & m, const int32_t * d_ids, int nn, float * x, cudaStream_t s) {
+    if (qx_supported(m.wtype)) { qx_embed_fine(m, d_ids, nn, x, s); return; }
     FineTables t; for (int i = 0; i < 8; i++) t.wte[i] = m.wte[i];
     BARK_LAUNCH(embed_fine_kernel, 1024, 256, 0, s, t, (int) m.wtype, m.wpe, d_ids, nn, m.n_embd, x);
 }
@@ -225,6 +227,7 @@ static bool use_tiled() { static const bool t = [] { const char * e = getenv("BA
 
 void lane_matmul(const DMat & W, const void * act, int act_gs, int rows, const MatmulEpilogue & ep, cudaStream_t s) {
     if (W.type == W_Q4_0) { q4_matmul(W, act, act_gs, rows, ep, s); return; }      // act_gs = f32 row stride for this type
+    if (qx_supported(W.type)) { qx_matmul(W, act, act_gs, rows, ep, s); return; }
     const int gx = (W.n_out + 7) / 8;
     {   // roofline annotation: algorithmic HBM bytes (weights once + operands) and flops of this mat-mul
         const double es = W.type == W_F16 ? 2.0 : 4.0;

@@ -34,6 +34,15 @@ void q4_split(const void * raw_blocks, size_t n_blocks, void * qs, void * scales
 void q4_set_scratch(void * q8, void * q8_scales);      // int8 [rows][K] + f32 [rows][K/32] for the activation operand, owned by the context
 void q4_matmul(const DMat & W, const void * act_f32, int ld_act, int rows, const MatmulEpilogue & ep, cudaStream_t s);
 
+// ---- experimental: q4_1 / q5_0 / q5_1 / q8_0 weights (qx_kernels.cu; BARK_B200_EXPERIMENTAL_QUANTS=1) -----------------------------
+bool   qx_supported(WType t);
+size_t qx_block_bytes(WType t);
+void   qx_split(const void * raw_blocks, size_t n_blocks, WType t, void * qs, void * qh, void * d, void * m, cudaStream_t s);
+void   qx_set_scratch(void * q8, void * q8_scales, void * q8_sums);
+void   qx_embed_causal(const GPTModel & m, const int32_t * d_tok, int N, int n_past, bool merge, float * x, cudaStream_t s);
+void   qx_embed_fine(const GPTModel & m, const int32_t * d_ids, int nn, float * x, cudaStream_t s);
+void   qx_matmul(const DMat & W, const void * act_f32, int ld_act, int rows, const MatmulEpilogue & ep, cudaStream_t s);
+
 // ---- register-tiled multi-row kernels (gemm_kernels.cu) ------------------------------------------------------------
 void lane_gemm_tiled(const DMat & W, const void * act, int act_gs, int rows, const MatmulEpilogue & ep, cudaStream_t s);
 void attention_tiled_scores(const float * Q, const float * Kc, int N, int n_kv, int n_past, int E, int H, float scale, bool causal, float * scores, cudaStream_t s);

@@ -37,6 +37,7 @@ size_t type_bytes(int ttype, size_t nel) {
         case W_F32: return nel * 4;
         case W_F16: return nel * 2;
         case W_Q4_0: return nel / 32 * 18;
+        case W_Q4_1: case W_Q5_0: case W_Q5_1: case W_Q8_0: return nel / 32 * qx_block_bytes((WType) ttype);
         default: return 0;
     }
 }
@@ -82,11 +83,17 @@ bool load_gpt(bark_context * ctx, std::ifstream & f, GPTModel & m, const char * 
         printf("%s: %s model: n_layer=%d n_head=%d n_embd=%d block_size=%d bias=%d n_in_vocab=%d n_out_vocab=%d n_lm_heads=%d n_wtes=%d ftype=%d\n",
                __func__, what, m.n_layer, m.n_head, m.n_embd, m.block_size, m.bias, m.n_in_vocab, m.n_out_vocab, m.n_lm_heads, m.n_wtes, m.ftype);
     m.ftype %= 1000;                                                          // GGML_QNT_VERSION_FACTOR, bark.cpp:727
-    if (m.ftype != W_F32 && m.ftype != W_F16 && m.ftype != W_Q4_0) {
-        fprintf(stderr, "%s: unsupported weight type (ftype %d) in %s model: this build reads f32, f16 and q4_0 GPT weights\n", __func__, m.ftype, what);
+    // enum ggml_ftype -> enum ggml_type (ggml.c ggml_ftype_to_ggml_type): 0 f32, 1 f16, 2 q4_0 coincide; q4_1 3 -> 3, q8_0 7 -> 8, q5_0 8 -> 6, q5_1 9 -> 7
+    const bool experimental = [] { const char * e = getenv("BARK_B200_EXPERIMENTAL_QUANTS"); return e && !strcmp(e, "1"); }();
+    int wt = -1;
+    switch (m.ftype) { case 0: wt = W_F32; break; case 1: wt = W_F16; break; case 2: wt = W_Q4_0; break;
+                       case 3: wt = W_Q4_1; break; case 7: wt = W_Q8_0; break; case 8: wt = W_Q5_0; break; case 9: wt = W_Q5_1; break; default: break; }
+    if (wt < 0 || (qx_supported((WType) wt) && !experimental)) {
+        fprintf(stderr, "%s: unsupported weight type (ftype %d) in %s model: this build reads f32, f16 and q4_0 GPT weights%s\n", __func__, m.ftype, what,
+                wt >= 0 ? " (q4_1 / q5_0 / q5_1 / q8_0 kernels exist but are experimental: BARK_B200_EXPERIMENTAL_QUANTS=1)" : "");
         return false;
     }
-    m.wtype = (WType) m.ftype;
+    m.wtype = (WType) wt;
     const int E = m.n_embd;
     if (m.n_layer <= 0 || m.n_head <= 0 || E <= 0 || E % 32 != 0 || E % m.n_head != 0 || (E / m.n_head) % 32 != 0 || (E / m.n_head) > 128 ||
         m.block_size <= 0 || m.block_size > 1024 || m.n_wtes < 1 || m.n_wtes > 8 || m.n_lm_heads < 1 || m.n_lm_heads > 8) {
@@ -136,6 +143,16 @@ bool load_gpt(bark_context * ctx, std::ifstream & f, GPTModel & m, const char * 
             void * raw = upload_raw(ctx, f, bytes, host, false);
             if (!raw) return false;
             DMat & d = *s.mat;
+            if (qx_supported(m.wtype)) {                     // experimental types: qs / qh / d / m arrays (qx_kernels.cu)
+                const size_t n_blocks = h.nel / 32;
+                d.n_out = s.ne1; d.K = s.ne0; d.Kp = d.K; d.type = m.wtype;
+                d.p = ctx_alloc(ctx, n_blocks * (m.wtype == W_Q8_0 ? 32 : 16)); d.scales = ctx_alloc(ctx, n_blocks * 2);
+                d.mins = ctx_alloc(ctx, n_blocks * 2); d.qh = ctx_alloc(ctx, n_blocks * 4);
+                qx_split(raw, n_blocks, m.wtype, d.p, d.qh, d.scales, d.mins, ctx->stream);
+                BARK_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+                BARK_CUDA_CHECK(cudaFree(raw));
+                continue;
+            }
             if (m.wtype == W_Q4_0) {                         // 18-byte blocks -> aligned nibble words + f16 scales (q4_kernels.cu)
                 const size_t n_blocks = h.nel / 32;
                 d.n_out = s.ne1; d.K = s.ne0; d.Kp = d.K; d.type = W_Q4_0;
@@ -329,8 +346,8 @@ bool load_model_file(const std::string & path, bark_context * ctx) {
     }
     ctx->d_ln_fallbacks = (unsigned *) ctx_alloc(ctx, 4 * sizeof(unsigned));
     BARK_CUDA_CHECK(cudaMemset(ctx->d_ln_fallbacks, 0, 4 * sizeof(unsigned)));
-    if (ctx->semantic.wtype != W_Q4_0) build_decode_tables(ctx, ctx->semantic);   // q4_0 models step through the per-op kernels
-    if (ctx->coarse.wtype != W_Q4_0) build_decode_tables(ctx, ctx->coarse);
+    if (!is_quant(ctx->semantic.wtype)) build_decode_tables(ctx, ctx->semantic);   // quantised models step through the per-op kernels
+    if (!is_quant(ctx->coarse.wtype)) build_decode_tables(ctx, ctx->coarse);
     return true;
 }
 

@@ -13,7 +13,8 @@ namespace bark {
 struct DMat {                 // 2-D weight [n_out][K] in LI layout (f32 / f16) or q4_0 blocks
     void * p = nullptr;
     int n_out = 0, K = 0, Kp = 0;   // Kp = padded row length in elements
-    void * scales = nullptr;        // q4_0: f16 block scales [n_out][K/32]; p then holds the 16-byte nibble words [n_out][K/32]
+    void * scales = nullptr;        // quantised: f16 block scales [n_out][K/32]; p then holds the 16-byte nibble words (32 B for q8_0) [n_out][K/32]
+    void * mins = nullptr, * qh = nullptr;   // experimental types: f16 block minima (q4_1, q5_1), fifth bits (q5_0, q5_1)
     void * p_gm = nullptr; int o_pad = 0;   // second copy in the group-major layout (common.cuh) for the tiled GEMM; rows padded to o_pad
     WType type = W_F16;
 };

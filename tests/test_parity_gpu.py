@@ -309,3 +309,40 @@ def test_packed_fma_variants_are_bit_identical(pkg, orc, weights_file, monkeypat
     lo, _ = o.gpt_eval(1, toks, 0, False)
     assert np.array_equal(bits(res["1"][0]), bits(lo))
     assert np.array_equal(bits(res["1"][2]), bits(o.fine_eval(buf, 5)))
+
+
+@pytest.mark.skipif(__import__("os").environ.get("BARK_B200_TEST_EXPERIMENTAL") != "1", reason="opt-in: BARK_B200_TEST_EXPERIMENTAL=1 (code paths not yet validated on a B200)")
+@pytest.mark.parametrize("qname,ftype_id", [("q4_1", 3), ("q5_0", 8), ("q5_1", 9), ("q8_0", 7)])
+@pytest.mark.parametrize("config,src_ftype,n_steps", [("tiny", "f16", 16), ("mini", "f32", 24)])
+def test_experimental_quant_types(pkg, orc, weights_file, tmp_path, monkeypatch, config, src_ftype, n_steps, qname, ftype_id):
+    """q4_1 / q5_0 / q5_1 / q8_0 GPT weights (qx_kernels.cu, loaded only with BARK_B200_EXPERIMENTAL_QUANTS=1) against the oracle,
+    whose arithmetic for these types is pinned bit-exactly against the unmodified reference (tests/test_quantize.py)."""
+    monkeypatch.setenv("BARK_B200_EXPERIMENTAL_QUANTS", "1")
+    src = weights_file(config, src_ftype)
+    path = str(tmp_path / f"{qname}.bin")
+    assert pkg.lib().bark_model_quantize(src.encode(), path.encode(), ftype_id)
+    o = orc.Oracle(path, seed=0, n_steps=n_steps)
+    rng = np.random.default_rng(31)
+    with pkg.Bark(path, seed=0, n_steps_text_encoder=n_steps) as b:
+        assert int(b.hparams(0)[9]) % 1000 == ftype_id
+        toks, pg, po = o.tokenize("Hello, world"), 0, 0
+        for step in range(5):
+            lg, pg = b.gpt_eval(0, toks, pg, True)
+            lo, po = o.gpt_eval(0, toks, po, True)
+            assert np.array_equal(bits(lg), bits(lo)), f"semantic step {step}: {int((lg != lo).sum())} logits differ, max {np.abs(lg - lo).max():.3e}"
+            toks = np.array([int(np.argmax(lo[:10000]))], np.int32)
+        toks = np.concatenate([rng.integers(0, 10000, 256), [12050], rng.integers(10000, 12048, 29)]).astype(np.int32)
+        pg = po = 0
+        for step in range(5):
+            lg, pg = b.gpt_eval(1, toks, pg, False)
+            lo, po = o.gpt_eval(1, toks, po, False)
+            assert np.array_equal(bits(lg), bits(lo)), f"coarse step {step}: {int((lg != lo).sum())} logits differ"
+            toks = np.array([10000 + int(np.argmax(lo[10000:12048]))], np.int32)
+        buf = rng.integers(0, 1024, (8, 1024)).astype(np.int32); buf[:, 400:] = 1024; buf[4:, :] = 1024
+        assert np.array_equal(bits(b.fine_eval(buf, 4)), bits(o.fine_eval(buf, 4)))
+        ref = o.generate("hello world")
+        audio = b.generate("hello world")
+        assert np.array_equal(b.tokens(0), ref["semantic"])
+        assert np.array_equal(b.tokens(1), ref["coarse"])
+        assert np.array_equal(b.tokens(2), ref["fine"])
+        assert wav_rel(audio, ref["audio"]) < WAV_RTOL
