@@ -49,6 +49,7 @@ EXPORTS = [
     "bark_b200_forward_coarse_encoder", "bark_b200_forward_fine_encoder", "bark_b200_get_tokens", "bark_b200_set_tokens",
     "bark_b200_get_stats", "bark_b200_get_hparams", "bark_b200_kernel_launches", "bark_b200_layernorm_fallbacks",
     "bark_b200_profile_enable", "bark_b200_profile_report", "bark_b200_io_counters", "bark_b200_decode_timing",
+    "bark_b200_fast_mode", "bark_b200_fast_gemm", "bark_b200_fast_attention",
     "ggml_time_init", "ggml_time_us", "ggml_time_ms", "ggml_init", "ggml_free",
 ]
 
@@ -112,6 +113,12 @@ def lib() -> C.CDLL:
     L.bark_b200_io_counters.argtypes = [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), C.c_int]
     L.bark_b200_decode_timing.restype = C.c_int
     L.bark_b200_decode_timing.argtypes = [vp, C.c_void_p, C.c_int]
+    L.bark_b200_fast_mode.restype = C.c_int
+    L.bark_b200_fast_mode.argtypes = [vp]
+    L.bark_b200_fast_gemm.restype = C.c_int
+    L.bark_b200_fast_gemm.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int]
+    L.bark_b200_fast_attention.restype = C.c_int
+    L.bark_b200_fast_attention.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int]
     L.ggml_time_us.restype = C.c_int64
     _lib = L
     return L
@@ -248,8 +255,32 @@ class Bark:
         lib().bark_b200_get_stats(self.ctx, C.byref(s), _p(pm))
         return s, pm.reshape(3, 3)
 
+    @property
+    def fast_mode(self) -> bool:
+        return bool(lib().bark_b200_fast_mode(self.ctx))
+
     def layernorm_fallbacks(self) -> int:
         return int(lib().bark_b200_layernorm_fallbacks(self.ctx))
+
+
+def fast_gemm(A: np.ndarray, W: np.ndarray) -> np.ndarray:
+    """C = A W^T on the tcgen05 path; A [M][K], W [N][K] float16."""
+    A = np.ascontiguousarray(A, np.float16); W = np.ascontiguousarray(W, np.float16)
+    M, K = A.shape; N = W.shape[0]
+    out = np.zeros((M, N), np.float32)
+    if not lib().bark_b200_fast_gemm(_p(A), _p(W), _p(out), M, N, K):
+        raise RuntimeError("bark_b200_fast_gemm failed")
+    return out
+
+
+def fast_attention(q: np.ndarray, k: np.ndarray, v: np.ndarray, n_head: int) -> np.ndarray:
+    """Non-causal attention on the tcgen05 path; q, k, v [n][E] float16 -> [n][E] float16."""
+    q, k, v = (np.ascontiguousarray(a, np.float16) for a in (q, k, v))
+    n, E = q.shape
+    out = np.zeros((n, E), np.float16)
+    if not lib().bark_b200_fast_attention(_p(q), _p(k), _p(v), _p(out), n, E, n_head):
+        raise RuntimeError("bark_b200_fast_attention failed")
+    return out
 
 
 def kernel_launches() -> int:

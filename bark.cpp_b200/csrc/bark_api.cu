@@ -20,7 +20,7 @@ using namespace bark;
 
 namespace {
 
-int  g_device_override = -1;
+thread_local int g_device_override = -1;   // bark_b200_set_device applies to the calling thread's next bark_load_model
 bool quiet() { static const bool q = [] { const char * e = getenv("BARK_B200_QUIET"); return e && *e && *e != '0'; }(); return q; }
 
 // ---------------------------------------------------------------------------------------------
@@ -199,7 +199,7 @@ bool run_chain(bark_context * ctx, GPTModel & m, const std::vector<int32_t> & fi
         for (int j = 0; j < n; j++) ctx->h_u[j] = std::generate_canonical<double, 53>(ctx->rng);     // one draw per sample, as discrete_distribution::operator() makes
         BARK_CUDA_CHECK(cudaMemcpyAsync(ctx->d_u, ctx->h_u, (size_t) n * sizeof(double), cudaMemcpyHostToDevice, s)); bark::g_h2d_bytes += (size_t) n * sizeof(double);
     }
-    const bool chain = ctx->use_decode_kernel && !is_quant(m.wtype);
+    const bool chain = ctx->use_decode_kernel && m.decode_ok && !is_quant(m.wtype);
     std::vector<int> past_before((size_t) n);
     std::vector<int32_t> cur_in = first_in;
     std::vector<float> host_logits;
@@ -428,6 +428,17 @@ void alloc_workspace(bark_context * ctx) {
         ctx->d_q8 = ctx_alloc(ctx, R * (size_t) 4 * E); ctx->d_q8_scales = ctx_alloc(ctx, R * (size_t)(4 * E / 32) * 4);
         ctx->d_q8_sums = ctx_alloc(ctx, R * (size_t)(4 * E / 32) * 4);
     }
+    if (ctx->fast_mode) {
+        const GPTModel & fm = ctx->fine;
+        if (fm.wtype != W_F16 || fm.n_embd / fm.n_head != 64 || fm.n_embd % 64 != 0) {
+            fprintf(stderr, "bark_b200: BARK_B200_MODE=fast needs f16 fine-model weights with 64-wide heads; using the parity path\n");
+            ctx->fast_mode = false;
+        } else {
+            const size_t FE = (size_t) fm.n_embd;
+            ctx->f_a16 = (__half *) ctx_alloc(ctx, R * FE * 2); ctx->f_h16 = (__half *) ctx_alloc(ctx, R * 4 * FE * 2);
+            ctx->f_qk16 = (__half *) ctx_alloc(ctx, R * 2 * FE * 2); ctx->f_vt16 = (__half *) ctx_alloc(ctx, FE * R * 2); ctx->f_att16 = (__half *) ctx_alloc(ctx, R * FE * 2);
+        }
+    }
     BARK_CUDA_CHECK(cudaMallocHost(&ctx->h_logits, n_logits * 4));
     BARK_CUDA_CHECK(cudaMallocHost(&ctx->h_tok, 8 * 1024 * 4));
     ctx->d_u = (double *) ctx_alloc(ctx, 1024 * 8); ctx->d_stok = (int32_t *) ctx_alloc(ctx, 1024 * 4);
@@ -491,7 +502,8 @@ extern "C" struct bark_context * bark_load_model(const char * model_path, struct
     }
     bark_context * ctx = new bark_context();
     ctx->device = dev;
-    ctx->n_sm = prop.multiProcessorCount;
+    ctx->n_sm = ctx->n_sm_total = prop.multiProcessorCount;
+    { const char * e = getenv("BARK_B200_MODE"); ctx->fast_mode = e && !strcmp(e, "fast"); }             // "fast": tensor-core fine passes (fast_kernels.cu), not bit-identical
     { const char * e = getenv("BARK_B200_DECODE_CTAS"); if (e && atoi(e) >= 64 && atoi(e) <= ctx->n_sm) ctx->n_sm = atoi(e); }   // experiment knob: CTAs of the persistent decode kernel
     { const char * e = getenv("BARK_B200_SAMPLE_FLAG_EVERY"); ctx->debug_flag_every = e ? atoi(e) : 0; }
     { const char * e = getenv("BARK_B200_SAMPLE"); ctx->sample_on_device = !(e && !strcmp(e, "host")); }      // "host": read logits back and sample on the CPU (A-B)
@@ -509,6 +521,7 @@ extern "C" struct bark_context * bark_load_model(const char * model_path, struct
     { const char * e = getenv("BARK_B200_POLL_NS"); if (e && atoi(e) >= 0 && atoi(e) <= 100000) ctx->poll_ns = (unsigned) atoi(e); }
     { const char * e = getenv("BARK_B200_POLL_ATT_NS"); if (e && atoi(e) >= 0 && atoi(e) <= 100000) ctx->att_ns = (unsigned) atoi(e); }
     { const char * e = getenv("BARK_B200_POLL_FIRST_NS"); if (e && atoi(e) >= 0 && atoi(e) <= 100000) ctx->first_ns = (unsigned) atoi(e); }
+    { const char * e = getenv("BARK_B200_TAG_BASE"); if (e) ctx->tag_base = (unsigned) strtoul(e, nullptr, 0); }      // tests: start the exchange epochs near the 32-bit wrap
     if (getenv("BARK_B200_DECODE_TIMING")) { ctx->d_timing = (unsigned long long *) ctx_alloc(ctx, 256 * 32 * 8); BARK_CUDA_CHECK(cudaMemset(ctx->d_timing, 0, 256 * 32 * 8)); }
     BARK_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     ctx->rng = std::mt19937(seed);
@@ -655,7 +668,7 @@ extern "C" void bark_b200_get_hparams(struct bark_context * ctx, int which, int3
     const int32_t v[10] = {m->n_layer, m->n_head, m->n_embd, m->block_size, m->bias, m->n_in_vocab, m->n_out_vocab, m->n_lm_heads, m->n_wtes, m->ftype};
     memcpy(out10, v, sizeof(v));
 }
-extern "C" unsigned long long bark_b200_kernel_launches(void) { return g_kernel_launches; }
+extern "C" unsigned long long bark_b200_kernel_launches(void) { return g_kernel_launches.load(); }
 extern "C" unsigned bark_b200_layernorm_fallbacks(struct bark_context * ctx) {
     if (!ctx) return 0;
     unsigned v = 0; BARK_CUDA_CHECK(cudaMemcpy(&v, ctx->d_ln_fallbacks, sizeof(v), cudaMemcpyDeviceToHost)); return v;
@@ -665,4 +678,39 @@ extern "C" int bark_b200_decode_timing(struct bark_context * ctx, unsigned long 
     BARK_CUDA_CHECK(cudaMemcpy(out, ctx->d_timing, sizeof(unsigned long long) * (size_t) std::min(n, 256 * 32), cudaMemcpyDeviceToHost));
     return std::min(n, 256 * 32);
 }
-extern "C" const char * bark_b200_version(void) { return "bark_b200 r1 (sm_100a, parity path)"; }
+// fast-mode kernels on host buffers (tests): C[M][N] = A[M][K] W[N][K]^T (f16 in, f32 out), and attention over [n][E] f16 q / k / v
+extern "C" int bark_b200_fast_gemm(const uint16_t * A, const uint16_t * W, float * C, int M, int N, int K) {
+    if (!A || !W || !C || M < 1 || N < 1 || K < 64 || K % 64) return 0;
+    __half * dA, * dW; float * dC; int dev = 0, n_sm = 0;
+    BARK_CUDA_CHECK(cudaGetDevice(&dev)); BARK_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    BARK_CUDA_CHECK(cudaMalloc(&dA, (size_t) M * K * 2)); BARK_CUDA_CHECK(cudaMalloc(&dW, (size_t) N * K * 2)); BARK_CUDA_CHECK(cudaMalloc(&dC, (size_t) M * N * 4));
+    BARK_CUDA_CHECK(cudaMemcpy(dA, A, (size_t) M * K * 2, cudaMemcpyHostToDevice)); BARK_CUDA_CHECK(cudaMemcpy(dW, W, (size_t) N * K * 2, cudaMemcpyHostToDevice));
+    BARK_CUDA_CHECK(cudaMemset(dC, 0xff, (size_t) M * N * 4));
+    FastEpi ep; ep.mode = FEPI_F32; ep.out32 = dC; ep.ldo = N;
+    const bool ok = fast_gemm(dA, K, dW, K, M, N, K, ep, n_sm, 0);
+    const cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) fprintf(stderr, "bark_b200_fast_gemm: %s\n", cudaGetErrorString(e));
+    else BARK_CUDA_CHECK(cudaMemcpy(C, dC, (size_t) M * N * 4, cudaMemcpyDeviceToHost));
+    cudaFree(dA); cudaFree(dW); cudaFree(dC);
+    return ok && e == cudaSuccess;
+}
+extern "C" int bark_b200_fast_attention(const uint16_t * q, const uint16_t * k, const uint16_t * v, uint16_t * out, int n, int E, int H) {
+    if (!q || !k || !v || !out || n < 256 || n % 256 || E != H * 64) return 0;
+    std::vector<uint16_t> qk((size_t) n * 2 * E), vt((size_t) E * n);
+    for (int r = 0; r < n; r++) {
+        memcpy(&qk[(size_t) r * 2 * E], q + (size_t) r * E, (size_t) E * 2); memcpy(&qk[(size_t) r * 2 * E + E], k + (size_t) r * E, (size_t) E * 2);
+        for (int c = 0; c < E; c++) vt[(size_t) c * n + r] = v[(size_t) r * E + c];
+    }
+    __half * dqk, * dvt, * dout;
+    BARK_CUDA_CHECK(cudaMalloc(&dqk, qk.size() * 2)); BARK_CUDA_CHECK(cudaMalloc(&dvt, vt.size() * 2)); BARK_CUDA_CHECK(cudaMalloc(&dout, (size_t) n * E * 2));
+    BARK_CUDA_CHECK(cudaMemcpy(dqk, qk.data(), qk.size() * 2, cudaMemcpyHostToDevice)); BARK_CUDA_CHECK(cudaMemcpy(dvt, vt.data(), vt.size() * 2, cudaMemcpyHostToDevice));
+    const bool ok = fast_attention(dqk, 2 * E, E, dvt, n, E, H, dout, 0);
+    const cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) fprintf(stderr, "bark_b200_fast_attention: %s\n", cudaGetErrorString(e));
+    else BARK_CUDA_CHECK(cudaMemcpy(out, dout, (size_t) n * E * 2, cudaMemcpyDeviceToHost));
+    cudaFree(dqk); cudaFree(dvt); cudaFree(dout);
+    return ok && e == cudaSuccess;
+}
+extern "C" int bark_b200_fast_mode(struct bark_context * ctx) { return ctx && ctx->fast_mode ? 1 : 0; }
+
+extern "C" const char * bark_b200_version(void) { return "bark_b200 r2 (sm_100a; parity path + opt-in tcgen05 fast mode)"; }

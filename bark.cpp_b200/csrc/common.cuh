@@ -10,6 +10,7 @@
 
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#include <atomic>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -26,16 +27,24 @@
 
 namespace bark {
 
+// Process-wide state is limited to counters (atomic) and per-thread annotations (thread_local), so that one host thread per GPU can
+// drive its own bark_context inside one process (tests/test_parity_gpu.py two-thread case).
 // number of kernels this library launched (bench.py reports it as gpu_launches)
-extern unsigned long long g_kernel_launches;
+extern std::atomic<unsigned long long> g_kernel_launches;
 // host<->device traffic issued by the library (bench.py: e2e.h2d_bytes_per_step / d2h_bytes_per_step)
-extern unsigned long long g_h2d_bytes, g_d2h_bytes;
+extern std::atomic<unsigned long long> g_h2d_bytes, g_d2h_bytes;
+// Kernel attributes (cudaFuncSetAttribute) are per DEVICE: true exactly once per (call site's mask, current device).
+inline bool first_use_on_this_device(std::atomic<unsigned long long> & mask) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) return true;
+    return !(mask.fetch_or(1ull << dev) >> dev & 1ull);
+}
 // optional per-launch device timing (prof.cu): CUDA events on the launching stream around every kernel
 extern bool g_prof_on;
 void prof_begin(const char * name, cudaStream_t s, double bytes, double flops);
 void prof_end(cudaStream_t s);
 // annotate the NEXT launch with its algorithmic HBM bytes and/or flops for the roofline report
-extern double g_next_bytes, g_next_flops;
+extern thread_local double g_next_bytes, g_next_flops;
 #define BARK_LAUNCH(kernel, grid, block, smem, stream, ...)                                           \
     do {                                                                                              \
         if (::bark::g_prof_on) ::bark::prof_begin(#kernel, (stream), ::bark::g_next_bytes, ::bark::g_next_flops);            \
@@ -46,7 +55,7 @@ extern double g_next_bytes, g_next_flops;
     } while (0)
 
 // weight element types as stored in ggml_weights.bin (ggml_type values)
-enum WType : int { W_F32 = 0, W_F16 = 1, W_Q4_0 = 2, W_Q4_1 = 3, W_Q5_0 = 6, W_Q5_1 = 7, W_Q8_0 = 8 };   // 3..8: experimental (qx_kernels.cu)
+enum WType : int { W_F32 = 0, W_F16 = 1, W_Q4_0 = 2, W_Q4_1 = 3, W_Q5_0 = 6, W_Q5_1 = 7, W_Q8_0 = 8 };   // 3..8: qx_kernels.cu
 inline bool is_quant(WType t) { return t != W_F32 && t != W_F16; }
 
 // ---------------------------------------------------------------------------------------------

@@ -16,6 +16,11 @@
 //    spin on the words they need until the epoch matches.  Data and "ready" flag arrive in the same L2 transaction, so a
 //    grid-wide dependency costs one store->load latency instead of store + fence + atomic + poll + load (a classic
 //    barrier measured 1.5-2 us here; 6 per layer).  Epochs are unique per use and never reset.
+//    The vectors EVERY CTA gathers (q, attention output, residual stream, MLP activations) are published into kReplicas copies
+//    (lanes 0..7 of the producing warp store the same word into 8 buffers) and CTA c polls copy c % 8 with 16-byte loads: an L2
+//    line then has 18 readers instead of 148 and half as many requests.  tools/microbench/exchange_rounds.cu: one grid-wide
+//    dependency of 768 words costs 2.2x less this way (profiles/r02_exchange_rounds.md) — the hot lines, not the latency of one
+//    L2 round trip, were what made an exchange cost 1.5-2 us.
 //  * KV rows of older positions are prefetched into registers BEFORE waiting for q / the probabilities.
 //  * Nothing the phases need lives in local memory: block-wide state is in static shared memory (BlockCtx).
 //
@@ -37,6 +42,7 @@ constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
 constexpr int kWarpSlotBytes = 12 * 1024;       // per-warp staging area: two halves, phases alternate (rows are fetched two phases ahead)
 constexpr int kHalfSlotBytes = kWarpSlotBytes / 2;
+constexpr int kReplicas = kDecodeReplicas;      // copies of every all-to-all exchange vector (gpt_kernels.h)
 
 struct SmemLayout {
     static constexpr int wslot = 0;                                 // kWarps x 12 KB: each warp's weight rows of its next two phases (TMA bulk copies)
@@ -84,6 +90,14 @@ __device__ __forceinline__ tagged_t peek(const tagged_t * p) {
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
     return w;
 }
+// two adjacent tagged words in one 16-byte request (each word is still its own {value, epoch} unit)
+__device__ __forceinline__ void peek2(const tagged_t * p, tagged_t & a, tagged_t & b) {
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+// lanes 0 .. kReplicas-1 of a warp store the same word into the kReplicas copies of an all-to-all vector (copy stride `n` words)
+__device__ __forceinline__ void publish_all(tagged_t * base, int n, int i, float v, uint32_t tag, int lane) {
+    if (lane < kReplicas) publish(base + (size_t) lane * n + i, v, tag);
+}
 __shared__ unsigned s_poll_ns, s_first_ns, s_att_ns;                           // back-off between polls (DecodeArgs::poll_ns, default 40); head start given to the two residual exchanges
 __device__ __forceinline__ float consume1(const tagged_t * p, uint32_t tag) {
     tagged_t w = peek(p);
@@ -118,17 +132,37 @@ __device__ __forceinline__ void tstamp(int i) {
 enum { SINK_PLAIN = 0, SINK_ACT = 1, SINK_ACT_R16 = 2 };
 template <int MAXJ>
 __device__ __forceinline__ void consume_to_smem_inl(const tagged_t * g, int n, uint32_t tag, float * dst, int mode, unsigned first_ns = 0) {
-    tagged_t w[MAXJ];
+    constexpr int PJ = MAXJ / 2;                             // pairs of words per thread (n is even: E % 32 == 0)
+    tagged_t w[PJ][2];
+    g += (size_t)(blockIdx.x % kReplicas) * n;               // this CTA's copy of the vector
     if (first_ns) __nanosleep(first_ns);                     // the producers are known to need at least this long: do not hammer their lines meanwhile
 #pragma unroll
-    for (int j = 0; j < MAXJ; j++) { const int i = threadIdx.x + j * kThreads; if (i < n) w[j] = peek(g + i); }
+    for (int j = 0; j < PJ; j++) { const int i = 2 * (threadIdx.x + j * kThreads); if (i < n) peek2(g + i, w[j][0], w[j][1]); }
 #pragma unroll
-    for (int j = 0; j < MAXJ; j++) {
+    for (int j = 0; j < PJ; j++) {
+        const int i = 2 * (threadIdx.x + j * kThreads);
+        if (i < n) {
+            while ((uint32_t)(w[j][0] >> 32) != tag || (uint32_t)(w[j][1] >> 32) != tag) { __nanosleep(s_poll_ns); peek2(g + i, w[j][0], w[j][1]); }
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const float v = __uint_as_float((uint32_t) w[j][e]);
+                if (mode == SINK_PLAIN) dst[i + e] = v; else dst[act_index(i + e)] = mode == SINK_ACT_R16 ? round_f16(v) : v;
+            }
+        }
+    }
+    __syncthreads();
+}
+// one private (not replicated) vector of any length, one word per load: the score row of a head (a few consumer CTAs per head)
+__device__ __noinline__ void consume_row_to_smem(const tagged_t * g, int n, uint32_t tag, float * dst) {
+    tagged_t w[2];
+#pragma unroll
+    for (int j = 0; j < 2; j++) { const int i = threadIdx.x + j * kThreads; if (i < n) w[j] = peek(g + i); }
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
         const int i = threadIdx.x + j * kThreads;
         if (i < n) {
             while ((uint32_t)(w[j] >> 32) != tag) { __nanosleep(s_poll_ns); w[j] = peek(g + i); }
-            const float v = __uint_as_float((uint32_t) w[j]);
-            if (mode == SINK_PLAIN) dst[i] = v; else dst[act_index(i)] = mode == SINK_ACT_R16 ? round_f16(v) : v;
+            dst[i] = __uint_as_float((uint32_t) w[j]);
         }
     }
     __syncthreads();
@@ -372,15 +406,18 @@ __device__ __noinline__ void run_phase(int phase, int ep, int layer, uint32_t ot
     tstamp<TM>(sb);
     const int E = s_bc.E;
     // one output row: lane 0 publishes / stores it in the form the consumer of this phase expects
+    // every lane holds the row's result (lane_tree_reduce): lanes 0..7 write the copies of an all-to-all vector, lane 0 everything else
     auto emit = [&](int r, float v) {
         if (ep == EP_QKV) {
             const size_t slot_off = ((size_t) layer * s_bc.ctx + s_bc.n_past) * E;
-            if (r < E) publish(s_bc.gq + r, v, otag);
-            else if (r < 2 * E) { publish(s_bc.gk + (r - E), v, otag); s_bc.mem_k[slot_off + (r - E)] = v; }
-            else                { publish(s_bc.gv + (r - 2 * E), v, otag); s_bc.mem_v[slot_off + (r - 2 * E)] = v; }
+            if (r < E) publish_all(s_bc.gq, E, r, v, otag, lane);
+            else if (lane == 0) {
+                if (r < 2 * E) { publish(s_bc.gk + (r - E), v, otag); s_bc.mem_k[slot_off + (r - E)] = v; }
+                else           { publish(s_bc.gv + (r - 2 * E), v, otag); s_bc.mem_v[slot_off + (r - 2 * E)] = v; }
+            }
         } else if (ep == EP_RESID) {
-            publish(s_bc.gx + r, __fadd_rn(v, xs[r]), otag);
-        } else {
+            publish_all(s_bc.gx, E, r, __fadd_rn(v, xs[r]), otag, lane);
+        } else if (lane == 0) {
             s_bc.logits[r] = v;
         }
     };
@@ -392,18 +429,18 @@ __device__ __noinline__ void run_phase(int phase, int ep, int layer, uint32_t ot
             float v[2];
             if (staged) row_dot<WT, true, 2>(row, p.row_bytes, act, p.K, lane, v);
             else { float u[1]; row_dot<WT, false, 1>(row, p.row_bytes, act, p.K, lane, u); v[0] = u[0]; row_dot<WT, false, 1>(row + p.row_bytes, p.row_bytes, act, p.K, lane, u); v[1] = u[0]; }
-            if (lane == 0) {
+            if (lane < kReplicas) {
                 if (ep == EP_GELU) {
                     const __half t0 = s_bc.gelu_tab[__half_as_ushort(__float2half_rn(v[0]))], t1 = s_bc.gelu_tab[__half_as_ushort(__float2half_rn(v[1]))];
-                    publish(s_bc.gff + r, gelu_sel(v[0], t0), otag); publish(s_bc.gff + r + 1, gelu_sel(v[1], t1), otag);
+                    publish_all(s_bc.gff, 4 * E, r, gelu_sel(v[0], t0), otag, lane); publish_all(s_bc.gff, 4 * E, r + 1, gelu_sel(v[1], t1), otag, lane);
                 } else { emit(r, v[0]); emit(r + 1, v[1]); }
             }
             r += 2; j += 2;
         } else {
             float v[1];
             if (staged) row_dot<WT, true, 1>(row, p.row_bytes, act, p.K, lane, v); else row_dot<WT, false, 1>(row, p.row_bytes, act, p.K, lane, v);
-            if (lane == 0) {
-                if (ep == EP_GELU) publish(s_bc.gff + r, gelu_sel(v[0], s_bc.gelu_tab[__half_as_ushort(__float2half_rn(v[0]))]), otag);
+            if (lane < kReplicas) {
+                if (ep == EP_GELU) publish_all(s_bc.gff, 4 * E, r, gelu_sel(v[0], s_bc.gelu_tab[__half_as_ushort(__float2half_rn(v[0]))]), otag, lane);
                 else emit(r, v[0]);
             }
             r += 1; j += 1;
@@ -562,7 +599,7 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
             __syncthreads();                                         // slower warps may still be reading q (in `qs`) for their score tasks
             tstamp<TM>(9);
             float * p = qs;                                          // scores row -> exp(score - max); the 1/sum factor is applied on use
-            consume_to_smem<2>(s_bc.gscores + (size_t) h * ctx, n_kv, t_sc, p, SINK_PLAIN);
+            consume_row_to_smem(s_bc.gscores + (size_t) h * ctx, n_kv, t_sc, p);
             tstamp<TM>(10);
             float mx = __int_as_float(0xff800000);
 #pragma unroll 1
@@ -654,7 +691,8 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
                     const float tj = act[j * 16 + tid];
                     if (j < n4) sum = __fadd_rn(sum, tj); else sum = __fmaf_rn(tj, __fmul_rn(p[np + j], sc_f), sum);
                 }
-                publish(s_bc.gatt + col0 + tid, sum, t_att);
+#pragma unroll
+                for (int rep = 0; rep < kReplicas; rep++) publish(s_bc.gatt + (size_t) rep * E + col0 + tid, sum, t_att);
             }
             __syncthreads();                                     // `act` / `qs` are reused by the next phase
         }
@@ -695,11 +733,9 @@ int decode_tags_per_step(int n_layer) { return 6 * n_layer; }
 
 template <typename WT, int DSTEPS, bool TM>
 static void launch_variant(DecodeArgs a, int n_sm, cudaStream_t s) {
-    static bool configured = false;
-    if (!configured) {
+    static std::atomic<unsigned long long> configured{0};
+    if (first_use_on_this_device(configured))
         BARK_CUDA_CHECK(cudaFuncSetAttribute(gpt_decode_step_kernel<WT, DSTEPS, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) decode_smem_bytes()));
-        configured = true;
-    }
     void * kargs[] = {(void *) &a};
     BARK_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *) gpt_decode_step_kernel<WT, DSTEPS, TM>, dim3(n_sm), dim3(kThreads), kargs, decode_smem_bytes(), s));
 }

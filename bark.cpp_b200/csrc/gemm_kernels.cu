@@ -11,7 +11,8 @@
 // Both operands are in the group-major layout (common.cuh), so a pipeline stage of the block tile is a handful of
 // contiguous spans: 2-4 TMA bulk copies into a 4-stage shared-memory ring (mbarrier complete_tx).
 //
-// F2 variants (BARK_B200_FFMA2=1, experimental, default off until validated on a B200): the 64 independent FMAs of a chain step
+// F2 variants (the default since they were validated bit-exact on a B200, round 2; BARK_B200_FFMA2=0 selects the scalar-FMA
+// kernels for A-B runs): the 64 independent FMAs of a chain step
 // are issued as 32 packed FFMA2 (sm_100 `fma.rn.f32x2`, __ffma2_rn: "numeric behavior per component is the same as
 // __fmaf_rn"), with the scalar operand broadcast by the instruction itself.  Same arithmetic, same order, half the issue
 // slots — the tiled kernels are issue-bound (43 % of issue slots busy, 59-76 % of the instructions are FMAs).
@@ -201,29 +202,26 @@ __global__ void __launch_bounds__(256, 2) lane_gemm_tiled_kernel(const T * __res
     }
 }
 
-// BARK_B200_FFMA2=1: packed-FMA variants of the three tiled kernels (see the header comment)
-static bool use_ffma2() { const char * e = getenv("BARK_B200_FFMA2"); return e && e[0] == '1' && e[1] == 0; }   // read per launch so one process can A-B the two
+// packed-FMA variants of the three tiled kernels (see the header comment) unless BARK_B200_FFMA2=0
+static bool use_ffma2() { const char * e = getenv("BARK_B200_FFMA2"); return !(e && e[0] == '0' && e[1] == 0); }   // read per launch so one process can A-B the two
 
 void lane_gemm_tiled(const DMat & W, const void * act, int act_gs, int rows, const MatmulEpilogue & ep, cudaStream_t s) {
     const size_t smem = (size_t) kStages * kStageBytes + kStages * 8 + kStages * 4 + 64;
-    static int n_sm = 0;
-    if (!n_sm) {
-        int dev = 0; BARK_CUDA_CHECK(cudaGetDevice(&dev));
-        BARK_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    int dev = 0, n_sm = 0;
+    BARK_CUDA_CHECK(cudaGetDevice(&dev));
+    BARK_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    static std::atomic<unsigned long long> configured{0};
+    if (first_use_on_this_device(configured)) {
         BARK_CUDA_CHECK(cudaFuncSetAttribute(lane_gemm_tiled_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         BARK_CUDA_CHECK(cudaFuncSetAttribute(lane_gemm_tiled_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        BARK_CUDA_CHECK(cudaFuncSetAttribute((lane_gemm_tiled_kernel<__half, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        BARK_CUDA_CHECK(cudaFuncSetAttribute((lane_gemm_tiled_kernel<float, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     }
     if (!W.p_gm) { fprintf(stderr, "bark_b200: matrix has no group-major copy for the tiled mat-mul\n"); abort(); }
     const int n_tiles = ((W.n_out + kBO - 1) / kBO) * ((rows + kBM - 1) / kBM);
     const int grid = min(n_tiles, 2 * n_sm);                   // persistent: two CTAs per SM (registers and shared memory allow exactly that)
     const int w_gs = W.o_pad * kGmGroup;
     if (use_ffma2()) {
-        static bool configured = false;
-        if (!configured) {
-            BARK_CUDA_CHECK(cudaFuncSetAttribute((lane_gemm_tiled_kernel<__half, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-            BARK_CUDA_CHECK(cudaFuncSetAttribute((lane_gemm_tiled_kernel<float, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-            configured = true;
-        }
         if (W.type == W_F16) BARK_LAUNCH((lane_gemm_tiled_kernel<__half, true>), grid, 256, smem, s, (const __half *) W.p_gm, W.K, w_gs, W.n_out, (const __half *) act, act_gs, rows, ep);
         else                 BARK_LAUNCH((lane_gemm_tiled_kernel<float, true>), grid, 256, smem, s, (const float *) W.p_gm, W.K, w_gs, W.n_out, (const float *) act, act_gs, rows, ep);
         return;

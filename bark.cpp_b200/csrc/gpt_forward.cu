@@ -54,6 +54,16 @@ static void run_layers(bark_context * ctx, GPTModel & m, int N, int n_past, bool
 // Phase table + exchange buffers of the persistent decode kernel (decode_kernels.cu), once per causal model.
 void build_decode_tables(bark_context * ctx, GPTModel & m) {
     const int L = m.n_layer, E = m.n_embd;
+    // Fixed capacities of gpt_decode_step_kernel: shared-memory vectors of 1024 (x, q / probabilities) and 4096 (activation operand)
+    // floats, 128 phase slots, one soft_max tile per CTA (H * head/16 tiles), 6 score tasks per warp.  A model outside them steps
+    // through the per-op kernels instead (same results, slower) — never through a kernel it would overrun.
+    const int D = E / m.n_head;
+    m.decode_ok = E <= 1024 && 4 * E <= 4096 && 4 * L + 1 <= 128 && m.block_size <= 1024 && m.n_head * (D / 16) <= ctx->n_sm &&
+                  (long long) m.n_head * m.block_size <= 6ll * ctx->n_sm * 16;
+    if (!m.decode_ok) {
+        fprintf(stderr, "bark_b200: model (n_embd %d, n_layer %d, n_head %d, block_size %d) exceeds the persistent decode kernel's capacities; decoding with the per-op kernels\n", E, L, m.n_head, m.block_size);
+        return;
+    }
     const size_t es = m.wtype == W_F16 ? 2 : 4;
     std::vector<DecodePhase> ph((size_t) 4 * L + 1);
     std::vector<DecodeLayerVec> lv((size_t) L);
@@ -69,13 +79,29 @@ void build_decode_tables(bark_context * ctx, GPTModel & m) {
     BARK_CUDA_CHECK(cudaMemcpy(m.d_phases, ph.data(), ph.size() * sizeof(DecodePhase), cudaMemcpyHostToDevice));
     BARK_CUDA_CHECK(cudaMemcpy(m.d_layer_vecs, lv.data(), lv.size() * sizeof(DecodeLayerVec), cudaMemcpyHostToDevice));
     auto tagged = [&](size_t n) { void * p = ctx_alloc(ctx, n * 8); BARK_CUDA_CHECK(cudaMemset(p, 0, n * 8)); return (unsigned long long *) p; };   // epoch 0 = never published
-    m.gx = tagged((size_t) E); m.gq = tagged((size_t) E); m.gk = tagged((size_t) E); m.gv = tagged((size_t) E); m.gatt = tagged((size_t) E);
-    m.gff = tagged((size_t) 4 * E); m.gscores = tagged((size_t) m.n_head * m.block_size);
+    const size_t R = kDecodeReplicas;                         // vectors every CTA gathers exist in R copies (decode_kernels.cu)
+    m.gx = tagged(R * E); m.gq = tagged(R * E); m.gk = tagged((size_t) E); m.gv = tagged((size_t) E); m.gatt = tagged(R * E);
+    m.gff = tagged(R * 4 * E); m.gscores = tagged((size_t) m.n_head * m.block_size);
     m.glogits = (float *) ctx_alloc(ctx, (size_t) m.n_out_vocab * 4);
 }
 
 // one decode token through the persistent kernel
 static void decode_step(bark_context * ctx, GPTModel & m, int token, const int32_t * d_token, int n_past, int lm_lo, int lm_hi) {
+    // Epochs are 32-bit and must never repeat while a stale word could still carry the old value (~30 M tokens for 24 layers):
+    // before the counter wraps, drain the stream, clear every exchange word (epoch 0 = never published) and start over.
+    const unsigned step_tags = (unsigned) decode_tags_per_step(m.n_layer);
+    if (ctx->tag_base + step_tags + 1u < ctx->tag_base) {
+        BARK_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        for (GPTModel * g : {&ctx->semantic, &ctx->coarse}) {
+            if (!g->decode_ok) continue;
+            const size_t E8 = (size_t) g->n_embd * 8, R = kDecodeReplicas;
+            BARK_CUDA_CHECK(cudaMemsetAsync(g->gx, 0, R * E8, ctx->stream)); BARK_CUDA_CHECK(cudaMemsetAsync(g->gq, 0, R * E8, ctx->stream));
+            BARK_CUDA_CHECK(cudaMemsetAsync(g->gatt, 0, R * E8, ctx->stream)); BARK_CUDA_CHECK(cudaMemsetAsync(g->gff, 0, R * 4 * E8, ctx->stream));
+            BARK_CUDA_CHECK(cudaMemsetAsync(g->gk, 0, E8, ctx->stream)); BARK_CUDA_CHECK(cudaMemsetAsync(g->gv, 0, E8, ctx->stream));
+            BARK_CUDA_CHECK(cudaMemsetAsync(g->gscores, 0, (size_t) g->n_head * g->block_size * 8, ctx->stream));
+        }
+        ctx->tag_base = 0;
+    }
     DecodeArgs a{};
     a.phases = (const DecodePhase *) m.d_phases; a.layer_vecs = (const DecodeLayerVec *) m.d_layer_vecs;
     a.wte = m.wte[0]; a.wpe = m.wpe; a.ln_f_g = m.ln_f_g; a.ln_f_b = m.ln_f_b; a.gelu_tab = ctx->d_gelu_tab;
@@ -103,8 +129,12 @@ bool gpt_eval(bark_context * ctx, GPTModel & m, const int32_t * tokens, int n, i
     int N = n;
     bool merge = false;
     if (lm_hi <= 0 || lm_hi > m.n_out_vocab || lm_lo < 0 || lm_lo >= lm_hi) { lm_lo = 0; lm_hi = m.n_out_vocab; }
+    if (!tokens || n < 1 || n > 8 * 1024) { fprintf(stderr, "%s: bad token buffer (n = %d)\n", __func__, n); return false; }
+    for (int i = 0; i < n; i++) if (tokens[i] < 0 || tokens[i] >= m.n_in_vocab) {      // the embedding gather is unchecked on the device
+        fprintf(stderr, "%s: token id %d at position %d is outside the model's input vocabulary (%d)\n", __func__, tokens[i], i, m.n_in_vocab); return false;
+    }
     if (*n_past > 0 && N == 1) {
-        if (ctx->use_decode_kernel && !is_quant(m.wtype) && *n_past + 1 <= m.block_size && tokens[0] >= 0 && tokens[0] < m.n_in_vocab) {
+        if (ctx->use_decode_kernel && m.decode_ok && !is_quant(m.wtype) && *n_past + 1 <= m.block_size) {
             decode_step(ctx, m, tokens[0], nullptr, *n_past, lm_lo, lm_hi);
             ctx->last_logits = m.glogits;
             if (logits_host) {
@@ -145,7 +175,7 @@ bool gpt_eval(bark_context * ctx, GPTModel & m, const int32_t * tokens, int n, i
 // One decode step whose input token is read from device memory (the previous step's sample): nothing to wait for on the
 // host, so a whole window of steps is enqueued back to back.
 bool gpt_decode_chained(bark_context * ctx, GPTModel & m, const int32_t * d_token, int * n_past, int lm_lo, int lm_hi) {
-    if (!ctx->use_decode_kernel || is_quant(m.wtype) || *n_past < 1) { fprintf(stderr, "%s: needs the persistent decode kernel and a filled KV cache\n", __func__); return false; }
+    if (!ctx->use_decode_kernel || !m.decode_ok || is_quant(m.wtype) || *n_past < 1) { fprintf(stderr, "%s: needs the persistent decode kernel and a filled KV cache\n", __func__); return false; }
     if (*n_past + 1 > m.block_size) { fprintf(stderr, "%s: context overflow (n_past %d + 1 > %d)\n", __func__, *n_past, m.block_size); return false; }
     if (lm_hi <= 0 || lm_hi > m.n_out_vocab || lm_lo < 0 || lm_lo >= lm_hi) { lm_lo = 0; lm_hi = m.n_out_vocab; }
     decode_step(ctx, m, 0, d_token, *n_past, lm_lo, lm_hi);
@@ -155,12 +185,16 @@ bool gpt_decode_chained(bark_context * ctx, GPTModel & m, const int32_t * d_toke
 }
 
 bool fine_eval(bark_context * ctx, const int32_t * in_buffer, int nn, float * logits_host) {
+    if (ctx->fast_mode) return fine_eval_fast(ctx, in_buffer, nn, logits_host);
     GPTModel & m = ctx->fine;
     if (nn < 1 || nn > 7) { fprintf(stderr, "%s: codebook index %d out of range\n", __func__, nn); return false; }
     const int64_t t0 = now_us();
     Workspace & ws = ctx->ws;
     cudaStream_t s = ctx->stream;
     const int E = m.n_embd, N = 1024;
+    for (int i = 0; i < (nn + 1) * 1024; i++) if (in_buffer[i] < 0 || in_buffer[i] >= m.n_in_vocab) {
+        fprintf(stderr, "%s: code %d (codebook %d, frame %d) is outside the fine model's input vocabulary (%d)\n", __func__, in_buffer[i], i / 1024, i % 1024, m.n_in_vocab); return false;
+    }
     memcpy(ctx->h_tok, in_buffer, (size_t) 8 * 1024 * sizeof(int32_t));
     BARK_CUDA_CHECK(cudaMemcpyAsync(ws.tok, ctx->h_tok, (size_t) 8 * 1024 * sizeof(int32_t), cudaMemcpyHostToDevice, s)); g_h2d_bytes += (size_t) 8 * 1024 * sizeof(int32_t);
     gpt_embed_fine(m, ws.tok, nn, ws.x, s);
@@ -169,6 +203,48 @@ bool fine_eval(bark_context * ctx, const int32_t * in_buffer, int nn, float * lo
     layernorm_act(ws.x, N, E, m.ln_f_g, m.ln_f_b, ws.act, is_quant(m.wtype) ? W_Q4_0 : m.wtype, kpE, ctx->d_ln_fallbacks, s);
     MatmulEpilogue st; st.mode = EPI_STORE; st.out = ws.logits; st.ldo = m.n_out_vocab;
     lane_matmul(m.lm_head[nn - 1], ws.act, kpE, N, st, s);                                                           // n_codes_given = 1 (bark.cpp:61,1573)
+    ctx->last_logits = ws.logits;
+    if (logits_host) {
+        const size_t nb = (size_t) N * m.n_out_vocab * sizeof(float);
+        BARK_CUDA_CHECK(cudaMemcpyAsync(ctx->h_logits, ws.logits, nb, cudaMemcpyDeviceToHost, s)); g_d2h_bytes += nb;
+        BARK_CUDA_CHECK(cudaStreamSynchronize(s));
+        memcpy(logits_host, ctx->h_logits, nb);
+    }
+    m.t_predict_us += now_us() - t0;
+    return true;
+}
+
+// FAST MODE: the same pass on the tensor cores (fast_kernels.cu): LayerNorm -> f16, tcgen05 GEMMs with fused epilogues, flash-style
+// attention.  Same inputs / outputs as fine_eval; logits agree with the reference to f16-operand accuracy, not bit for bit.
+bool fine_eval_fast(bark_context * ctx, const int32_t * in_buffer, int nn, float * logits_host) {
+    GPTModel & m = ctx->fine;
+    if (nn < 1 || nn > 7) { fprintf(stderr, "%s: codebook index %d out of range\n", __func__, nn); return false; }
+    const int64_t t0 = now_us();
+    Workspace & ws = ctx->ws;
+    cudaStream_t s = ctx->stream;
+    const int E = m.n_embd, H = m.n_head, N = 1024, n_sm = ctx->n_sm_total;
+    for (int i = 0; i < (nn + 1) * 1024; i++) if (in_buffer[i] < 0 || in_buffer[i] >= m.n_in_vocab) {
+        fprintf(stderr, "%s: code %d (codebook %d, frame %d) is outside the fine model's input vocabulary (%d)\n", __func__, in_buffer[i], i / 1024, i % 1024, m.n_in_vocab); return false;
+    }
+    memcpy(ctx->h_tok, in_buffer, (size_t) 8 * 1024 * sizeof(int32_t));
+    BARK_CUDA_CHECK(cudaMemcpyAsync(ws.tok, ctx->h_tok, (size_t) 8 * 1024 * sizeof(int32_t), cudaMemcpyHostToDevice, s)); g_h2d_bytes += (size_t) 8 * 1024 * sizeof(int32_t);
+    gpt_embed_fine(m, ws.tok, nn, ws.x, s);
+    for (int il = 0; il < m.n_layer; il++) {
+        const GPTLayer & L = m.layers[(size_t) il];
+        fast_layernorm(ws.x, N, E, L.ln_1_g, L.ln_1_b, ctx->f_a16, s);
+        FastEpi qkv; qkv.mode = FEPI_QKV16; qkv.out16 = ctx->f_qk16; qkv.ldo = 2 * E; qkv.vt = ctx->f_vt16; qkv.vt_ld = N; qkv.v_col0 = 2 * E;
+        if (!fast_gemm(ctx->f_a16, E, (const __half *) L.c_attn.p_rm, E, N, 3 * E, E, qkv, n_sm, s)) return false;
+        if (!fast_attention(ctx->f_qk16, 2 * E, E, ctx->f_vt16, N, E, H, ctx->f_att16, s)) return false;
+        FastEpi res; res.mode = FEPI_RESID; res.out32 = ws.x; res.ldo = E;
+        if (!fast_gemm(ctx->f_att16, E, (const __half *) L.c_proj.p_rm, E, N, E, E, res, n_sm, s)) return false;
+        fast_layernorm(ws.x, N, E, L.ln_2_g, L.ln_2_b, ctx->f_a16, s);
+        FastEpi ge; ge.mode = FEPI_GELU16; ge.out16 = ctx->f_h16; ge.ldo = 4 * E; ge.gelu_tab = ctx->d_gelu_tab;
+        if (!fast_gemm(ctx->f_a16, E, (const __half *) L.fc.p_rm, E, N, 4 * E, E, ge, n_sm, s)) return false;
+        if (!fast_gemm(ctx->f_h16, 4 * E, (const __half *) L.proj.p_rm, 4 * E, N, E, 4 * E, res, n_sm, s)) return false;
+    }
+    fast_layernorm(ws.x, N, E, m.ln_f_g, m.ln_f_b, ctx->f_a16, s);
+    FastEpi st; st.mode = FEPI_F32; st.out32 = ws.logits; st.ldo = m.n_out_vocab;
+    if (!fast_gemm(ctx->f_a16, E, (const __half *) m.lm_head[nn - 1].p_rm, E, N, m.n_out_vocab, E, st, n_sm, s)) return false;
     ctx->last_logits = ws.logits;
     if (logits_host) {
         const size_t nb = (size_t) N * m.n_out_vocab * sizeof(float);
@@ -218,13 +294,18 @@ bool codec_decode(bark_context * ctx, const int32_t * codes, int T) {
     CodecModel & cm = ctx->codec;
     cudaStream_t s = ctx->stream;
     static const int ratios[4] = {8, 5, 4, 2};
+    for (size_t i = 0; i < (size_t) 8 * T; i++) if (codes[i] < 0 || codes[i] >= cm.n_bins) {
+        fprintf(stderr, "%s: code %d (codebook %zu, frame %zu) is outside the codebooks (%d bins)\n", __func__, codes[i], i / T, i % T, cm.n_bins); return false;
+    }
     const size_t need = (size_t) 10240 * T + 1024;             // largest activation: [64][160T] = [32][320T] = 10240*T floats
     if (need > ctx->c_cap) {
-        for (int i = 0; i < 3; i++) { if (ctx->c_buf[i]) BARK_CUDA_CHECK(cudaFree(ctx->c_buf[i])); BARK_CUDA_CHECK(cudaMalloc(&ctx->c_buf[i], need * sizeof(float))); }
-        if (ctx->c_gi) BARK_CUDA_CHECK(cudaFree(ctx->c_gi));
-        BARK_CUDA_CHECK(cudaMalloc(&ctx->c_gi, (size_t) T * 2048 * sizeof(float)));
-        if (ctx->d_codes) BARK_CUDA_CHECK(cudaFree(ctx->d_codes));
-        BARK_CUDA_CHECK(cudaMalloc(&ctx->d_codes, (size_t) 8 * T * sizeof(int32_t)));
+        // out of memory here is recoverable (a very long clip): report it and return false like the reference's failed encodec_eval
+        auto grow = [&](void ** p, size_t bytes) { if (*p) { cudaFree(*p); *p = nullptr; } return cudaMalloc(p, bytes) == cudaSuccess; };
+        ctx->c_cap = 0;
+        bool ok = true;
+        for (int i = 0; i < 3; i++) ok = ok && grow((void **) &ctx->c_buf[i], need * sizeof(float));
+        ok = ok && grow((void **) &ctx->c_gi, (size_t) T * 2048 * sizeof(float)) && grow((void **) &ctx->d_codes, (size_t) 8 * T * sizeof(int32_t));
+        if (!ok) { (void) cudaGetLastError(); fprintf(stderr, "%s: out of device memory for a %d-frame clip\n", __func__, T); return false; }
         if (!ctx->c_hbuf) { ctx->c_hbuf = (float *) ctx_alloc(ctx, 2 * 512 * sizeof(float)); ctx->c_counter = (unsigned *) ctx_alloc(ctx, sizeof(unsigned)); }
         ctx->c_cap = need;
     }

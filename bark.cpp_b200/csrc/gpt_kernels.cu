@@ -13,7 +13,7 @@
 
 namespace bark {
 
-unsigned long long g_kernel_launches = 0;
+std::atomic<unsigned long long> g_kernel_launches{0};
 
 // ------------------------------------------------------------------------------------------------
 // weight re-layout: row-major [n_out][K] -> lane-interleaved [n_out][Kp]

@@ -34,7 +34,7 @@ void q4_split(const void * raw_blocks, size_t n_blocks, void * qs, void * scales
 void q4_set_scratch(void * q8, void * q8_scales);      // int8 [rows][K] + f32 [rows][K/32] for the activation operand, owned by the context
 void q4_matmul(const DMat & W, const void * act_f32, int ld_act, int rows, const MatmulEpilogue & ep, cudaStream_t s);
 
-// ---- experimental: q4_1 / q5_0 / q5_1 / q8_0 weights (qx_kernels.cu; BARK_B200_EXPERIMENTAL_QUANTS=1) -----------------------------
+// ---- q4_1 / q5_0 / q5_1 / q8_0 weights (qx_kernels.cu) ---------------------------------------------------------------------------
 bool   qx_supported(WType t);
 size_t qx_block_bytes(WType t);
 void   qx_split(const void * raw_blocks, size_t n_blocks, WType t, void * qs, void * qh, void * d, void * m, cudaStream_t s);
@@ -48,7 +48,20 @@ void lane_gemm_tiled(const DMat & W, const void * act, int act_gs, int rows, con
 void attention_tiled_scores(const float * Q, const float * Kc, int N, int n_kv, int n_past, int E, int H, float scale, bool causal, float * scores, cudaStream_t s);
 void attention_tiled_pv(const float * scores, const float * Vc, int N, int n_kv, int E, int H, void * act, WType wt, int Kp, cudaStream_t s);
 
+// ---- fast mode (fast_kernels.cu, BARK_B200_MODE=fast): tcgen05 GEMM + flash-style attention for the dense passes -------------------
+enum { FEPI_F32 = 0, FEPI_RESID = 1, FEPI_GELU16 = 2, FEPI_F16 = 3, FEPI_QKV16 = 4 };
+struct FastEpi {
+    int mode = FEPI_F32;
+    float * out32 = nullptr; __half * out16 = nullptr; int ldo = 0;      // row-major targets
+    __half * vt = nullptr; int vt_ld = 0, v_col0 = 0;                    // QKV16: columns >= v_col0 are written transposed, vt[(n - v_col0) * vt_ld + m]
+    const __half * gelu_tab = nullptr;
+};
+bool fast_gemm(const __half * A, int lda, const __half * W, int ldw, int M, int N, int K, const FastEpi & ep, int n_sm, cudaStream_t s);
+bool fast_attention(const __half * qk, int ldq, int k_col0, const __half * vt, int n, int E, int H, __half * out, cudaStream_t s);
+void fast_layernorm(const float * x, int rows, int E, const float * g, const float * b, __half * out, cudaStream_t s);
+
 // ---- persistent decode step (decode_kernels.cu) -----------------------------------------------------------------
+constexpr int kDecodeReplicas = 8;        // copies of each all-to-all exchange vector (gx, gq, gatt, gff): CTA c reads copy c % 8
 struct DecodePhase { const void * w; int n_out, row_bytes, K, pad; };            // one streamed matrix: LI rows
 struct DecodeLayerVec { const float * ln_1_g, * ln_1_b, * ln_2_g, * ln_2_b; };
 struct DecodeArgs {

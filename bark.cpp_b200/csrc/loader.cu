@@ -84,13 +84,11 @@ bool load_gpt(bark_context * ctx, std::ifstream & f, GPTModel & m, const char * 
                __func__, what, m.n_layer, m.n_head, m.n_embd, m.block_size, m.bias, m.n_in_vocab, m.n_out_vocab, m.n_lm_heads, m.n_wtes, m.ftype);
     m.ftype %= 1000;                                                          // GGML_QNT_VERSION_FACTOR, bark.cpp:727
     // enum ggml_ftype -> enum ggml_type (ggml.c ggml_ftype_to_ggml_type): 0 f32, 1 f16, 2 q4_0 coincide; q4_1 3 -> 3, q8_0 7 -> 8, q5_0 8 -> 6, q5_1 9 -> 7
-    const bool experimental = [] { const char * e = getenv("BARK_B200_EXPERIMENTAL_QUANTS"); return e && !strcmp(e, "1"); }();
     int wt = -1;
     switch (m.ftype) { case 0: wt = W_F32; break; case 1: wt = W_F16; break; case 2: wt = W_Q4_0; break;
                        case 3: wt = W_Q4_1; break; case 7: wt = W_Q8_0; break; case 8: wt = W_Q5_0; break; case 9: wt = W_Q5_1; break; default: break; }
-    if (wt < 0 || (qx_supported((WType) wt) && !experimental)) {
-        fprintf(stderr, "%s: unsupported weight type (ftype %d) in %s model: this build reads f32, f16 and q4_0 GPT weights%s\n", __func__, m.ftype, what,
-                wt >= 0 ? " (q4_1 / q5_0 / q5_1 / q8_0 kernels exist but are experimental: BARK_B200_EXPERIMENTAL_QUANTS=1)" : "");
+    if (wt < 0) {
+        fprintf(stderr, "%s: unsupported weight type (ftype %d) in %s model: this build reads f32, f16, q4_0, q4_1, q5_0, q5_1 and q8_0 GPT weights\n", __func__, m.ftype, what);
         return false;
     }
     m.wtype = (WType) wt;
@@ -173,7 +171,8 @@ bool load_gpt(bark_context * ctx, std::ifstream & f, GPTModel & m, const char * 
                 permute_to_gm(raw, d.p_gm, d.n_out, d.o_pad, d.K, m.wtype, ctx->stream);
             }
             BARK_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-            BARK_CUDA_CHECK(cudaFree(raw));
+            if (ctx->fast_mode && !causal && m.wtype == W_F16) { d.p_rm = raw; ctx->device_allocs.push_back(raw); }   // fast mode: the tensor cores read the file's own row-major layout
+            else BARK_CUDA_CHECK(cudaFree(raw));
         } else {
             void * raw = upload_raw(ctx, f, bytes, host, true);
             if (!raw) return false;

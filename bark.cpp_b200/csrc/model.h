@@ -16,6 +16,7 @@ struct DMat {                 // 2-D weight [n_out][K] in LI layout (f32 / f16) 
     void * scales = nullptr;        // quantised: f16 block scales [n_out][K/32]; p then holds the 16-byte nibble words (32 B for q8_0) [n_out][K/32]
     void * mins = nullptr, * qh = nullptr;   // experimental types: f16 block minima (q4_1, q5_1), fifth bits (q5_0, q5_1)
     void * p_gm = nullptr; int o_pad = 0;   // second copy in the group-major layout (common.cuh) for the tiled GEMM; rows padded to o_pad
+    void * p_rm = nullptr;                  // fast mode only: the file's row-major [n_out][K] f16 matrix = K-major tcgen05 operand (fast_kernels.cu)
     WType type = W_F16;
 };
 
@@ -36,6 +37,7 @@ struct GPTModel {
     std::vector<GPTLayer> layers;
     float * mem_k = nullptr, * mem_v = nullptr;   // [L][block_size][E] f32 (bark.cpp:980-981); null for the fine model
     // persistent decode step (decode_kernels.cu): phase table + cross-CTA exchange buffers, built once at load
+    bool decode_ok = false;           // the model fits the persistent kernel's fixed capacities (build_decode_tables); otherwise per-op stepping
     void * d_phases = nullptr, * d_layer_vecs = nullptr;
     unsigned long long * gx = nullptr, * gq = nullptr, * gk = nullptr, * gv = nullptr, * gatt = nullptr, * gff = nullptr, * gscores = nullptr;
     float * glogits = nullptr;

@@ -5,19 +5,21 @@
 #include "common.cuh"
 
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
 namespace bark {
 
-unsigned long long g_h2d_bytes = 0, g_d2h_bytes = 0;
+std::atomic<unsigned long long> g_h2d_bytes{0}, g_d2h_bytes{0};
 bool g_prof_on = false;
-double g_next_bytes = 0.0, g_next_flops = 0.0;
+thread_local double g_next_bytes = 0.0, g_next_flops = 0.0;
 
 namespace {
 struct Rec { const char * name; cudaEvent_t a, b; double bytes, flops; };
 std::vector<Rec> g_recs;
 std::vector<cudaEvent_t> g_pool;
+std::mutex g_prof_mutex;                           // profiling is a single-context measurement tool; the lock only keeps the lists consistent
 cudaEvent_t get_event() {
     if (!g_pool.empty()) { cudaEvent_t e = g_pool.back(); g_pool.pop_back(); return e; }
     cudaEvent_t e; BARK_CUDA_CHECK(cudaEventCreate(&e)); return e;
@@ -25,11 +27,12 @@ cudaEvent_t get_event() {
 }  // namespace
 
 void prof_begin(const char * name, cudaStream_t s, double bytes, double flops) {
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
     Rec r{name, get_event(), get_event(), bytes, flops};
     BARK_CUDA_CHECK(cudaEventRecord(r.a, s));
     g_recs.push_back(r);
 }
-void prof_end(cudaStream_t s) { BARK_CUDA_CHECK(cudaEventRecord(g_recs.back().b, s)); }
+void prof_end(cudaStream_t s) { std::lock_guard<std::mutex> lock(g_prof_mutex); BARK_CUDA_CHECK(cudaEventRecord(g_recs.back().b, s)); }
 
 }  // namespace bark
 
@@ -65,7 +68,7 @@ extern "C" int bark_b200_profile_report(char * buf, int cap) {
 }
 
 extern "C" void bark_b200_io_counters(unsigned long long * h2d, unsigned long long * d2h, int reset) {
-    if (h2d) *h2d = g_h2d_bytes;
-    if (d2h) *d2h = g_d2h_bytes;
-    if (reset) g_h2d_bytes = g_d2h_bytes = 0;
+    if (h2d) *h2d = g_h2d_bytes.load();
+    if (d2h) *d2h = g_d2h_bytes.load();
+    if (reset) { g_h2d_bytes = 0; g_d2h_bytes = 0; }
 }

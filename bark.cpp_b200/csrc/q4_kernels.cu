@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256) q4_matmul_kernel(const uint4 * __restrict
     }
 }
 
-int8_t * g_q8 = nullptr; float * g_q8d = nullptr;
+thread_local int8_t * g_q8 = nullptr; thread_local float * g_q8d = nullptr;   // per host thread: one thread drives one context
 
 }  // namespace
 

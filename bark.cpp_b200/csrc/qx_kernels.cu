@@ -1,4 +1,4 @@
-// EXPERIMENTAL (BARK_B200_EXPERIMENTAL_QUANTS=1 at load; not yet run on a B200): q4_1, q5_0, q5_1 and q8_0 GPT weights — the other
+// q4_1, q5_0, q5_1 and q8_0 GPT weights (validated bit-exact against the oracle on a B200 in round 2) — the other
 // types the reference's `quantize` tool writes.  Same scheme as q4_kernels.cu (eight lanes own the eight float accumulators of one
 // output, one dp4a + one fma per 32-element block, hsum_float_8 as three xor-shuffles), with the per-type details of the pinned AVX2
 // build (ggml-quants.c): q5 codes take their fifth bit from qh, q4_1 / q5_1 add `m_w * s_a` per block in ONE scalar fused chain
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(256) qx_matmul_kernel(const unsigned char * __
     }
 }
 
-int8_t * g_qx_q8 = nullptr; float * g_qx_d = nullptr, * g_qx_s = nullptr;
+thread_local int8_t * g_qx_q8 = nullptr; thread_local float * g_qx_d = nullptr, * g_qx_s = nullptr;
 
 }  // namespace
 

@@ -129,8 +129,8 @@ __global__ void __launch_bounds__(kSampleThreads) sample_rows_kernel(const float
 void sample_rows(const float * logits, int ld, int n, int rows, float temp, const double * d_u, int32_t * d_out_tok, int tok_add, int32_t * d_feed,
                  float * d_eos_p, int32_t * d_flags, int force_flag, cudaStream_t s) {
     const size_t smem = ((size_t) n * sizeof(float) + 15) & ~(size_t) 15;
-    static bool configured = false;
-    if (!configured) { BARK_CUDA_CHECK(cudaFuncSetAttribute(sample_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); configured = true; }
+    static std::atomic<unsigned long long> configured{0};
+    if (first_use_on_this_device(configured)) BARK_CUDA_CHECK(cudaFuncSetAttribute(sample_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     g_next_bytes = (double) rows * n * 4.0;
     BARK_LAUNCH(sample_rows_kernel, rows, kSampleThreads, smem, s, logits, ld, n, rows, temp, d_u, d_out_tok, tok_add, d_feed, d_eos_p, d_flags, force_flag);
 }

@@ -32,8 +32,16 @@ import numpy as np  # noqa: E402
 
 import __graft_entry__ as graft  # noqa: E402
 
-METRIC = "audio sec/sec (inverse RTF), bark-small f16, batch 1 per GPU, semantic->coarse->fine->encodec"
 UNIT = "audio_s/s"
+# --config: which BASELINE.json config the line measures (metric text and workload name follow it)
+BENCH_CONFIGS = {
+    "small":      dict(dims="small", ftype="f16", quant=None,   label="bark-small f16",                          baseline="BASELINE configs[1]"),
+    "large":      dict(dims="large", ftype="f16", quant=None,   label="bark-large f16",                          baseline="BASELINE configs[2] (one prompt per GPU)"),
+    "small_q4_0": dict(dims="small", ftype="f16", quant="q4_0", label="bark-small q4_0 GPT weights + f16 codec", baseline="BASELINE configs[3]"),
+    "tiny":       dict(dims="tiny",  ftype="f16", quant=None,   label="tiny test config f16",                    baseline="test plumbing only"),
+}
+def metric_name(cfg):
+    return f"audio sec/sec (inverse RTF), {BENCH_CONFIGS[cfg]['label']}, batch 1 per GPU, semantic->coarse->fine->encodec"
 PROMPT = "hello world"
 N_STEPS_TEXT = 138
 SAMPLE_RATE = 24000
@@ -63,16 +71,28 @@ BENCH_CONFIG = os.environ.get("BARK_B200_BENCH_CONFIG", "small")
 
 
 def weights_path(config=None, ftype="f16", seed=1234):
+    """Synthetic ggml_weights.bin of a bench config (written once per box).  Quantised configs are made from the f16 file by the
+    library's own bark_model_quantize, which is byte-identical to the reference tool (tests/test_quantize.py)."""
     config = config or BENCH_CONFIG
+    spec = BENCH_CONFIGS.get(config, dict(dims=config, ftype=ftype, quant=None))
     import importlib
-    graft.load_package()
+    pkg = graft.load_package()
     weights = importlib.import_module("bark_cpp_b200.weights")
     os.makedirs(FIXTURE_DIR, exist_ok=True)
-    path = os.path.join(FIXTURE_DIR, f"{config}_{ftype}_{seed}.bin")
+    path = os.path.join(FIXTURE_DIR, f"{spec['dims']}_{spec['ftype']}_{seed}.bin")
     if not os.path.exists(path):
         tmp = path + f".tmp{os.getpid()}"
-        weights.write_weights(tmp, weights.CONFIGS[config](weights.F16 if ftype == "f16" else weights.F32), seed)
+        weights.write_weights(tmp, weights.CONFIGS[spec["dims"]](weights.F16 if spec["ftype"] == "f16" else weights.F32), seed)
         os.replace(tmp, path)
+    if spec.get("quant"):
+        qpath = os.path.join(FIXTURE_DIR, f"{spec['dims']}_{spec['quant']}_{seed}.bin")
+        if not os.path.exists(qpath):
+            tmp = qpath + f".tmp{os.getpid()}"
+            ftype_id = {"q4_0": 2, "q4_1": 3, "q5_0": 8, "q5_1": 9, "q8_0": 7}[spec["quant"]]      # enum ggml_ftype (include/ggml.h)
+            if not pkg.lib().bark_model_quantize(os.fsencode(path), os.fsencode(tmp), ftype_id):
+                raise RuntimeError("bark_model_quantize failed")
+            os.replace(tmp, qpath)
+        path = qpath
     return path
 
 
@@ -115,6 +135,29 @@ def dist_env():
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     return rank, world, local
+
+
+def pin_to_gpu_numa(device):
+    """Bind this process to the CPUs local to its GPU (sysfs local_cpulist of the GPU's PCI function).  At N = 8 each rank issues
+    ~3 k launches per clip; ranks scheduled on the far socket paid ~4 % (SCALE_r01).  Returns the CPU list string or None."""
+    try:
+        bus = subprocess.run(["nvidia-smi", f"--id={device}", "--query-gpu=pci.bus_id", "--format=csv,noheader"], capture_output=True, text=True, timeout=20).stdout.strip()
+        if not bus:
+            return None
+        dom, rest = bus.split(":", 1)
+        sysfs = f"/sys/bus/pci/devices/{dom[-4:].lower()}:{rest.lower()}/local_cpulist"
+        cpus = set()
+        txt = open(sysfs).read().strip()
+        for part in txt.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return txt
+    except Exception:
+        pass
+    return None
 
 
 def rank_workload(rank):
@@ -160,6 +203,7 @@ def run_ours(args):
     if dist:
         dist.barrier()
     device = local if world > 1 else int(os.environ.get("BARK_B200_DEVICE", "0"))
+    pinned = pin_to_gpu_numa(device) if world > 1 else None
     wl = rank_workload(rank)
     b = pkg.Bark(path, seed=wl["seed"], n_steps_text_encoder=N_STEPS_TEXT, device=device)
     prompt = wl["prompt"]
@@ -199,46 +243,57 @@ def run_ours(args):
     audio_s_per_step = total_audio_samples / SAMPLE_RATE
     e2e_value = audio_s_per_step * args.steps / elapsed_max
 
-    # ---- per-kernel device time (CUDA events on the launching stream) for the roofline: one extra profiled step on rank 0
-    roofline, roofline_all, kernels, value = None, None, None, e2e_value
+    # ---- per-kernel device time (CUDA events on the launching stream) for the roofline: one extra profiled step on EVERY rank.
+    # The profiled step starts from the load-time RNG state (reseed), so rank 0's tokens are the ones the reference produces
+    # for (file, prompt, seed 0, 138 steps): the parity leg below compares them with the cpu_baseline run of the same clip.
+    pkg.profile_enable(True)
+    b.reseed(wl["seed"])
+    audio_prof = b.generate(prompt)
+    ours_tokens = dict(semantic=b.tokens(0).copy(), coarse=b.tokens(1).copy(), fine=b.tokens(2).copy(), audio=audio_prof)
+    rep = pkg.profile_report()
+    pkg.profile_enable(False)
+    tot_ms = sum(v["ms"] for v in rep.values()) or 1.0
+    # value = whole-job throughput with inputs resident: all ranks' audio / MAX over ranks of the summed device kernel time of one clip
+    dev_s_max, _ = reduce_over_ranks(dist, tot_ms * 1e-3, n_audio, "cuda")
+    value = audio_s_per_step / dev_s_max
+
+    roofline, roofline_all, kernels = None, None, None
     if rank == 0:
-        pkg.profile_enable(True)
-        b.generate(prompt)
-        rep = pkg.profile_report()
-        pkg.profile_enable(False)
         P = peaks()
-        tot_ms = sum(v["ms"] for v in rep.values()) or 1.0
         kernels = {k: dict(launches=v["launches"], ms=round(v["ms"], 3), share=round(v["ms"] / tot_ms, 4)) for k, v in sorted(rep.items(), key=lambda kv: -kv[1]["ms"])}
         def roof(name, v):
-            """achieved vs the measured peak of whichever roof is closer for this kernel (HBM bytes or dense flops)"""
+            """achieved vs the measured peak of the roof that bounds this kernel: dense passes (mat-mul / attention of the prefill and
+            fine passes) on the tensor roof by themselves, everything else on HBM bytes"""
             sec = v["ms"] * 1e-3
             gbs = v["bytes"] / sec / 1e9 if sec else 0.0
             tfs = v["flops"] / sec / 1e12 if sec else 0.0
             f_h, f_t = gbs / P["hbm_gbs"], tfs / P["tflops"]
             common = dict(kernel=name, launches=v["launches"], avg_launch_us=round(sec * 1e6 / max(v["launches"], 1), 2), share=round(v["ms"] / tot_ms, 4),
                           traffic=measured_traffic(name), algorithmic_bytes_per_launch=int(v["bytes"] / max(v["launches"], 1)), peak_source=P["source"])
-            ridge = P["tflops"] * 1e12 / (P["hbm_gbs"] * 1e9)                       # flop per byte where the two roofs meet
-            if v["bytes"] > 0 and (v["flops"] <= 0 or v["flops"] / v["bytes"] < ridge):   # the roof that bounds this kernel's arithmetic intensity
+            dense = any(t in name for t in ("gemm", "attn_", "flash", "umma"))
+            if v["bytes"] > 0 and not (dense and v["flops"] > 0):
                 return dict(bound="hbm", achieved=round(gbs, 1), peak=P["hbm_gbs"], unit="GB/s", frac=round(f_h, 4), **common)
             return dict(bound="tensor", achieved=round(tfs, 2), peak=P["tflops"], unit="TFLOP/s", frac=round(f_t, 4),
-                        note="parity path: f16 operands, fp32 FMA chains in the reference's lane order on CUDA cores; bf16 cuBLAS peak is the ceiling of the contraction without the bit-exactness constraint", **common)
+                        note="dense contraction against the measured bf16 tensor peak; in parity mode it runs as fp32 FMA chains in the reference's lane order on CUDA cores (ceiling ~74 TFLOP/s)", **common)
         ranked = sorted(rep.items(), key=lambda kv: -kv[1]["ms"])
         roofline = roof(*ranked[0])
-        roofline_all = [roof(n, v) for n, v in ranked[:6]]
-        # value = same metric with inputs resident: sum of device kernel time of the profiled step (no host sampling, no copies)
-        value = audio_s_per_step / world / (tot_ms * 1e-3) * world if tot_ms else e2e_value
+        roofline_all = [roof(n, v) for n, v in ranked[:8]]
 
     if rank != 0:
         b.close()
         if dist:
             dist.destroy_process_group()
         return
+    spec = BENCH_CONFIGS[BENCH_CONFIG]
     result = {
-        "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": metric_name(BENCH_CONFIG), "value": round(value, 4), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(elapsed_max / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f16 weights/operands, f32 accumulate (reference arithmetic)", "data": "synthetic (seeded random weights in ggml_weights.bin format, prompt 'hello world')",
-        "config": {"workload": "bark-small f16, batch=1 per GPU, n_steps_text_encoder=138 -> 2.76 s clip (BASELINE configs[1])", "parallelism": f"replica x{world} (one prompt per GPU, no collective)",
-                   "mode": "parity (token ids bit-identical to the CPU reference); coarse windows start from the cached canonical K/V rows (exact, DESIGN.md §6)", "l2": "inputs larger than L2: 0.84 GB of weights streamed per clip vs 126 MB L2; no flush needed"},
+        "dtype": ("q4_0 weights / q8_0 activation blocks, " if spec["quant"] else "f16 weights/operands, ") + "f32 accumulate (reference arithmetic)",
+        "data": "synthetic (seeded random weights in ggml_weights.bin format, prompt 'hello world')",
+        "config": {"workload": f"{spec['label']}, batch=1 per GPU, n_steps_text_encoder={N_STEPS_TEXT} -> {audio_s_per_step / world:.2f} s clip ({spec['baseline']})", "parallelism": f"replica x{world} (one prompt per GPU, no collective" + (f"; each rank pinned to its GPU's local CPUs, rank 0: {pinned}" if pinned else "") + ")",
+                   "mode": os.environ.get("BARK_B200_MODE", "parity") + " (parity = token ids bit-identical to the CPU reference; coarse windows start from the cached canonical K/V rows, exact, DESIGN.md §6)",
+                   "l2": "inputs larger than L2: the weights streamed per clip exceed the 126 MB L2 many times over; no flush needed"},
+        "value_note": "all ranks' audio / MAX over ranks of the summed CUDA-event kernel time of one clip (inputs resident, no host gaps)",
         "e2e": {"value": round(e2e_value, 4), "unit": UNIT, "h2d_bytes_per_step": int(h2d / args.steps), "d2h_bytes_per_step": int(d2h / args.steps),
                 "note": "wall clock around bark_generate_audio (C-ABI, host text in / host waveform out): prompt ids, uniforms and codes H2D, sampled tokens and waveform D2H inside the timed region"},
         "gpu_launches": int(launches),
@@ -246,14 +301,28 @@ def run_ours(args):
         "stages": {n: {"tokens_per_s": round(float(ns) / n_calls / (us / args.steps * 1e-6), 1) if us else None, "ms": round(us / args.steps / 1e3, 2)}
                    for n, ns, us in zip(("semantic", "coarse", "fine"), n_samples, stage_us)},
         "audio_seconds_per_step": round(audio_s_per_step, 4),
-        "roofline": roofline, "roofline_top6": roofline_all, "kernels": kernels,
+        "roofline": roofline, "roofline_top": roofline_all, "kernels": kernels,
     }
+    ok = True
     if world == 1 and not args.no_cpu_baseline:
-        result["cpu_baseline"] = cpu_baseline(path, budget_s=args.cpu_budget)
+        base, ref_out = cpu_baseline(path, budget_s=args.cpu_budget, want_outputs=True)
+        result["cpu_baseline"] = base
+        if ref_out is not None:
+            par = {k: bool(np.array_equal(ours_tokens[k], ref_out[k])) for k in ("semantic", "coarse", "fine")}
+            same_len = ours_tokens["audio"].shape == ref_out["audio"].shape
+            par["wav_rel"] = float(np.abs(ours_tokens["audio"] - ref_out["audio"]).max() / max(np.abs(ref_out["audio"]).max(), 1e-30)) if same_len else None
+            par["against"] = f"{base['kind']} CPU run of the same file / prompt / seed 0 / n_steps_text_encoder={N_STEPS_TEXT} inside this job"
+            fast = os.environ.get("BARK_B200_MODE", "parity") != "parity"
+            ok = fast or (par["semantic"] and par["coarse"] and par["fine"] and same_len and par["wav_rel"] < 1e-3)
+            par["ok"] = bool(ok)
+            result["parity"] = par
     b.close()
     if dist:
         dist.destroy_process_group()
     emit(result)
+    if not ok:
+        sys.stderr.write("bench.py: PARITY FAILURE against the CPU reference on the benchmarked clip\n")
+        sys.exit(3)
 
 
 def usable_cpus():
@@ -268,78 +337,100 @@ def usable_cpus():
     return n
 
 
-def cpu_baseline(path, budget_s=30.0, steps=1):
-    """The reference's CPU path on this box's host cores: oracle/_ref (the unmodified reference) when it travelled with the
-    snapshot, else the C oracle port.  Bounded sample: the clip is shortened (n_steps_text_encoder) until one run fits the budget."""
+REF_2GIB_NOTE = " (the unmodified reference cannot load this file: it is >= 2 GiB and bark.cpp:1150 keeps the codec offset in an int)"
+
+
+def ref_can_load(orc, path):
+    return orc.have_ref() and os.path.getsize(path) < 2 ** 31
+
+
+def best_threads(orc, path):
+    """ggml's thread pool spins on a barrier per graph node, so "all cores" is not its fastest setting on a big host:
+    try a few thread counts on a short clip and keep the best (reported as `cores`)."""
+    usable = usable_cpus()
+    cands = sorted({c for c in (4, 8, 16, 32, usable) if c <= usable})
+    best = None
+    for c in cands:                                          # ascending; stop as soon as more threads stop helping
+        r = orc.Ref(path, seed=0, n_steps=8)
+        t0 = time.perf_counter(); r.generate(PROMPT, n_threads=c); dt = time.perf_counter() - t0
+        r.close()
+        if best is not None and dt > best[1]:
+            break
+        best = (c, dt)
+    return best[0], cands
+
+
+def cpu_baseline(path, budget_s=30.0, steps=1, want_outputs=False):
+    """The reference's CPU path on this box's host cores, on the SAME clip the CUDA arm times (same file, prompt, seed,
+    n_steps_text_encoder): oracle/_ref (the unmodified reference) when it travelled with the snapshot, else the C oracle port
+    on a bounded sample.  One full clip is ~8 s at the best thread count on the GPU box's host."""
     orc = graft.load_oracle_bindings()
     cores = os.cpu_count() or 1
-    if orc.have_ref():
-        # ggml's thread pool spins on a barrier per graph node, so "all cores" is not its fastest setting on a big host:
-        # try a few thread counts on a short clip and keep the best (reported as `cores`).
-        usable = usable_cpus()
-        cands = sorted({c for c in (4, 8, 16, 32, usable) if c <= usable})
-        best = None
-        for c in cands:                                      # ascending; stop as soon as more threads stop helping
-            r = orc.Ref(path, seed=0, n_steps=8)
-            t0 = time.perf_counter(); r.generate(PROMPT, n_threads=c); dt = time.perf_counter() - t0
-            st = r.stats()
-            if best is not None and dt > best[1]:
-                break
-            best = (c, dt, st[4] * 1e-6)
-        threads, t_short, t_fine = best
-        # fine stage cost is fixed (6 passes over 1024 rows); semantic+coarse scale with the clip
-        per_tok = max((t_short - t_fine) / 8.0, 1e-4)
-        n = int(max(8, min(N_STEPS_TEXT, (budget_s - t_fine) / per_tok)))
-        r = orc.Ref(path, seed=0, n_steps=n)
+    if ref_can_load(orc, path):
+        threads, cands = best_threads(orc, path)
+        r = orc.Ref(path, seed=0, n_steps=N_STEPS_TEXT)
         t0 = time.perf_counter()
         for _ in range(steps):
             g = r.generate(PROMPT, n_threads=threads)
         dt = (time.perf_counter() - t0) / steps
         st = r.stats()
-        return {"value": round(g["audio"].size / SAMPLE_RATE / dt, 5), "unit": UNIT, "cores": threads, "host_cores": cores, "kind": "reference",
-                "sample": f"same weights/prompt/seed, n_steps_text_encoder={n} -> {g['audio'].size / SAMPLE_RATE:.2f} s clip, one bark_generate_audio at -t {threads} "
+        base = {"value": round(g["audio"].size / SAMPLE_RATE / dt, 5), "unit": UNIT, "cores": threads, "host_cores": cores, "kind": "reference",
+                "sample": f"same weights/prompt/seed, n_steps_text_encoder={N_STEPS_TEXT} -> {g['audio'].size / SAMPLE_RATE:.2f} s clip (the whole bench clip), one bark_generate_audio at -t {threads} "
                           f"(best of {cands} on a short clip): {dt:.2f} s (semantic {st[2] / 1e3:.0f} ms, coarse {st[3] / 1e3:.0f} ms, fine {st[4] / 1e3:.0f} ms)",
                 "build": r.build_info(), "seconds": round(dt, 3)}
+        return (base, g) if want_outputs else base
+    orc.build_oracle()
     o = orc.Oracle(path, seed=0, n_steps=4)
     t0 = time.perf_counter(); g = o.generate(PROMPT); dt = time.perf_counter() - t0
-    return {"value": round(g["audio"].size / SAMPLE_RATE / dt, 5), "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"C oracle (OpenMP), n_steps_text_encoder=4 -> {g['audio'].size / SAMPLE_RATE:.2f} s clip in {dt:.2f} s", "seconds": round(dt, 3)}
+    base = {"value": round(g["audio"].size / SAMPLE_RATE / dt, 5), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"C oracle (OpenMP), bounded sample n_steps_text_encoder=4 -> {g['audio'].size / SAMPLE_RATE:.2f} s clip in {dt:.2f} s" + REF_2GIB_NOTE * (os.path.getsize(path) >= 2 ** 31),
+            "seconds": round(dt, 3)}
+    return (base, None) if want_outputs else base
 
 
 def run_reference(args):
+    """The reference's own CPU implementation on the host cores, SAME config as the CUDA arm: same file, prompt, seed and
+    n_steps_text_encoder (one step = one whole clip, ~8 s on the GPU box's host)."""
     rank, world, _ = dist_env()
     if rank != 0:
         return
     path = weights_path()
-    per_step_budget = max(6.0, 200.0 / max(args.steps + args.warmup, 1))
-    # one calibration inside the first warm-up, then identical steps
-    base = cpu_baseline(path, budget_s=per_step_budget, steps=1)
     orc = graft.load_oracle_bindings()
-    cores = base.get("cores", os.cpu_count() or 1)
-    n = int(base["sample"].split("n_steps_text_encoder=")[1].split(" ")[0]) if "n_steps_text_encoder=" in base["sample"] else 8
     times, audio_s = [], None
-    if orc.have_ref():
-        r = orc.Ref(path, seed=0, n_steps=n)
-        for i in range(max(args.warmup - 1, 0) + args.steps):
+    spec = BENCH_CONFIGS[BENCH_CONFIG]
+    if ref_can_load(orc, path):
+        cores, cands = best_threads(orc, path)
+        r = orc.Ref(path, seed=0, n_steps=N_STEPS_TEXT)
+        st = None
+        for i in range(args.warmup + args.steps):
+            r.reseed(0)
             t0 = time.perf_counter(); g = r.generate(PROMPT, n_threads=cores); dt = time.perf_counter() - t0
-            if i >= max(args.warmup - 1, 0):
+            if i >= args.warmup:
                 times.append(dt)
             audio_s = g["audio"].size / SAMPLE_RATE
+            st = r.stats()
+        kind, n = "reference", N_STEPS_TEXT
+        sample = (f"same weights/prompt/seed as the CUDA arm, n_steps_text_encoder={n} -> {audio_s:.2f} s clip per step, -t {cores} (best of {cands} on a short clip); "
+                  f"last step: semantic {st[2] / 1e3:.0f} ms, coarse {st[3] / 1e3:.0f} ms, fine {st[4] / 1e3:.0f} ms")
+        build = r.build_info()
     else:
+        cores, n = os.cpu_count() or 1, 4
+        orc.build_oracle()
         o = orc.Oracle(path, seed=0, n_steps=n)
-        for i in range(max(args.warmup - 1, 0) + args.steps):
+        for i in range(args.warmup + args.steps):
             t0 = time.perf_counter(); g = o.generate(PROMPT); dt = time.perf_counter() - t0
-            if i >= max(args.warmup - 1, 0):
+            if i >= args.warmup:
                 times.append(dt)
             audio_s = g["audio"].size / SAMPLE_RATE
+        kind, sample, build = "port", f"C oracle (OpenMP), bounded sample n_steps_text_encoder={n} -> {audio_s:.2f} s clip per step" + REF_2GIB_NOTE * (os.path.getsize(path) >= 2 ** 31), "oracle/bark_oracle.c"
     total = sum(times)
     value = audio_s * len(times) / total
-    base.update(value=round(value, 5))
+    base = {"value": round(value, 5), "unit": UNIT, "cores": cores, "host_cores": os.cpu_count() or 1, "kind": kind, "sample": sample, "build": build, "seconds": round(total / len(times), 3)}
     emit({
-        "impl": "reference", "metric": METRIC, "value": round(value, 5), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "impl": "reference", "metric": metric_name(BENCH_CONFIG), "value": round(value, 5), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(total / len(times) * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f16 weights/operands, f32 accumulate", "data": "synthetic (same file as the CUDA arm)",
-        "config": {"workload": f"bark-{BENCH_CONFIG} f16, batch=1, bounded sample n_steps_text_encoder={n} ({audio_s:.2f} s clip) of BASELINE configs[1]", "parallelism": f"host CPU, {cores} threads"},
+        "dtype": "f16 weights/operands, f32 accumulate" if not spec["quant"] else "q4_0 weights / q8_0 activation blocks, f32 accumulate", "data": "synthetic (same file as the CUDA arm)",
+        "config": {"workload": f"{spec['label']}, batch=1, n_steps_text_encoder={n} -> {audio_s:.2f} s clip ({spec['baseline']})", "parallelism": f"host CPU, {cores} threads"},
         "cpu_baseline": base, "e2e": {"value": round(value, 5), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     })
 
@@ -365,7 +456,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=30.0)
+    ap.add_argument("--config", default=None, choices=sorted(BENCH_CONFIGS), help="which BASELINE config to measure (default: bark-small f16 = configs[1])")
     args = ap.parse_args()
+    global BENCH_CONFIG
+    if args.config:
+        BENCH_CONFIG = args.config
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)

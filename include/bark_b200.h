@@ -58,6 +58,16 @@ BARK_API void bark_b200_io_counters(unsigned long long * h2d_bytes, unsigned lon
  * stamping thread of CTA 0 per layer; rows 64 + cta: every CTA at layer 5; slot meaning in tools/decode_timing.py) */
 BARK_API int  bark_b200_decode_timing(struct bark_context * ctx, unsigned long long * out, int n);
 
+
+/* FAST MODE (BARK_B200_MODE=fast in the environment at load; opt-in, NOT bit-identical to the reference): the fine model's
+ * 1024-row passes (bark.cpp:1416-1584) run as tcgen05 tensor-core GEMMs + flash-style attention (csrc/fast_kernels.cu).
+ * The two kernel hooks below run on host buffers without a context, for the numerics tests:
+ *   bark_b200_fast_gemm ....... C[M][N] (f32) = A[M][K] (f16 bits) * W[N][K]^T (f16 bits), K % 64 == 0
+ *   bark_b200_fast_attention .. out[n][E] (f16 bits) = soft_max(Q K^T / 8) V per 64-wide head, non-causal, n % 256 == 0 */
+BARK_API int  bark_b200_fast_mode(struct bark_context * ctx);              /* 1 if this context runs the fast fine passes */
+BARK_API int  bark_b200_fast_gemm(const uint16_t * A, const uint16_t * W, float * C, int M, int N, int K);
+BARK_API int  bark_b200_fast_attention(const uint16_t * q, const uint16_t * k, const uint16_t * v, uint16_t * out, int n, int E, int H);
+
 #ifdef __cplusplus
 }
 #endif

@@ -2,7 +2,7 @@
 path at -t 4.  tests/golden/small_f32_n12.npz holds the reference's token ids and waveform for n_steps_text_encoder = 12 (a 15 s CPU
 run; made by tests/golden/make_golden_small.py; the 1.6 GB weight file comes from bark.cpp_b200/weights.py and is not committed).
 
-Both checks are slow (the weight file alone takes ~20 s to write) and are therefore opt-in: BARK_B200_SLOW_TESTS=1."""
+The CPU-oracle check takes 3 minutes and stays opt-in (BARK_B200_SLOW_TESTS=1); the CUDA check is part of the default `-m gpu` run."""
 import hashlib
 import os
 
@@ -44,7 +44,6 @@ def test_oracle_reproduces_the_reference_at_bark_small_f32(orc, weights_file):
     assert np.array_equal(bits(r["audio"]), bits(g["audio"]))
 
 
-@slow
 @pytest.mark.gpu
 def test_cuda_path_reproduces_the_reference_at_bark_small_f32(pkg, weights_file):
     g = golden()

@@ -282,10 +282,9 @@ def test_bark_large_widths(pkg, orc, weights_file):
         assert np.array_equal(bits(b.fine_eval(buf, 3)), bits(o.fine_eval(buf, 3)))      # one 1024-row pass (a whole generation costs the CPU oracle a minute)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("BARK_B200_TEST_EXPERIMENTAL") != "1", reason="opt-in: BARK_B200_TEST_EXPERIMENTAL=1 (code paths not yet validated on a B200)")
 @pytest.mark.parametrize("config,ftype", [("tiny", "f16"), ("mini", "f32"), ("mini", "f16")])
 def test_packed_fma_variants_are_bit_identical(pkg, orc, weights_file, monkeypatch, config, ftype):
-    """BARK_B200_FFMA2=1: the tiled mat-mul / scores / P.V kernels with the 64 FMAs of a chain step issued as 32 packed FFMA2
+    """BARK_B200_FFMA2 (default on; 0 = scalar FMA): the tiled mat-mul / scores / P.V kernels with the 64 FMAs of a chain step issued as 32 packed FFMA2
     (fma.rn.f32x2).  Per component the arithmetic is __fmaf_rn's, so prefill logits, fine passes and a whole generation must not
     move by a bit — against the default kernels and against the oracle."""
     path = weights_file(config, ftype)
@@ -311,13 +310,11 @@ def test_packed_fma_variants_are_bit_identical(pkg, orc, weights_file, monkeypat
     assert np.array_equal(bits(res["1"][2]), bits(o.fine_eval(buf, 5)))
 
 
-@pytest.mark.skipif(__import__("os").environ.get("BARK_B200_TEST_EXPERIMENTAL") != "1", reason="opt-in: BARK_B200_TEST_EXPERIMENTAL=1 (code paths not yet validated on a B200)")
 @pytest.mark.parametrize("qname,ftype_id", [("q4_1", 3), ("q5_0", 8), ("q5_1", 9), ("q8_0", 7)])
 @pytest.mark.parametrize("config,src_ftype,n_steps", [("tiny", "f16", 16), ("mini", "f32", 24)])
 def test_experimental_quant_types(pkg, orc, weights_file, tmp_path, monkeypatch, config, src_ftype, n_steps, qname, ftype_id):
-    """q4_1 / q5_0 / q5_1 / q8_0 GPT weights (qx_kernels.cu, loaded only with BARK_B200_EXPERIMENTAL_QUANTS=1) against the oracle,
+    """q4_1 / q5_0 / q5_1 / q8_0 GPT weights (qx_kernels.cu) against the oracle,
     whose arithmetic for these types is pinned bit-exactly against the unmodified reference (tests/test_quantize.py)."""
-    monkeypatch.setenv("BARK_B200_EXPERIMENTAL_QUANTS", "1")
     src = weights_file(config, src_ftype)
     path = str(tmp_path / f"{qname}.bin")
     assert pkg.lib().bark_model_quantize(src.encode(), path.encode(), ftype_id)
@@ -346,3 +343,54 @@ def test_experimental_quant_types(pkg, orc, weights_file, tmp_path, monkeypatch,
         assert np.array_equal(b.tokens(1), ref["coarse"])
         assert np.array_equal(b.tokens(2), ref["fine"])
         assert wav_rel(audio, ref["audio"]) < WAV_RTOL
+
+
+def _generate_in_thread(pkg, path, device, seed, prompt, out, key):
+    try:
+        with pkg.Bark(path, seed=seed, n_steps_text_encoder=20, device=device) as b:
+            audio = b.generate(prompt)
+            out[key] = (b.tokens(0).copy(), b.tokens(1).copy(), b.tokens(2).copy(), audio)
+    except Exception as e:                                         # surfaces in the asserting thread
+        out[key] = e
+
+
+@pytest.mark.parametrize("two_devices", [False, True])
+def test_one_host_thread_per_context_in_one_process(pkg, weights_file, two_devices):
+    """SURVEY §5 / bark.h threading contract as this library states it: one host thread per context, several
+    contexts per process — on one GPU, and on two GPUs (kernel attributes are configured per device, launch annotations are
+    thread-local, counters atomic).  Each thread's tokens and waveform equal the single-threaded run of the same (seed, prompt)."""
+    import threading
+    from conftest import cuda_device_count
+    if two_devices and cuda_device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    path = weights_file("mini", "f16")
+    jobs = [(0, 3, "hello world"), (1 if two_devices else 0, 4, "The quick brown fox")]
+    ref = {}
+    for i, (dev, seed, prompt) in enumerate(jobs):
+        _generate_in_thread(pkg, path, dev, seed, prompt, ref, i)
+        assert not isinstance(ref[i], Exception), ref[i]
+    got = {}
+    threads = [threading.Thread(target=_generate_in_thread, args=(pkg, path, dev, seed, prompt, got, i)) for i, (dev, seed, prompt) in enumerate(jobs)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(300)
+    for i in range(len(jobs)):
+        assert not isinstance(got[i], Exception), got[i]
+        for a, c in zip(ref[i][:3], got[i][:3]):
+            assert np.array_equal(a, c)
+        assert np.array_equal(bits(ref[i][3]), bits(got[i][3]))
+
+
+def test_exchange_epochs_survive_the_32_bit_wrap(pkg, weights_file, monkeypatch):
+    """The decode kernel's tagged exchanges use a 32-bit epoch that advances 6 * n_layer per token; just before it would wrap the host
+    drains the stream, clears the exchange words and restarts at 0 (gpt_forward.cu decode_step).  Start 40 tokens before the wrap."""
+    path = weights_file("tiny", "f16")
+    with pkg.Bark(path, seed=0, n_steps_text_encoder=20) as b:
+        a0 = b.generate("hello world"); t0 = [b.tokens(i).copy() for i in range(3)]
+    monkeypatch.setenv("BARK_B200_TAG_BASE", str(2 ** 32 - 40 * 12))
+    with pkg.Bark(path, seed=0, n_steps_text_encoder=20) as b:
+        a1 = b.generate("hello world"); t1 = [b.tokens(i).copy() for i in range(3)]
+    for x, y in zip(t0, t1):
+        assert np.array_equal(x, y)
+    assert np.array_equal(bits(a0), bits(a1))
