@@ -49,6 +49,7 @@ EXPORTS = [
     "bark_b200_forward_coarse_encoder", "bark_b200_forward_fine_encoder", "bark_b200_get_tokens", "bark_b200_set_tokens",
     "bark_b200_get_stats", "bark_b200_get_hparams", "bark_b200_kernel_launches", "bark_b200_layernorm_fallbacks",
     "bark_b200_profile_enable", "bark_b200_profile_report", "bark_b200_io_counters", "bark_b200_decode_timing",
+    "bark_b200_shard_init", "bark_b200_shard_connect", "bark_b200_shard_nvlink_bytes",
     "bark_b200_fast_mode", "bark_b200_fast_gemm", "bark_b200_fast_attention",
     "ggml_time_init", "ggml_time_us", "ggml_time_ms", "ggml_init", "ggml_free",
 ]
@@ -113,6 +114,12 @@ def lib() -> C.CDLL:
     L.bark_b200_io_counters.argtypes = [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), C.c_int]
     L.bark_b200_decode_timing.restype = C.c_int
     L.bark_b200_decode_timing.argtypes = [vp, C.c_void_p, C.c_int]
+    L.bark_b200_shard_init.restype = C.c_int
+    L.bark_b200_shard_init.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.bark_b200_shard_connect.restype = C.c_int
+    L.bark_b200_shard_connect.argtypes = [vp, vp]
+    L.bark_b200_shard_nvlink_bytes.restype = C.c_ulonglong
+    L.bark_b200_shard_nvlink_bytes.argtypes = [vp, C.c_int]
     L.bark_b200_fast_mode.restype = C.c_int
     L.bark_b200_fast_mode.argtypes = [vp]
     L.bark_b200_fast_gemm.restype = C.c_int
@@ -254,6 +261,22 @@ class Bark:
         pm = np.zeros(9, np.int64)
         lib().bark_b200_get_stats(self.ctx, C.byref(s), _p(pm))
         return s, pm.reshape(3, 3)
+
+    def shard_init(self, rank: int, world: int) -> bytes:
+        """Row-sharded fine stage, step 1: returns this rank's 64-byte CUDA IPC handle."""
+        h = C.create_string_buffer(64)
+        if not lib().bark_b200_shard_init(self.ctx, rank, world, C.cast(h, C.c_void_p)):
+            raise RuntimeError("bark_b200_shard_init failed")
+        return h.raw
+
+    def shard_connect(self, all_handles: bytes):
+        """step 2: all ranks' handles, rank order (world * 64 bytes)."""
+        buf = C.create_string_buffer(all_handles, len(all_handles))
+        if not lib().bark_b200_shard_connect(self.ctx, C.cast(buf, C.c_void_p)):
+            raise RuntimeError("bark_b200_shard_connect failed")
+
+    def shard_nvlink_bytes(self, reset: bool = False) -> int:
+        return int(lib().bark_b200_shard_nvlink_bytes(self.ctx, int(reset)))
 
     @property
     def fast_mode(self) -> bool:

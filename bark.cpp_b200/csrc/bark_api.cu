@@ -384,10 +384,14 @@ bool run_fine(bark_context * ctx) {
         for (int c = 0; c < 8; c++) for (int j = 0; j < 1024; j++) buf[(size_t) c * 1024 + j] = arr[(size_t)(start + j) * 8 + c];
         for (int nn = n_coarse; nn < n_cb; nn++) {
             if (P.progress_callback) P.progress_callback(ctx, FINE, 100 * (n * (n_cb - n_coarse) + (nn - n_coarse + 1)) / (n_loops * (n_cb - n_coarse)), P.progress_callback_user_data);
+            if (ctx->shard.on) {                              // rows of the window split over the GPUs of the job (shard.cu)
+                if (!fine_eval_shard(ctx, buf.data(), nn) || !sample_shard(ctx, cb_size, P.fine_temp, sampled.data())) { fprintf(stderr, "%s: Could not generate token\n", __func__); return false; }
+            } else {
             if (!fine_eval(ctx, buf.data(), nn, dev ? nullptr : logits.data())) { fprintf(stderr, "%s: Could not generate token\n", __func__); return false; }
             if (dev && !sample_device(ctx, m, ctx->last_logits, m.n_out_vocab, cb_size, 1024, P.fine_temp, sampled.data(), nullptr)) return false;
+            }
             for (int i = 0; i < 1024; i++) {
-                const int32_t next = dev ? sampled[(size_t) i] : sample_token(ctx, m, logits.data() + (size_t) i * m.n_out_vocab, cb_size, P.fine_temp, nullptr);
+                const int32_t next = (dev || ctx->shard.on) ? sampled[(size_t) i] : sample_token(ctx, m, logits.data() + (size_t) i * m.n_out_vocab, cb_size, P.fine_temp, nullptr);
                 // For clips <= 1024 frames (rel == 0) this is the reference's write (bark.cpp:2037).  For longer clips the
                 // reference indexes buf[nn*1024 + rel + i] and runs off the buffer (SURVEY finding 5); there we keep the
                 // original Bark semantics: every row is sampled (same RNG consumption) and rows >= rel are written in place.
@@ -590,6 +594,8 @@ extern "C" void bark_free(struct bark_context * ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (void * p : ctx->device_allocs) cudaFree(p);
+    for (int p = 0; p < ctx->shard.world; p++) if (p != ctx->shard.rank && ctx->shard.peer[p]) cudaIpcCloseMemHandle(ctx->shard.peer[p]);
+    if (ctx->shard.local) cudaFree(ctx->shard.local);
     for (int i = 0; i < 3; i++) if (ctx->c_buf[i]) cudaFree(ctx->c_buf[i]);
     if (ctx->c_gi) cudaFree(ctx->c_gi);
     if (ctx->d_codes) cudaFree(ctx->d_codes);

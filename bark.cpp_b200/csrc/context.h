@@ -9,6 +9,14 @@
 #include <string>
 #include <vector>
 
+// row-sharded fine stage (shard.cu): this rank's IPC-exported buffer and the peers' mapped ones
+struct ShardState {
+    bool on = false; int rank = 0, world = 1;
+    unsigned char * local = nullptr, * peer[8] = {nullptr};
+    unsigned epoch = 0; unsigned * d_err = nullptr;
+    unsigned long long nvlink_bytes = 0;             // bytes this rank stored into peer memory (K / V rows, sampled ids)
+};
+
 struct bark_context {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -30,6 +38,8 @@ struct bark_context {
     // BARK_B200_MODE=fast: the fine model's passes run on the tensor cores (fast_kernels.cu); not bit-identical to the reference
     bool fast_mode = false;
     __half * f_a16 = nullptr, * f_h16 = nullptr, * f_qk16 = nullptr, * f_vt16 = nullptr, * f_att16 = nullptr;   // [1024][E], [1024][4E], [1024][2E], [E][1024], [1024][E]
+
+    ShardState shard;
 
     bark::Workspace ws;
     void * d_q8_sums = nullptr;                       // experimental q4_1 / q5_1: q8_1 block sums s = f16(d * sum(q))
@@ -76,6 +86,8 @@ bool gpt_eval(bark_context * ctx, GPTModel & m, const int32_t * tokens, int n, i
 void build_decode_tables(bark_context * ctx, GPTModel & m);
 // one non-causal pass of the fine model; mirrors bark_eval_fine_encoder_internal (bark.cpp:1907-1959)
 bool fine_eval(bark_context * ctx, const int32_t * in_buffer /*[8][1024]*/, int nn, float * logits_host /*[1024][n_out]*/);
+bool fine_eval_shard(bark_context * ctx, const int32_t * in_buffer, int nn);                          // this rank's rows of one pass (shard.cu)
+bool sample_shard(bark_context * ctx, int n, float temp, int32_t * out_all /*[1024]*/);
 bool fine_eval_fast(bark_context * ctx, const int32_t * in_buffer, int nn, float * logits_host);      // tensor-core variant (fast mode)
 // EnCodec decode; codes [8][T] on the host; result in ctx->audio
 bool codec_decode(bark_context * ctx, const int32_t * codes, int T);

@@ -347,7 +347,8 @@ __device__ __forceinline__ void row_dot(const unsigned char * row, int row_bytes
     for (int n = 0; n < NR; n++) out[n] = lane_tree_reduce(acc[n]);
 }
 
-constexpr int kMaxTasks = 6;        // (h, k) score tasks per warp: H * block_size / (n_cta * kWarps) <= 16 * 1024 / (132 * 16) < 8
+constexpr int kMaxTasks = 8;        // (h, k) score tasks per warp with their K rows prefetched: H * block_size / (n_score_cta * kWarps) = 12 * 1024 / (100 * 16) < 8 (bark-small);
+                                    // beyond that (bark-large past n_kv = 672) the remaining tasks run without the prefetch
 
 // Block-wide state of the phases, in static shared memory (a by-reference struct in local memory cost L1/L2 round trips on
 // the critical path: the 72 KB of per-thread stack frames do not fit the L1 left over next to 220 KB of shared memory).
@@ -513,6 +514,8 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
     const bool pv_cta = (int) blockIdx.x < H * parts;
     const int pv_h = blockIdx.x / parts, pv_c = blockIdx.x % parts;
     const int np = n_kv & ~31;
+    const unsigned score_cta0 = (gridDim.x >= (unsigned)(H * parts + 64)) ? (unsigned)(H * parts) : 0u;      // first CTA that takes score tasks
+    const bool score_cta = blockIdx.x >= score_cta0;
 
 #pragma unroll 1
     for (int il = 0; il < L; il++) {
@@ -538,10 +541,12 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
             if (np + pv_v < n_past) vl = __ldcg(Vc + (size_t)(np + pv_v) * E + pv_dd);          // one element of the leftover rows k = np + v
         }
 
-        // ---- P2: scores.  K rows of older positions are fetched before q arrives. ----
-        {
+        // ---- P2: scores.  K rows of older positions are fetched before q arrives.  The CTAs that own a soft_max tile (P3) take no
+        // score tasks when enough other CTAs exist: they are the critical path of the layer (they still have the whole of P3 to do
+        // once the scores exist), and the V prefetch above already keeps their load queues busy. ----
+        if (score_cta) {
             const float * Kc = A.mem_k + (size_t) il * ctx * E;
-            const int total = H * n_kv, gw = blockIdx.x * kWarps + warp, nw = gridDim.x * kWarps;
+            const int total = H * n_kv, gw = (int)(blockIdx.x - score_cta0) * kWarps + warp, nw = (int)(gridDim.x - score_cta0) * kWarps;
             float kf[kMaxTasks][DSTEPS];
 #pragma unroll
             for (int i = 0; i < kMaxTasks; i++) {

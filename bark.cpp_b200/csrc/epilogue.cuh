@@ -42,8 +42,8 @@ __device__ __forceinline__ void matmul_epilogue(const MatmulEpilogue & ep, int m
         case EPI_QKV: {
             const int E = ep.ldo;
             if (o < E)          ep.out[(size_t) m * E + o] = r;
-            else if (o < 2 * E) ep.k_out[(size_t) m * E + (o - E)] = r;
-            else                ep.v_out[(size_t) m * E + (o - 2 * E)] = r;
+            else if (o < 2 * E) { ep.k_out[(size_t) m * E + (o - E)] = r;     for (int p = 0; p < ep.n_peer; p++) ep.k_peer[p][(size_t) m * E + (o - E)] = r; }
+            else                { ep.v_out[(size_t) m * E + (o - 2 * E)] = r; for (int p = 0; p < ep.n_peer; p++) ep.v_peer[p][(size_t) m * E + (o - 2 * E)] = r; }
         } break;
     }
 }

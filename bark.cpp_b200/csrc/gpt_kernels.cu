@@ -85,12 +85,12 @@ __global__ void embed_causal_kernel(const void * __restrict__ wte, int wt, const
 // fine model (bark.cpp:1454-1472): tok_emb starts as a zeroed leaf, then += wte[c][ids[c][r]] for c = 0..nn
 struct FineTables { const void * wte[8]; };
 __global__ void embed_fine_kernel(FineTables tabs, int wt, const float * __restrict__ wpe, const int32_t * __restrict__ ids /*[8][1024]*/,
-                                  int nn, int E, float * __restrict__ x) {
-    const int r = blockIdx.x;
+                                  int nn, int E, float * __restrict__ x, int row0) {
+    const int r = row0 + blockIdx.x;                        // x holds rows [row0, row0 + gridDim.x) of the window (row-sharded passes: shard.cu)
     for (int i = threadIdx.x; i < E; i += blockDim.x) {
         float v = 0.0f;
         for (int c = 0; c <= nn; c++) v = __fadd_rn(v, wte_value(tabs.wte[c], wt, E, ids[c * 1024 + r], i));
-        x[(size_t) r * E + i] = __fadd_rn(v, wpe[(size_t) r * E + i]);
+        x[(size_t) blockIdx.x * E + i] = __fadd_rn(v, wpe[(size_t) r * E + i]);
     }
 }
 
@@ -98,10 +98,10 @@ void gpt_embed_causal(const GPTModel & m, const int32_t * d_tok, int N, int n_pa
     if (qx_supported(m.wtype)) { qx_embed_causal(m, d_tok, N, n_past, merge, x, s); return; }
     BARK_LAUNCH(embed_causal_kernel, N, 256, 0, s, m.wte[0], (int) m.wtype, m.wpe, d_tok, N, n_past, merge ? 1 : 0, m.n_embd, x);
 }
-void gpt_embed_fine(const GPTModel & m, const int32_t * d_ids, int nn, float * x, cudaStream_t s) {
+void gpt_embed_fine(const GPTModel & m, const int32_t * d_ids, int nn, float * x, cudaStream_t s, int row0, int rows) {
     if (qx_supported(m.wtype)) { qx_embed_fine(m, d_ids, nn, x, s); return; }
     FineTables t; for (int i = 0; i < 8; i++) t.wte[i] = m.wte[i];
-    BARK_LAUNCH(embed_fine_kernel, 1024, 256, 0, s, t, (int) m.wtype, m.wpe, d_ids, nn, m.n_embd, x);
+    BARK_LAUNCH(embed_fine_kernel, rows, 256, 0, s, t, (int) m.wtype, m.wpe, d_ids, nn, m.n_embd, x, row0);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -10,6 +10,9 @@ struct MatmulEpilogue {
     int mode = EPI_STORE;
     float * out = nullptr; int ldo = 0;              // STORE / RESID target ([m][ldo]); QKV: q rows with ldo = E
     float * k_out = nullptr, * v_out = nullptr;      // QKV: K/V rows (KV cache slot of the first new position, or the fine model's buffers)
+    // row-sharded fine pass (shard.cu): the same K/V rows are also stored into the other GPUs' buffers over NVLink (peer pointers),
+    // so the all-gather of K and V is the mat-mul's own epilogue
+    int n_peer = 0; float * k_peer[7] = {nullptr}, * v_peer[7] = {nullptr};
     void * act_out = nullptr; int act_wt = 0, act_Kp = 0;   // GELU_ACT: operand for the following mul_mat (act_Kp = its group stride)
     const __half * gelu_tab = nullptr;
 };
@@ -18,7 +21,7 @@ void permute_to_li(const void * src_rowmajor, void * dst_li, int n_out, int K, W
 void permute_to_gm(const void * src_rowmajor, void * dst_gm, int n_out, int o_pad, int K, WType t, cudaStream_t s);
 
 void gpt_embed_causal(const GPTModel & m, const int32_t * d_tok, int N, int n_past, bool merge, float * x, cudaStream_t s);
-void gpt_embed_fine(const GPTModel & m, const int32_t * d_ids, int nn, float * x, cudaStream_t s);
+void gpt_embed_fine(const GPTModel & m, const int32_t * d_ids, int nn, float * x, cudaStream_t s, int row0 = 0, int rows = 1024);   // rows [row0, row0 + rows) of the window
 
 // `Kp` of the activation operands below is the GROUP STRIDE of the group-major layout (elements), not a row length
 void layernorm_act(const float * x, int rows, int E, const float * g, const float * b, void * act, WType wt, int Kp,

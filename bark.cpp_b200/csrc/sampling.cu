@@ -20,10 +20,12 @@
 
 namespace bark {
 
-constexpr int kSampleThreads = 256;
+// 256 threads per row when many rows are sampled at once (fine passes: 1024 rows), 1024 threads for the single row of a decode
+// step (the exp / division / scan passes of a 10 048-wide semantic row are 4x shorter; the sequential sum is unchanged)
 
 // One CTA of 256 threads per row.  tok_add is added to the sampled index (coarse stage: offset of the codebook window in
 // the vocabulary); feed, when set, receives the token for the NEXT decode step to read (no host round trip).
+template <int kSampleThreads>
 __global__ void __launch_bounds__(kSampleThreads) sample_rows_kernel(const float * __restrict__ logits, int ld, int n, int rows, float temp, const double * __restrict__ u,
                                                                      int32_t * __restrict__ out_tok, int tok_add, int32_t * __restrict__ feed,
                                                                      float * __restrict__ eos_p, int32_t * __restrict__ flags, int force_flag) {
@@ -130,9 +132,13 @@ void sample_rows(const float * logits, int ld, int n, int rows, float temp, cons
                  float * d_eos_p, int32_t * d_flags, int force_flag, cudaStream_t s) {
     const size_t smem = ((size_t) n * sizeof(float) + 15) & ~(size_t) 15;
     static std::atomic<unsigned long long> configured{0};
-    if (first_use_on_this_device(configured)) BARK_CUDA_CHECK(cudaFuncSetAttribute(sample_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    if (first_use_on_this_device(configured)) {
+        BARK_CUDA_CHECK(cudaFuncSetAttribute(sample_rows_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        BARK_CUDA_CHECK(cudaFuncSetAttribute(sample_rows_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    }
     g_next_bytes = (double) rows * n * 4.0;
-    BARK_LAUNCH(sample_rows_kernel, rows, kSampleThreads, smem, s, logits, ld, n, rows, temp, d_u, d_out_tok, tok_add, d_feed, d_eos_p, d_flags, force_flag);
+    if (rows == 1) BARK_LAUNCH(sample_rows_kernel<1024>, rows, 1024, smem, s, logits, ld, n, rows, temp, d_u, d_out_tok, tok_add, d_feed, d_eos_p, d_flags, force_flag);
+    else           BARK_LAUNCH(sample_rows_kernel<256>, rows, 256, smem, s, logits, ld, n, rows, temp, d_u, d_out_tok, tok_add, d_feed, d_eos_p, d_flags, force_flag);
 }
 
 }  // namespace bark

@@ -38,6 +38,8 @@ BENCH_CONFIGS = {
     "small":      dict(dims="small", ftype="f16", quant=None,   label="bark-small f16",                          baseline="BASELINE configs[1]"),
     "large":      dict(dims="large", ftype="f16", quant=None,   label="bark-large f16",                          baseline="BASELINE configs[2] (one prompt per GPU)"),
     "small_q4_0": dict(dims="small", ftype="f16", quant="q4_0", label="bark-small q4_0 GPT weights + f16 codec", baseline="BASELINE configs[3]"),
+    "fine_only":  dict(dims="small", ftype="f16", quant=None,   label="fine encoder only, bark-small f16, 6144 sampled tokens (one 1024-frame window x 6 codebook passes), rows of the window sharded over the GPUs",
+                       baseline="BASELINE configs[4]"),
     "tiny":       dict(dims="tiny",  ftype="f16", quant=None,   label="tiny test config f16",                    baseline="test plumbing only"),
 }
 def metric_name(cfg):
@@ -317,11 +319,155 @@ def run_ours(args):
             par["ok"] = bool(ok)
             result["parity"] = par
     b.close()
+    if world == 1 and not args.no_fast and BENCH_CONFIGS[BENCH_CONFIG]["quant"] is None and os.environ.get("BARK_B200_MODE", "parity") == "parity":
+        result["fast_mode"] = fast_mode_leg(pkg, path, device, prompt, args, ours_tokens)
     if dist:
         dist.destroy_process_group()
     emit(result)
     if not ok:
         sys.stderr.write("bench.py: PARITY FAILURE against the CPU reference on the benchmarked clip\n")
+        sys.exit(3)
+
+
+def fast_mode_leg(pkg, path, device, prompt, args, parity_out):
+    """The same clip with BARK_B200_MODE=fast (fine passes on the tensor cores: tcgen05 GEMMs + flash-style attention,
+    csrc/fast_kernels.cu).  NOT the contract path: fine ids are not bit-identical; reported next to the parity numbers."""
+    os.environ["BARK_B200_MODE"] = "fast"
+    try:
+        b = pkg.Bark(path, seed=0, n_steps_text_encoder=N_STEPS_TEXT, device=device)
+        if not b.fast_mode:
+            b.close()
+            return {"available": False}
+        for _ in range(2):
+            b.generate(prompt)
+        t0 = time.perf_counter(); fine_us = 0
+        for _ in range(args.steps):
+            audio = b.generate(prompt)
+            fine_us += b.stats()[0].t_fine_us
+        dt = (time.perf_counter() - t0) / args.steps
+        pkg.profile_enable(True)
+        b.reseed(0)
+        audio = b.generate(prompt)
+        rep = pkg.profile_report()
+        pkg.profile_enable(False)
+        fine = b.tokens(2)
+        same_front = bool(np.array_equal(b.tokens(0), parity_out["semantic"]) and np.array_equal(b.tokens(1), parity_out["coarse"]))
+        P = peaks()
+        dense = {k: v for k, v in rep.items() if "umma" in k or "flash" in k}
+        d_ms = sum(v["ms"] for v in dense.values()); d_fl = sum(v["flops"] for v in dense.values())
+        out = {"available": True, "e2e": {"value": round(audio.size / SAMPLE_RATE / dt, 4), "unit": UNIT}, "ms_per_step": round(dt * 1e3, 3), "fine_stage_ms": round(fine_us / args.steps / 1e3, 3),
+               "fine_pass_ms": round(fine_us / args.steps / 1e3 / 6, 3),
+               "semantic_coarse_ids_identical_to_parity": same_front, "fine_ids_equal_to_parity": round(float((fine == parity_out["fine"]).mean()), 4) if fine.shape == parity_out["fine"].shape else None,
+               "wav_rel_vs_parity": round(float(np.abs(audio - parity_out["audio"]).max() / max(np.abs(parity_out["audio"]).max(), 1e-30)), 4) if audio.shape == parity_out["audio"].shape else None,
+               "tensor_kernels": {k: dict(launches=v["launches"], ms=round(v["ms"], 3), tflops=round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1) if v["ms"] else None) for k, v in dense.items()},
+               "roofline": {"bound": "tensor", "achieved": round(d_fl / (d_ms * 1e-3) / 1e12, 1) if d_ms else None, "peak": P["tflops"], "unit": "TFLOP/s",
+                            "frac": round(d_fl / (d_ms * 1e-3) / 1e12 / P["tflops"], 4) if d_ms else None, "kernels": "umma_gemm_kernel + flash_attn_kernel of one clip (CUDA events)", "peak_source": P["source"]},
+               "note": "opt-in BARK_B200_MODE=fast; validated by teacher forcing (tests/test_fast_mode.py), not bit-identical"}
+        b.close()
+        return out
+    finally:
+        os.environ.pop("BARK_B200_MODE", None)
+
+
+def run_fine_only(args):
+    """BASELINE configs[4]: the fine stage alone on a synthetic 1024-frame window (coarse codes uniform in [0, 1024)), STRONG scaling:
+    the 1024 rows of every pass are split over the N GPUs (csrc/shard.cu: K / V rows stored into the peers' buffers over NVLink from
+    the QKV mat-mul's epilogue, one flag barrier per layer, sampled ids published the same way).  Every rank must end with the fine
+    tokens of the unsharded run, bit for bit; the line says so (`parity`) and the run fails otherwise."""
+    rank, world, local = dist_env()
+    pkg = graft.load_package()
+    dist = None
+    import torch
+    if world > 1:
+        import torch.distributed as dist_mod
+        torch.cuda.set_device(local)
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist = dist_mod
+    if rank == 0:
+        path = weights_path()
+    if dist:
+        dist.barrier()
+    path = weights_path()
+    device = local if world > 1 else int(os.environ.get("BARK_B200_DEVICE", "0"))
+    pinned = pin_to_gpu_numa(device) if world > 1 else None
+    b = pkg.Bark(path, seed=0, n_steps_text_encoder=N_STEPS_TEXT, device=device)
+    coarse = np.random.default_rng(11).integers(0, 1024, (1024, 2)).astype(np.int32)
+
+    def one_pass():
+        b.reseed(0)
+        b.set_tokens(1, coarse)
+        b.forward(2)
+        return b.tokens(2).copy()
+
+    ref_tokens = one_pass()                                   # unsharded: the N = 1 answer, on every rank
+    if world > 1:
+        h = b.shard_init(rank, world)
+        t = torch.frombuffer(bytearray(h), dtype=torch.uint8).cuda()
+        allh = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(allh, t)
+        b.shard_connect(b"".join(bytes(x.cpu().numpy().tobytes()) for x in allh))
+        dist.barrier()
+    for _ in range(args.warmup):
+        tokens = one_pass()
+    sampler = ClockSampler(device)
+    launches0 = pkg.kernel_launches()
+    pkg.io_counters(reset=True)
+    b.shard_nvlink_bytes(reset=True)
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        tokens = one_pass()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    elapsed = time.perf_counter() - t0
+    clocks = sampler.stop()
+    launches = pkg.kernel_launches() - launches0
+    h2d, d2h = pkg.io_counters()
+    nvl = b.shard_nvlink_bytes()
+    same = bool(np.array_equal(tokens, ref_tokens))
+    elapsed_max, n_same = reduce_over_ranks(dist, elapsed, 1.0 if same else 0.0, "cuda")
+    # device-time figure: summed CUDA-event kernel time of one profiled window, MAX over ranks
+    pkg.profile_enable(True)
+    one_pass()
+    rep = pkg.profile_report()
+    pkg.profile_enable(False)
+    tot_ms = sum(v["ms"] for v in rep.values()) or 1.0
+    dev_s_max, _ = reduce_over_ranks(dist, tot_ms * 1e-3, 0, "cuda")
+    b.close()
+    if dist:
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    ok = n_same == world
+    P = peaks()
+    ranked = sorted(rep.items(), key=lambda kv: -kv[1]["ms"])
+    top, tv = ranked[0]
+    tfs = tv["flops"] / (tv["ms"] * 1e-3) / 1e12 if tv["ms"] else 0.0
+    e2e = 6144 * args.steps / elapsed_max
+    emit({
+        "metric": "fine-stage tokens/s, " + BENCH_CONFIGS["fine_only"]["label"], "value": round(6144 / dev_s_max, 1), "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(elapsed_max / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f16 weights/operands, f32 accumulate (reference arithmetic)", "data": "synthetic (seeded random weights; coarse codes uniform in [0, 1024), seed 11)",
+        "config": {"workload": "fine-only, 6144 tokens: one 1024-frame window, 6 codebook passes (BASELINE configs[4])", "parallelism": f"rows of the window sharded x{world}" + (f" (pinned: {pinned})" if pinned else ""),
+                   "collective": "K/V all-gather fused into the QKV mat-mul epilogue (peer stores over NVLink, CUDA IPC) + one flag barrier per layer; no NCCL on the data path" if world > 1 else "none",
+                   "l2": "weights (0.17 GB per pass) exceed the L2"},
+        "value_note": "6144 tokens / MAX over ranks of the summed CUDA-event kernel time of one window",
+        "e2e": {"value": round(e2e, 1), "unit": "tokens/s", "h2d_bytes_per_step": int(h2d / args.steps), "d2h_bytes_per_step": int(d2h / args.steps),
+                "note": "wall clock around bark_forward_fine_encoder (C-ABI; codes in, sampled ids out) incl. host sampling control, max over ranks"},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "parity": {"fine_ids_identical_to_unsharded_on_all_ranks": ok, "ok": ok},
+        "nvlink": {"bytes_stored_to_peers_per_step_rank0": int(nvl / args.steps), "achieved_GBps_rank0_out": round(nvl / elapsed / 1e9, 2) if world > 1 else 0.0,
+                   "note": "payload is small (K/V rows of 1024/N positions per layer); the stage is bounded by the parity-mode mat-muls, not by the link"},
+        "roofline": {"bound": "tensor", "kernel": top, "achieved": round(tfs, 2), "peak": P["tflops"], "unit": "TFLOP/s", "frac": round(tfs / P["tflops"], 4), "launches": tv["launches"],
+                     "avg_launch_us": round(tv["ms"] * 1e3 / max(tv["launches"], 1), 2), "traffic": None, "peak_source": P["source"]},
+        "kernels": {k: dict(launches=v["launches"], ms=round(v["ms"], 3)) for k, v in ranked[:8]},
+    })
+    if not ok:
+        sys.stderr.write("bench.py: sharded fine tokens differ from the unsharded run\n")
         sys.exit(3)
 
 
@@ -455,6 +601,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fast", action="store_true", help="skip the extra fast-mode (tensor-core fine passes) leg")
     ap.add_argument("--cpu-budget", type=float, default=30.0)
     ap.add_argument("--config", default=None, choices=sorted(BENCH_CONFIGS), help="which BASELINE config to measure (default: bark-small f16 = configs[1])")
     args = ap.parse_args()
@@ -464,6 +611,8 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
+    elif BENCH_CONFIG == "fine_only":
+        run_fine_only(args)
     else:
         run_ours(args)
 

@@ -59,6 +59,16 @@ BARK_API void bark_b200_io_counters(unsigned long long * h2d_bytes, unsigned lon
 BARK_API int  bark_b200_decode_timing(struct bark_context * ctx, unsigned long long * out, int n);
 
 
+/* ROW-SHARDED FINE STAGE (BASELINE configs[4]; csrc/shard.cu): one process per GPU; every rank loads the same file and the same coarse
+ * tokens, evaluates rows [rank * 1024 / world, ...) of each fine pass, stores its K / V rows into the peers' buffers over NVLink from
+ * the QKV mat-mul's epilogue, and ends with the full fine token array, bit-identical to the single-GPU run.
+ *   1. bark_b200_shard_init(ctx, rank, world, handle64)   -> 64-byte CUDA IPC handle of this rank's exchange buffer
+ *   2. (caller all-gathers the handles, e.g. torch.distributed)
+ *   3. bark_b200_shard_connect(ctx, all_handles)           -> maps the peers' buffers; bark_b200_forward_fine_encoder is sharded from here on */
+BARK_API int  bark_b200_shard_init(struct bark_context * ctx, int rank, int world, void * handle_out);
+BARK_API int  bark_b200_shard_connect(struct bark_context * ctx, const void * all_handles);
+BARK_API unsigned long long bark_b200_shard_nvlink_bytes(struct bark_context * ctx, int reset);
+
 /* FAST MODE (BARK_B200_MODE=fast in the environment at load; opt-in, NOT bit-identical to the reference): the fine model's
  * 1024-row passes (bark.cpp:1416-1584) run as tcgen05 tensor-core GEMMs + flash-style attention (csrc/fast_kernels.cu).
  * The two kernel hooks below run on host buffers without a context, for the numerics tests:
