@@ -497,9 +497,8 @@ extern "C" struct bark_context * bark_load_model(const char * model_path, struct
     int dev = g_device_override;
     if (dev < 0) { const char * e = getenv("BARK_B200_DEVICE"); dev = e ? atoi(e) : 0; }
     if (dev < 0 || dev >= n_dev) { fprintf(stderr, "%s: CUDA device %d out of range (%d present)\n", __func__, dev, n_dev); return nullptr; }
-    BARK_CUDA_CHECK(cudaSetDevice(dev));
     cudaDeviceProp prop;
-    BARK_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+    if (cudaSetDevice(dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { fprintf(stderr, "%s: cannot use CUDA device %d: %s\n", __func__, dev, cudaGetErrorString(cudaGetLastError())); return nullptr; }
     if (prop.major != 10) {
         fprintf(stderr, "%s: device %d is sm_%d%d; this library is built for sm_100a (B200) only\n", __func__, dev, prop.major, prop.minor);
         return nullptr;
@@ -513,21 +512,26 @@ extern "C" struct bark_context * bark_load_model(const char * model_path, struct
     { const char * e = getenv("BARK_B200_SAMPLE"); ctx->sample_on_device = !(e && !strcmp(e, "host")); }      // "host": read logits back and sample on the CPU (A-B)
     { const char * e = getenv("BARK_B200_KV_REUSE"); ctx->kv_reuse = !(e && !strcmp(e, "0")); }              // "0": re-prefill every coarse window like the reference (A-B)
     { const char * e = getenv("BARK_B200_DECODE"); ctx->use_decode_kernel = !(e && !strcmp(e, "multi")); }   // "multi": one kernel per op (debug / A-B)
-    ctx->params = params;
-    BARK_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    if (!load_model_file(model_path, ctx)) {
-        fprintf(stderr, "%s: failed to load model weights from '%s'\n", __func__, model_path);
-        bark_free(ctx);
-        return nullptr;
-    }
-    alloc_workspace(ctx);
     { const char * e = getenv("BARK_B200_DECODE_TIMING_TID"); if (e && atoi(e) >= 0 && atoi(e) < 512) ctx->timing_tid = atoi(e) & ~31; }
     { const char * e = getenv("BARK_B200_POLL_NS"); if (e && atoi(e) >= 0 && atoi(e) <= 100000) ctx->poll_ns = (unsigned) atoi(e); }
     { const char * e = getenv("BARK_B200_POLL_ATT_NS"); if (e && atoi(e) >= 0 && atoi(e) <= 100000) ctx->att_ns = (unsigned) atoi(e); }
     { const char * e = getenv("BARK_B200_POLL_FIRST_NS"); if (e && atoi(e) >= 0 && atoi(e) <= 100000) ctx->first_ns = (unsigned) atoi(e); }
+    { const char * e = getenv("BARK_B200_ADAPT"); ctx->adapt_on = e && !strcmp(e, "1"); }                     // "1": self-tuning head starts (experiment; measured WORSE: the feedback is collective and runs away)
+    ctx->params = params;
+    const bool loaded = guarded(false, [&] {                  // a CUDA failure while loading (out of memory, ...) is a failed load, not an abort
+    BARK_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    if (!load_model_file(model_path, ctx)) return false;
+    alloc_workspace(ctx);
     { const char * e = getenv("BARK_B200_TAG_BASE"); if (e) ctx->tag_base = (unsigned) strtoul(e, nullptr, 0); }      // tests: start the exchange epochs near the 32-bit wrap
     if (getenv("BARK_B200_DECODE_TIMING")) { ctx->d_timing = (unsigned long long *) ctx_alloc(ctx, 256 * 32 * 8); BARK_CUDA_CHECK(cudaMemset(ctx->d_timing, 0, 256 * 32 * 8)); }
     BARK_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    return true;
+    });
+    if (!loaded) {
+        fprintf(stderr, "%s: failed to load model weights from '%s'\n", __func__, model_path);
+        bark_free(ctx);
+        return nullptr;
+    }
     ctx->rng = std::mt19937(seed);
     ctx->stats.t_load_us = now_us() - t0;
     return ctx;
@@ -541,15 +545,15 @@ extern "C" void bark_reset_statistics(struct bark_context * ctx) {
                                           // the first generate; keeping it is the useful reading of "load time of the model"
 }
 
-extern "C" bool bark_b200_forward_text_encoder(struct bark_context * ctx, int) { return ctx && run_semantic(ctx); }
-extern "C" bool bark_b200_forward_coarse_encoder(struct bark_context * ctx, int) { return ctx && run_coarse(ctx); }
-extern "C" bool bark_b200_forward_fine_encoder(struct bark_context * ctx, int) { return ctx && run_fine(ctx); }
+extern "C" bool bark_b200_forward_text_encoder(struct bark_context * ctx, int) { return guarded(false, [&] { return ctx && run_semantic(ctx); }); }
+extern "C" bool bark_b200_forward_coarse_encoder(struct bark_context * ctx, int) { return guarded(false, [&] { return ctx && run_coarse(ctx); }); }
+extern "C" bool bark_b200_forward_fine_encoder(struct bark_context * ctx, int) { return guarded(false, [&] { return ctx && run_fine(ctx); }); }
 // the reference also exports these three as C++ symbols without a header (bark.cpp:1703,1865,2061)
 BARK_API bool bark_forward_text_encoder(struct bark_context * ctx, int n) { return bark_b200_forward_text_encoder(ctx, n); }
 BARK_API bool bark_forward_coarse_encoder(struct bark_context * ctx, int n) { return bark_b200_forward_coarse_encoder(ctx, n); }
 BARK_API bool bark_forward_fine_encoder(struct bark_context * ctx, int n) { return bark_b200_forward_fine_encoder(ctx, n); }
 
-extern "C" bool bark_generate_audio(struct bark_context * ctx, const char * text, int n_threads) {
+static bool bark_generate_audio_impl(struct bark_context * ctx, const char * text, int n_threads) {
     (void) n_threads;                      // CPU thread count of the reference's backend; nothing to size here
     if (!ctx) { fprintf(stderr, "%s: invalid bark context\n", __func__); return false; }
     if (!text) { fprintf(stderr, "%s: null prompt\n", __func__); return false; }
@@ -571,6 +575,7 @@ extern "C" bool bark_generate_audio(struct bark_context * ctx, const char * text
     ctx->stats.t_eval_us = now_us() - t0;
     return true;
 }
+extern "C" bool bark_generate_audio(struct bark_context * ctx, const char * text, int n_threads) { return guarded((bool) false, [&] { return bark_generate_audio_impl(ctx, text, n_threads); }); }
 
 extern "C" float * bark_get_audio_data(struct bark_context * ctx) {
     if (!ctx) { fprintf(stderr, "%s: invalid bark context\n", __func__); return nullptr; }
@@ -614,17 +619,19 @@ extern "C" void bark_free(struct bark_context * ctx) {
 // ---------------------------------------------------------------------------------------------
 static GPTModel * pick(bark_context * ctx, int which) { return which == 0 ? &ctx->semantic : which == 1 ? &ctx->coarse : which == 2 ? &ctx->fine : nullptr; }
 
-extern "C" int bark_b200_gpt_eval(struct bark_context * ctx, int which, const int32_t * tokens, int n, int * n_past, int merge_ctx, float * logits_out) {
+static int bark_b200_gpt_eval_impl(struct bark_context * ctx, int which, const int32_t * tokens, int n, int * n_past, int merge_ctx, float * logits_out) {
     if (!ctx || which < 0 || which > 1 || !tokens || !logits_out) return 0;
     BARK_CUDA_CHECK(cudaSetDevice(ctx->device));
     return gpt_eval(ctx, *pick(ctx, which), tokens, n, n_past, merge_ctx != 0, logits_out) ? 1 : 0;
 }
-extern "C" int bark_b200_fine_eval(struct bark_context * ctx, const int32_t * in_buffer, int nn, float * logits_out) {
+extern "C" int bark_b200_gpt_eval(struct bark_context * ctx, int which, const int32_t * tokens, int n, int * n_past, int merge_ctx, float * logits_out) { return guarded((int) 0, [&] { return bark_b200_gpt_eval_impl(ctx, which, tokens, n, n_past, merge_ctx, logits_out); }); }
+static int bark_b200_fine_eval_impl(struct bark_context * ctx, const int32_t * in_buffer, int nn, float * logits_out) {
     if (!ctx || !in_buffer || !logits_out) return 0;
     BARK_CUDA_CHECK(cudaSetDevice(ctx->device));
     return fine_eval(ctx, in_buffer, nn, logits_out) ? 1 : 0;
 }
-extern "C" int bark_b200_encodec_decode(struct bark_context * ctx, const int32_t * codes, int n_frames, float * out, int out_cap) {
+extern "C" int bark_b200_fine_eval(struct bark_context * ctx, const int32_t * in_buffer, int nn, float * logits_out) { return guarded((int) 0, [&] { return bark_b200_fine_eval_impl(ctx, in_buffer, nn, logits_out); }); }
+static int bark_b200_encodec_decode_impl(struct bark_context * ctx, const int32_t * codes, int n_frames, float * out, int out_cap) {
     if (!ctx || !codes) return -1;
     BARK_CUDA_CHECK(cudaSetDevice(ctx->device));
     if (!codec_decode(ctx, codes, n_frames)) return -1;
@@ -632,11 +639,12 @@ extern "C" int bark_b200_encodec_decode(struct bark_context * ctx, const int32_t
     if (out) memcpy(out, ctx->audio.data(), sizeof(float) * (size_t) std::min(n, out_cap));
     return n;
 }
+extern "C" int bark_b200_encodec_decode(struct bark_context * ctx, const int32_t * codes, int n_frames, float * out, int out_cap) { return guarded((int) -1, [&] { return bark_b200_encodec_decode_impl(ctx, codes, n_frames, out, out_cap); }); }
 extern "C" int bark_b200_sample(struct bark_context * ctx, int which, const float * logits, int n, float temp, float * eos_p) {
     if (!ctx || !logits || n < 1) return -1;
     return sample_token(ctx, *pick(ctx, which < 0 || which > 2 ? 0 : which), logits, n, temp, eos_p);
 }
-extern "C" int bark_b200_sample_rows(struct bark_context * ctx, const float * logits, int n, int rows, float temp, int32_t * tokens_out, float * eos_p_out) {
+static int bark_b200_sample_rows_impl(struct bark_context * ctx, const float * logits, int n, int rows, float temp, int32_t * tokens_out, float * eos_p_out) {
     if (!ctx || !logits || !tokens_out || rows < 1 || rows > 1024 || n < 2 || (size_t) n * 4 > 64 * 1024) return -1;
     const size_t cap = std::max<size_t>({(size_t) ctx->semantic.n_out_vocab, (size_t) ctx->coarse.n_out_vocab, (size_t) 1024 * ctx->fine.n_out_vocab});
     if ((size_t) rows * n > cap) return -1;
@@ -646,6 +654,7 @@ extern "C" int bark_b200_sample_rows(struct bark_context * ctx, const float * lo
     if (!sample_device(ctx, ctx->fine, ctx->ws.logits, n, n, rows, temp, tokens_out, eos_p_out)) return -1;
     return (int)(ctx->n_sample_host_replays - before);
 }
+extern "C" int bark_b200_sample_rows(struct bark_context * ctx, const float * logits, int n, int rows, float temp, int32_t * tokens_out, float * eos_p_out) { return guarded((int) -1, [&] { return bark_b200_sample_rows_impl(ctx, logits, n, rows, temp, tokens_out, eos_p_out); }); }
 extern "C" void bark_b200_reseed(struct bark_context * ctx, uint32_t seed) { if (ctx) ctx->rng = std::mt19937(seed); }
 extern "C" void bark_b200_tokenize(struct bark_context * ctx, const char * text, int32_t * out513) {
     if (!ctx || !text || !out513) return;
@@ -675,17 +684,19 @@ extern "C" void bark_b200_get_hparams(struct bark_context * ctx, int which, int3
     memcpy(out10, v, sizeof(v));
 }
 extern "C" unsigned long long bark_b200_kernel_launches(void) { return g_kernel_launches.load(); }
-extern "C" unsigned bark_b200_layernorm_fallbacks(struct bark_context * ctx) {
+static unsigned bark_b200_layernorm_fallbacks_impl(struct bark_context * ctx) {
     if (!ctx) return 0;
     unsigned v = 0; BARK_CUDA_CHECK(cudaMemcpy(&v, ctx->d_ln_fallbacks, sizeof(v), cudaMemcpyDeviceToHost)); return v;
 }
-extern "C" int bark_b200_decode_timing(struct bark_context * ctx, unsigned long long * out, int n) {
+extern "C" unsigned bark_b200_layernorm_fallbacks(struct bark_context * ctx) { return guarded((unsigned) 0, [&] { return bark_b200_layernorm_fallbacks_impl(ctx); }); }
+static int bark_b200_decode_timing_impl(struct bark_context * ctx, unsigned long long * out, int n) {
     if (!ctx || !ctx->d_timing || !out) return 0;
     BARK_CUDA_CHECK(cudaMemcpy(out, ctx->d_timing, sizeof(unsigned long long) * (size_t) std::min(n, 256 * 32), cudaMemcpyDeviceToHost));
     return std::min(n, 256 * 32);
 }
+extern "C" int bark_b200_decode_timing(struct bark_context * ctx, unsigned long long * out, int n) { return guarded((int) 0, [&] { return bark_b200_decode_timing_impl(ctx, out, n); }); }
 // fast-mode kernels on host buffers (tests): C[M][N] = A[M][K] W[N][K]^T (f16 in, f32 out), and attention over [n][E] f16 q / k / v
-extern "C" int bark_b200_fast_gemm(const uint16_t * A, const uint16_t * W, float * C, int M, int N, int K) {
+static int bark_b200_fast_gemm_impl(const uint16_t * A, const uint16_t * W, float * C, int M, int N, int K) {
     if (!A || !W || !C || M < 1 || N < 1 || K < 64 || K % 64) return 0;
     __half * dA, * dW; float * dC; int dev = 0, n_sm = 0;
     BARK_CUDA_CHECK(cudaGetDevice(&dev)); BARK_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
@@ -700,7 +711,8 @@ extern "C" int bark_b200_fast_gemm(const uint16_t * A, const uint16_t * W, float
     cudaFree(dA); cudaFree(dW); cudaFree(dC);
     return ok && e == cudaSuccess;
 }
-extern "C" int bark_b200_fast_attention(const uint16_t * q, const uint16_t * k, const uint16_t * v, uint16_t * out, int n, int E, int H) {
+extern "C" int bark_b200_fast_gemm(const uint16_t * A, const uint16_t * W, float * C, int M, int N, int K) { return guarded((int) 0, [&] { return bark_b200_fast_gemm_impl(A, W, C, M, N, K); }); }
+static int bark_b200_fast_attention_impl(const uint16_t * q, const uint16_t * k, const uint16_t * v, uint16_t * out, int n, int E, int H) {
     if (!q || !k || !v || !out || n < 256 || n % 256 || E != H * 64) return 0;
     std::vector<uint16_t> qk((size_t) n * 2 * E), vt((size_t) E * n);
     for (int r = 0; r < n; r++) {
@@ -716,6 +728,20 @@ extern "C" int bark_b200_fast_attention(const uint16_t * q, const uint16_t * k, 
     else BARK_CUDA_CHECK(cudaMemcpy(out, dout, (size_t) n * E * 2, cudaMemcpyDeviceToHost));
     cudaFree(dqk); cudaFree(dvt); cudaFree(dout);
     return ok && e == cudaSuccess;
+}
+extern "C" int bark_b200_fast_attention(const uint16_t * q, const uint16_t * k, const uint16_t * v, uint16_t * out, int n, int E, int H) { return guarded((int) 0, [&] { return bark_b200_fast_attention_impl(q, k, v, out, n, E, H); }); }
+// the decode kernel's self-tuned head starts, [n_cta][8] nanoseconds (decode_kernels.cu XT_* order); which: 0 semantic, 1 coarse
+extern "C" int bark_b200_decode_adapt(struct bark_context * ctx, int which, unsigned * out, int n) {
+    if (!ctx || !out || which < 0 || which > 1) return 0;
+    return guarded(0, [&] {
+        const GPTModel * m = pick(ctx, which);
+        if (!m->d_adapt) return 0;
+        const int cnt = std::min(n, ctx->n_sm_total * 8);
+        BARK_CUDA_CHECK(cudaSetDevice(ctx->device));
+        BARK_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        BARK_CUDA_CHECK(cudaMemcpy(out, m->d_adapt, (size_t) cnt * 4, cudaMemcpyDeviceToHost));
+        return cnt;
+    });
 }
 extern "C" int bark_b200_fast_mode(struct bark_context * ctx) { return ctx && ctx->fast_mode ? 1 : 0; }
 

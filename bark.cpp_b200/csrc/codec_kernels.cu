@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(256) conv1d_lane_kernel(const float * __restri
 
 void conv1d(const float * x, int Cin, int T, const ConvW & cv, bool elu_in, const float * resid, float * y, cudaStream_t s) {
     const int K = Cin * cv.k, nsteps = K / 32, ngroups = (nsteps + 7) / 8;
-    if (ngroups > 4) { fprintf(stderr, "bark_b200: unsupported conv shape Cin=%d k=%d\n", Cin, cv.k); abort(); }
+    if (ngroups > 4) { fprintf(stderr, "bark_b200: unsupported conv shape Cin=%d k=%d\n", Cin, cv.k); throw std::runtime_error("unsupported configuration (see the message above)"); }
     const int TT = 32;
     const int S = (TT + cv.k - 1) | 1;
     const size_t smem = (size_t) Cin * S * sizeof(float);
@@ -121,7 +121,7 @@ void conv1d(const float * x, int Cin, int T, const ConvW & cv, bool elu_in, cons
     if (cv.k == 1)      { if (ngroups <= 1) CONV_CASE(1, 1) else CONV_CASE(1, 2) }
     else if (cv.k == 3) { if (ngroups <= 1) CONV_CASE(3, 1) else if (ngroups <= 2) CONV_CASE(3, 2) else CONV_CASE(3, 3) }
     else if (cv.k == 7) { if (ngroups <= 1) CONV_CASE(7, 1) else CONV_CASE(7, 4) }
-    else { fprintf(stderr, "bark_b200: unsupported conv kernel size %d\n", cv.k); abort(); }
+    else { fprintf(stderr, "bark_b200: unsupported conv kernel size %d\n", cv.k); throw std::runtime_error("unsupported configuration (see the message above)"); }
 #undef CONV_CASE
 }
 
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(256) convtr1d_lane_kernel(const float * __rest
 
 void convtr1d(const float * x, int Cin, int T, const ConvW & cv, int stride, float * y, cudaStream_t s) {
     const int nsteps = Cin / 32, ngroups = (nsteps + 7) / 8;
-    if (Cin % 32 != 0 || ngroups > 2 || cv.k != 2 * stride) { fprintf(stderr, "bark_b200: unsupported transposed conv Cin=%d k=%d s=%d\n", Cin, cv.k, stride); abort(); }
+    if (Cin % 32 != 0 || ngroups > 2 || cv.k != 2 * stride) { fprintf(stderr, "bark_b200: unsupported transposed conv Cin=%d k=%d s=%d\n", Cin, cv.k, stride); throw std::runtime_error("unsupported configuration (see the message above)"); }
     const int TF = 16, S = TF + 1 + ((TF + 1) % 2 == 0);
     const size_t smem = (size_t) Cin * S * sizeof(float);
     const int tiles = (T + TF - 1) / TF;
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(UPB * 4 * 32) lstm_recur_kernel(const float * 
 void lstm_layer(const float * x, int C, int T, const __half * wih_li, const __half * whh_li, int Kp, const float * bih, const float * bhh,
                 const float * skip, float * gi_scratch, float * hbuf, unsigned * counter, float * out, cudaStream_t s) {
     const int Hn = C, G4 = 4 * Hn;
-    if (Hn % 32 != 0 || Hn > 512 || Hn % 4 != 0) { fprintf(stderr, "bark_b200: unsupported LSTM width %d\n", Hn); abort(); }
+    if (Hn % 32 != 0 || Hn > 512 || Hn % 4 != 0) { fprintf(stderr, "bark_b200: unsupported LSTM width %d\n", Hn); throw std::runtime_error("unsupported configuration (see the message above)"); }
     g_next_flops = 2.0 * (double) T * G4 * C;
     BARK_LAUNCH(lstm_inproj_lane_kernel, dim3((T + 7) / 8, 32), 256, (size_t) 8 * C * sizeof(float), s, x, C, T, wih_li, Kp, bih, G4, gi_scratch);
     BARK_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(unsigned), s));

@@ -11,21 +11,34 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <atomic>
+#include <exception>
+#include <stdexcept>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 
+// A failed CUDA call is reported on stderr and thrown; every extern "C" entry point catches it and returns its failure value
+// (nullptr / false / 0), as bark.h's contract says (bark.cpp:1174-1177, 2126-2141) — a drop-in library must not abort() its host.
+namespace bark { struct CudaFailure { cudaError_t err; const char * file; int line; }; }
 #define BARK_CUDA_CHECK(expr)                                                                         \
     do {                                                                                              \
         cudaError_t err__ = (expr);                                                                   \
         if (err__ != cudaSuccess) {                                                                   \
             fprintf(stderr, "bark_b200: CUDA error %s at %s:%d: %s\n", cudaGetErrorName(err__), __FILE__, __LINE__, \
                     cudaGetErrorString(err__));                                                       \
-            abort();                                                                                  \
+            throw ::bark::CudaFailure{err__, __FILE__, __LINE__};                                     \
         }                                                                                             \
     } while (0)
 
 namespace bark {
+
+// run `f`; a CUDA failure (already reported) or any other exception becomes the entry point's failure value
+template <typename R, typename F> inline R guarded(R fail, F && f) {
+    try { return f(); }
+    catch (const CudaFailure &) { return fail; }
+    catch (const std::exception & e) { fprintf(stderr, "bark_b200: %s\n", e.what()); return fail; }
+    catch (...) { fprintf(stderr, "bark_b200: unexpected exception\n"); return fail; }
+}
 
 // Process-wide state is limited to counters (atomic) and per-thread annotations (thread_local), so that one host thread per GPU can
 // drive its own bark_context inside one process (tests/test_parity_gpu.py two-thread case).

@@ -99,6 +99,28 @@ __device__ __forceinline__ void publish_all(tagged_t * base, int n, int i, float
     if (lane < kReplicas) publish(base + (size_t) lane * n + i, v, tag);
 }
 __shared__ unsigned s_poll_ns, s_first_ns, s_att_ns;                           // back-off between polls (DecodeArgs::poll_ns, default 40); head start given to the two residual exchanges
+// Adaptive head start.  Polling is not free: 148 x 512 threads re-reading tagged words every ~100 ns approach the L2's request rate and
+// slow the very producers they wait for (polling from the start of each exchange costs +21 us per token, profiles/r02_decode.md), while
+// sleeping past the arrival sits on the critical path.  So every CTA keeps, per exchange type, how long it sleeps before its FIRST
+// poll and steers it toward "one or two polls were needed": no poll needed -> it slept too long, shorten; more than two -> lengthen.
+// The values survive from token to token in global memory (DecodeArgs::adapt); they change timing only, never results.
+// MEASURED (round 2, profiles/r02_decode.md): OFF by default.  The feedback is collective — a CTA that sleeps too long delays its own
+// next phase, every other CTA then sees "many polls" and lengthens ITS sleep — and the values run away (359-431 us per token against
+// 273 us with the fixed 500 ns / 2000 ns head starts).  Kept behind BARK_B200_ADAPT=1 as a documented negative result.
+enum { XT_Q = 0, XT_ATT = 1, XT_X1 = 2, XT_FF = 3, XT_X2 = 4, XT_SC = 5, XT_COUNT = 8 };
+__shared__ unsigned s_adapt[XT_COUNT], s_obs[XT_COUNT], s_adapt_on;
+__device__ __forceinline__ void adapt_observe(int xt, unsigned rounds) {
+    if (!s_adapt_on) return;
+    const unsigned ob = __reduce_or_sync(0xffffffffu, rounds == 0 ? 0u : rounds > 2 ? 3u : 1u);
+    if ((threadIdx.x & 31) == 0 && ob) atomicOr(&s_obs[xt], ob);
+}
+__device__ __forceinline__ void adapt_update(int xt) {          // thread 0, after the block barrier that ends the exchange
+    if (!s_adapt_on) return;
+    const unsigned f = s_obs[xt]; s_obs[xt] = 0;
+    unsigned v = s_adapt[xt];
+    if (f == 0) v = v > 96 ? v - 96 : 0; else if (f & 2) v = min(v + 160u, 8000u);
+    s_adapt[xt] = v;
+}
 __device__ __forceinline__ float consume1(const tagged_t * p, uint32_t tag) {
     tagged_t w = peek(p);
     while ((uint32_t)(w >> 32) != tag) { __nanosleep(s_poll_ns); w = peek(p); }       // back off: thousands of pollers share a few L2 lines
@@ -131,18 +153,20 @@ __device__ __forceinline__ void tstamp(int i) {
 // footprint (a 100 KB body re-fetched from L2 every layer cost 5-10x), so shared pieces are real calls.
 enum { SINK_PLAIN = 0, SINK_ACT = 1, SINK_ACT_R16 = 2 };
 template <int MAXJ>
-__device__ __forceinline__ void consume_to_smem_inl(const tagged_t * g, int n, uint32_t tag, float * dst, int mode, unsigned first_ns = 0) {
+__device__ __forceinline__ void consume_to_smem_inl(const tagged_t * g, int n, uint32_t tag, float * dst, int mode, int xt) {
     constexpr int PJ = MAXJ / 2;                             // pairs of words per thread (n is even: E % 32 == 0)
     tagged_t w[PJ][2];
     g += (size_t)(blockIdx.x % kReplicas) * n;               // this CTA's copy of the vector
-    if (first_ns) __nanosleep(first_ns);                     // the producers are known to need at least this long: do not hammer their lines meanwhile
+    const unsigned first_ns = s_adapt[xt];
+    if (first_ns) __nanosleep(first_ns);                     // the producers need about this long: do not hammer their lines meanwhile
 #pragma unroll
     for (int j = 0; j < PJ; j++) { const int i = 2 * (threadIdx.x + j * kThreads); if (i < n) peek2(g + i, w[j][0], w[j][1]); }
+    unsigned rounds = 0;
 #pragma unroll
     for (int j = 0; j < PJ; j++) {
         const int i = 2 * (threadIdx.x + j * kThreads);
         if (i < n) {
-            while ((uint32_t)(w[j][0] >> 32) != tag || (uint32_t)(w[j][1] >> 32) != tag) { __nanosleep(s_poll_ns); peek2(g + i, w[j][0], w[j][1]); }
+            while ((uint32_t)(w[j][0] >> 32) != tag || (uint32_t)(w[j][1] >> 32) != tag) { __nanosleep(s_poll_ns); peek2(g + i, w[j][0], w[j][1]); rounds++; }
 #pragma unroll
             for (int e = 0; e < 2; e++) {
                 const float v = __uint_as_float((uint32_t) w[j][e]);
@@ -150,27 +174,34 @@ __device__ __forceinline__ void consume_to_smem_inl(const tagged_t * g, int n, u
             }
         }
     }
+    adapt_observe(xt, rounds);
     __syncthreads();
+    if (threadIdx.x == 0) adapt_update(xt);
 }
 // one private (not replicated) vector of any length, one word per load: the score row of a head (a few consumer CTAs per head)
 __device__ __noinline__ void consume_row_to_smem(const tagged_t * g, int n, uint32_t tag, float * dst) {
     tagged_t w[2];
+    const unsigned first_ns = s_adapt[XT_SC];
+    if (first_ns) __nanosleep(first_ns);
+    unsigned rounds = 0;
 #pragma unroll
     for (int j = 0; j < 2; j++) { const int i = threadIdx.x + j * kThreads; if (i < n) w[j] = peek(g + i); }
 #pragma unroll
     for (int j = 0; j < 2; j++) {
         const int i = threadIdx.x + j * kThreads;
         if (i < n) {
-            while ((uint32_t)(w[j] >> 32) != tag) { __nanosleep(s_poll_ns); w[j] = peek(g + i); }
+            while ((uint32_t)(w[j] >> 32) != tag) { __nanosleep(s_poll_ns); w[j] = peek(g + i); rounds++; }
             dst[i] = __uint_as_float((uint32_t) w[j]);
         }
     }
+    adapt_observe(XT_SC, rounds);
     __syncthreads();
+    if (threadIdx.x == 0) adapt_update(XT_SC);
 }
 // out-of-line copy: the kernel lives or dies by its instruction-cache footprint, so shared pieces are real calls
 template <int MAXJ>
-__device__ __noinline__ void consume_to_smem(const tagged_t * g, int n, uint32_t tag, float * dst, int mode, unsigned first_ns = 0) {
-    consume_to_smem_inl<MAXJ>(g, n, tag, dst, mode, first_ns);
+__device__ __noinline__ void consume_to_smem(const tagged_t * g, int n, uint32_t tag, float * dst, int mode, int xt) {
+    consume_to_smem_inl<MAXJ>(g, n, tag, dst, mode, xt);
 }
 
 // FP64 is scarce on this part (a double division is ~2400 cycles of dependent latency — measured: it dominated the whole
@@ -216,9 +247,16 @@ __device__ __noinline__ void block_layernorm(const float * xs, int E, double inv
     __syncthreads();
     float mean;
     {
-        double S = 0.0; float A = 0.0f;
+        // pairwise (depth 4) instead of 16 dependent adds: the double adds were the hottest instructions of this function
+        // (profiles/r02_decode.md); any order is covered by the bracket below, and every thread uses the same one
+        double qd[kWarps]; float qf[kWarps];
 #pragma unroll
-        for (int w = 0; w < kWarps; w++) { S += sA[w]; A += fA[w]; }
+        for (int w = 0; w < kWarps; w++) { qd[w] = sA[w]; qf[w] = fA[w]; }
+#pragma unroll
+        for (int st = kWarps / 2; st > 0; st >>= 1)
+#pragma unroll
+            for (int w = 0; w < st; w++) { qd[w] += qd[w + st]; qf[w] += qf[w + st]; }
+        const double S = qd[0]; const float A = qf[0];
         const double c = S * inv_E;
         const double hw = (slack * (double) A * 1.001) * inv_E + fabs(c) * 0x1p-50;     // 1.001: the float abs-sum may be low by n*2^-24
         mean = __double2float_rn(c - hw);
@@ -239,9 +277,14 @@ __device__ __noinline__ void block_layernorm(const float * xs, int E, double inv
     __syncthreads();
     float scale;
     {
-        double S2 = 0.0;
+        double qd[kWarps];
 #pragma unroll
-        for (int w = 0; w < kWarps; w++) S2 += sB[w];
+        for (int w = 0; w < kWarps; w++) qd[w] = sB[w];
+#pragma unroll
+        for (int st = kWarps / 2; st > 0; st >>= 1)
+#pragma unroll
+            for (int w = 0; w < st; w++) qd[w] += qd[w + st];
+        const double S2 = qd[0];
         const double c = S2 * inv_E;
         const double hw = (slack * S2) * inv_E + c * 0x1p-50;
         float variance = __double2float_rn(c - hw);
@@ -489,6 +532,12 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
         s_bc.policy = l2_evict_first_policy();
         s_bc.E = E; s_bc.ctx = ctx; s_bc.n_past = n_past; s_bc.n_phases = n_phases;
         s_tim = A.timing; s_tim_layer = 0; s_tim_tid = A.timing_tid; s_poll_ns = A.poll_ns; s_first_ns = A.first_ns; s_att_ns = A.att_ns;
+        s_adapt_on = A.adapt != nullptr;
+    }
+    if (tid < XT_COUNT) {                                    // head starts: carried over from the previous token, or the fixed knobs
+        const unsigned fixed = tid == XT_X1 || tid == XT_X2 ? A.first_ns : (tid == XT_ATT && (int) blockIdx.x >= A.H * ((A.E / A.H) >> 4)) ? A.att_ns : 0u;
+        s_adapt[tid] = A.adapt ? A.adapt[blockIdx.x * XT_COUNT + tid] : fixed;
+        s_obs[tid] = 0;
     }
     if (lane == 0) {
         mbar_init(smem_u32(&s_bar[warp][0]), 1); mbar_init(smem_u32(&s_bar[warp][1]), 1);
@@ -560,7 +609,7 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
                 }
             }
             tstamp<TM>(6);
-            consume_to_smem<2>(s_bc.gq, E, t_qkv, qs, SINK_PLAIN);
+            consume_to_smem<2>(s_bc.gq, E, t_qkv, qs, SINK_PLAIN, XT_Q);
             tstamp<TM>(7);
 #pragma unroll
             for (int i = 0; i < kMaxTasks; i++) {
@@ -704,12 +753,12 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
         tstamp<TM>(16);
 
         // ---- P4: c_proj + residual ----
-        consume_to_smem<2>(s_bc.gatt, E, t_att, act, kSinkAct, pv_cta ? 0u : s_att_ns);   // CTAs without a soft_max tile would poll for the whole of P3
+        consume_to_smem<2>(s_bc.gatt, E, t_att, act, kSinkAct, XT_ATT);    // (CTAs without a soft_max tile would otherwise poll for the whole of P3)
         tstamp<TM>(17);
         run_phase<WT, TM>(4 * il + 1, EP_RESID, il, t_x1, 18);
 
         // ---- P5: LN2 -> c_fc -> GELU ----
-        consume_to_smem<2>(s_bc.gx, E, t_x1, xs, SINK_PLAIN, s_first_ns);
+        consume_to_smem<2>(s_bc.gx, E, t_x1, xs, SINK_PLAIN, XT_X1);
         tstamp<TM>(21);
         block_layernorm<kRound, TM>(xs, E, inv_E, lv.ln_2_g, lv.ln_2_b, act, red, A.ln_fallbacks, 22);
         tstamp<TM>(23);
@@ -718,11 +767,11 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
         tstamp<TM>(27);
 
         // ---- P6: mlp/c_proj + residual ----
-        consume_to_smem<8>(s_bc.gff, 4 * E, t_ff, act, kSinkAct);
+        consume_to_smem<8>(s_bc.gff, 4 * E, t_ff, act, kSinkAct, XT_FF);
         tstamp<TM>(28);
         run_phase<WT, TM>(4 * il + 3, EP_RESID, il, t_x2, 29);
 
-        consume_to_smem<2>(s_bc.gx, E, t_x2, xs, SINK_PLAIN, s_first_ns);
+        consume_to_smem<2>(s_bc.gx, E, t_x2, xs, SINK_PLAIN, XT_X2);
     }
     if (tid == A.timing_tid) s_tim_layer = L;                 // row L: start of the final norm
     // ---- final norm + lm_head window ----
@@ -730,6 +779,7 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
     block_layernorm<kRound, TM>(xs, E, inv_E, A.ln_f_g, A.ln_f_b, act, red, A.ln_fallbacks, 1);
     tstamp<TM>(2);
     run_phase<WT, TM>(4 * L, EP_LOGITS, 0, 0, 3);
+    if (A.adapt && tid < XT_COUNT) A.adapt[blockIdx.x * XT_COUNT + tid] = s_adapt[tid];      // (last changed a whole phase ago, by thread 0)
 }
 
 static size_t decode_smem_bytes() { return (size_t) SmemLayout::total + 128; }

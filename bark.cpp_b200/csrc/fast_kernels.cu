@@ -87,10 +87,21 @@ constexpr int kGemmThreads = 192;
 // ------------------------------------------------------------------------------------------------
 // GEMM
 // ------------------------------------------------------------------------------------------------
+// GELU as the reference's table defines it (ggml.c:2546-2571: f16(x) -> 0.5 x (1 + tanh(sqrt(2/pi) x (1 + 0.044715 x^2))) -> f16), evaluated
+// with the hardware tanh instead of a 64 K-entry table: 128 dependent table look-ups per thread made the GELU epilogue 3/4 of the
+// fc GEMM's time (profiles/r02_fast_mode.md).  tanh.approx is accurate to ~2^-11 relative: the result can differ from the table by
+// one f16 ulp, which is inside fast mode's tolerance (it is not the bit-exact path).
+__device__ __forceinline__ float gelu_fast(float v) {
+    const float x = __half2float(__float2half_rn(v));
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.79788456080286535588f * x * (1.0f + 0.044715f * x * x)));
+    return 0.5f * x * (1.0f + t);
+}
+
 template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                                      int M, int N, int K, FastEpi ep) {
-    constexpr int kStages = BN >= 128 ? 6 : 8;
+    constexpr int kStages = BN >= 256 ? 4 : BN >= 128 ? 6 : 8;
     constexpr int kABytes = kBM * kBK * 2, kBBytes = BN * kBK * 2, kStageBytes = kABytes + kBBytes;
     constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
     extern __shared__ unsigned char smem_raw[];
@@ -169,14 +180,20 @@ __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid
                 for (int i = 0; i < 32 && n + i < N; i++) ep.vt[(size_t)(n + i - ep.v_col0) * ep.vt_ld + m] = __float2half_rn(v[i]);
             } else {
                 __half * dst = ep.out16 + (size_t) m * ep.ldo + n;
-                __half h[32];
+                if (ep.mode == FEPI_GELU16) {
 #pragma unroll
-                for (int i = 0; i < 32; i++) h[i] = ep.mode == FEPI_GELU16 ? __float2half_rn(gelu_lookup(ep.gelu_tab, v[i])) : __float2half_rn(v[i]);
+                    for (int i = 0; i < 32; i++) v[i] = gelu_fast(v[i]);
+                }
                 if (full && (ep.ldo & 7) == 0) {
 #pragma unroll
-                    for (int i = 0; i < 32; i += 8) *reinterpret_cast<uint4 *>(dst + i) = *reinterpret_cast<const uint4 *>(h + i);
+                    for (int i = 0; i < 32; i += 8) {
+                        uint4 pk;
+                        __half2 h0 = __floats2half2_rn(v[i], v[i + 1]), h1 = __floats2half2_rn(v[i + 2], v[i + 3]), h2 = __floats2half2_rn(v[i + 4], v[i + 5]), h3 = __floats2half2_rn(v[i + 6], v[i + 7]);
+                        pk.x = *reinterpret_cast<uint32_t *>(&h0); pk.y = *reinterpret_cast<uint32_t *>(&h1); pk.z = *reinterpret_cast<uint32_t *>(&h2); pk.w = *reinterpret_cast<uint32_t *>(&h3);
+                        *reinterpret_cast<uint4 *>(dst + i) = pk;
+                    }
                 } else {
-                    for (int i = 0; i < 32 && n + i < N; i++) dst[i] = h[i];
+                    for (int i = 0; i < 32 && n + i < N; i++) dst[i] = __float2half_rn(v[i]);
                 }
             }
         }
@@ -330,6 +347,162 @@ __global__ void __launch_bounds__(kGemmThreads, 1) flash_attn_kernel(const __gri
 }
 
 // ------------------------------------------------------------------------------------------------
+// attention, pipelined (the default): key blocks of 128 with S, P and the block's P.V double-buffered, so the tensor pipe computes
+// S of block j+1 while the 128 soft_max threads work on block j, and the O update of block j-1 is deferred until P of block j is
+// on its way (its P.V result sits in the other TMEM buffer meanwhile).  flash_attn_kernel above is the serial first version
+// (BARK_B200_FLASH=v1), kept for A-B runs: every soft_max step there waits for the MMA before and after it.
+// ------------------------------------------------------------------------------------------------
+constexpr int kKeyBlk2 = 128, kKvStages = 3;
+struct Flash2Smem {
+    static constexpr int q = 0;                                    // [128 queries][64] f16                            16 KB
+    static constexpr int k = q + 128 * 128;                        // 3 stages x [128 keys][64] f16                    48 KB
+    static constexpr int v = k + kKvStages * kKeyBlk2 * 128;       // 3 stages x 2 atoms x [64 d][64 keys] f16         48 KB
+    static constexpr int p = v + kKvStages * kKeyBlk2 * 128;       // 2 buffers x 2 atoms x [128 queries][64 keys]     64 KB
+    static constexpr int bars = p + 2 * 2 * 128 * 128;             // q_full, kv_full[3], kv_empty[3], s_full[2], p_ready[2], pv_full[2]
+    static constexpr int total = bars + 16 * 8;
+};
+
+__global__ void __launch_bounds__(kGemmThreads, 1) flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmVT,
+                                                                       int n_keys, int k_col0, float scale_log2e, __half * __restrict__ out, int ldo) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char * smem = (unsigned char *)(((uintptr_t) smem_raw + 1023) & ~(uintptr_t) 1023);
+    uint64_t * bars = reinterpret_cast<uint64_t *>(smem + Flash2Smem::bars);
+    uint32_t * tmem_slot = reinterpret_cast<uint32_t *>(bars + 14);
+    const uint32_t b0 = smem_u32(bars);
+    const uint32_t q_full = b0, kv_full0 = b0 + 8, kv_empty0 = b0 + 32, s_full0 = b0 + 56, p_ready0 = b0 + 72, pv_full0 = b0 + 88;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int h = blockIdx.y, q0 = blockIdx.x * 128;
+    const int nblk = n_keys / kKeyBlk2;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmQK); prefetch_tmap(&tmVT);
+        mbar_init(q_full, 1);
+        for (int s = 0; s < kKvStages; s++) { mbar_init(kv_full0 + s * 8, 1); mbar_init(kv_empty0 + s * 8, 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(s_full0 + s * 8, 1); mbar_init(p_ready0 + s * 8, 128); mbar_init(pv_full0 + s * 8, 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);       // S[2]: columns [0,128) [128,256);  P.V[2]: [256,320) [320,384)
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t sQ = smem_u32(smem + Flash2Smem::q), sK = smem_u32(smem + Flash2Smem::k), sV = smem_u32(smem + Flash2Smem::v), sP = smem_u32(smem + Flash2Smem::p);
+    constexpr uint32_t kStage = kKeyBlk2 * 128, kPBuf = 2 * 128 * 128;
+
+    if (warp == 0) {
+        if (lane == 0) {                                      // ===== TMA producer =====
+            mbar_expect_tx(q_full, 128 * 128);
+            tma_load_2d(sQ, &tmQK, h * kHeadD, q0, q_full);
+            for (int j = 0; j < nblk; j++) {
+                const int s = j % kKvStages;
+                mbar_wait(kv_empty0 + s * 8, ((j / kKvStages) & 1) ^ 1);
+                mbar_expect_tx(kv_full0 + s * 8, 2 * kStage);
+                tma_load_2d(sK + s * kStage, &tmQK, k_col0 + h * kHeadD, j * kKeyBlk2, kv_full0 + s * 8);
+                for (int a = 0; a < 2; a++) tma_load_2d(sV + s * kStage + a * 64 * 128, &tmVT, j * kKeyBlk2 + a * 64, h * kHeadD, kv_full0 + s * 8);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                                      // ===== MMA issuer =====
+            constexpr uint32_t idesc_s = f16_idesc(128, kKeyBlk2), idesc_o = f16_idesc(128, kHeadD);
+            auto issue_s = [&](int j) {                       // S_j = Q K_j^T  (128 x 128, K = 64) into S[j & 1]
+                const int s = j % kKvStages;
+                mbar_wait(kv_full0 + s * 8, (j / kKvStages) & 1);
+                tc_fence_after();
+                const uint64_t dq = kmajor_sw128_desc(sQ), dk = kmajor_sw128_desc(sK + s * kStage);
+#pragma unroll
+                for (int k = 0; k < kHeadD / 16; k++) umma_f16(tmem + (uint32_t)(j & 1) * 128, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+                umma_commit(s_full0 + (j & 1) * 8);
+            };
+            mbar_wait(q_full, 0);
+            issue_s(0);
+            for (int j = 0; j < nblk; j++) {
+                if (j + 1 < nblk) issue_s(j + 1);             // runs on the tensor pipe while the soft_max threads work on block j
+                mbar_wait(p_ready0 + (j & 1) * 8, (j >> 1) & 1);
+                tc_fence_after();
+                const int s = j % kKvStages;
+#pragma unroll
+                for (int kk = 0; kk < kKeyBlk2 / 16; kk++) {  // P.V of block j (128 x 64, K = 128 keys) into PV[j & 1]
+                    const uint64_t dp = kmajor_sw128_desc(sP + (uint32_t)(j & 1) * kPBuf + (kk >> 2) * 128 * 128) + 2 * (kk & 3);
+                    const uint64_t dv = kmajor_sw128_desc(sV + s * kStage + (kk >> 2) * 64 * 128) + 2 * (kk & 3);
+                    umma_f16(tmem + 256 + (uint32_t)(j & 1) * 64, dp, dv, idesc_o, kk != 0);
+                }
+                umma_commit(kv_empty0 + s * 8);
+                umma_commit(pv_full0 + (j & 1) * 8);
+            }
+        }
+    } else {                                                  // ===== soft_max + output: one query row per thread =====
+        const int q = warp & 3, row = q * 32 + lane;
+        const uint32_t tlane = (uint32_t)(q * 32) << 16;
+        float o[kHeadD];
+#pragma unroll
+        for (int i = 0; i < kHeadD; i++) o[i] = 0.0f;
+        float m_run = -INFINITY, l_run = 0.0f, alpha_prev = 0.0f;
+        auto accumulate = [&](int j, float alpha) {           // O = O * alpha + (P.V of block j)
+            mbar_wait(pv_full0 + (j & 1) * 8, (j >> 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < kHeadD / 32; c++) {
+                float v[32]; tmem_ld32(tmem + tlane + 256 + (uint32_t)(j & 1) * 64 + c * 32, v);
+#pragma unroll
+                for (int i = 0; i < 32; i++) o[c * 32 + i] = o[c * 32 + i] * alpha + v[i];
+            }
+        };
+        for (int j = 0; j < nblk; j++) {
+            mbar_wait(s_full0 + (j & 1) * 8, (j >> 1) & 1);
+            tc_fence_after();
+            const uint32_t ts = tmem + tlane + (uint32_t)(j & 1) * 128;
+            float mx = m_run;
+#pragma unroll 1
+            for (int c = 0; c < kKeyBlk2 / 32; c++) {
+                float v[32]; tmem_ld32(ts + c * 32, v);
+#pragma unroll
+                for (int i = 0; i < 32; i++) mx = fmaxf(mx, v[i]);
+            }
+            const float alpha = exp2f((m_run - mx) * scale_log2e);
+            float sum = 0.0f;
+#pragma unroll 1
+            for (int c = 0; c < kKeyBlk2 / 32; c++) {
+                float v[32]; tmem_ld32(ts + c * 32, v);
+                uint32_t pk[16];
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    const float p0 = exp2f((v[i] - mx) * scale_log2e), p1 = exp2f((v[i + 1] - mx) * scale_log2e);
+                    const __half2 hp = __floats2half2_rn(p0, p1);
+                    sum += __low2float(hp) + __high2float(hp);
+                    pk[i >> 1] = *reinterpret_cast<const uint32_t *>(&hp);
+                }
+                const uint32_t base = sP + (uint32_t)(j & 1) * kPBuf + (c >> 1) * 128 * 128 + row * 128;
+#pragma unroll
+                for (int w = 0; w < 4; w++) {
+                    const uint32_t chunk = (uint32_t)((c & 1) * 4 + w) ^ (uint32_t)(row & 7);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + chunk * 16), "r"(pk[4 * w]), "r"(pk[4 * w + 1]), "r"(pk[4 * w + 2]), "r"(pk[4 * w + 3]) : "memory");
+                }
+            }
+            l_run = l_run * alpha + sum;
+            m_run = mx;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            tc_fence_before();
+            mbar_arrive(p_ready0 + (j & 1) * 8);
+            if (j > 0) accumulate(j - 1, alpha_prev);         // block j-1's P.V has been in TMEM for a while by now
+            alpha_prev = alpha;
+        }
+        accumulate(nblk - 1, alpha_prev);
+        const float inv = 1.0f / l_run;
+        __half * dst = out + (size_t)(q0 + row) * ldo + h * kHeadD;
+#pragma unroll
+        for (int i = 0; i < kHeadD; i += 8) {
+            __half hh[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++) hh[e] = __float2half_rn(o[i + e] * inv);
+            *reinterpret_cast<uint4 *>(dst + i) = *reinterpret_cast<const uint4 *>(hh);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
 // LayerNorm -> f16 row-major operand: one warp per row
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) ln_rows_f16_kernel(const float * __restrict__ x, int rows, int E, const float * __restrict__ g, const float * __restrict__ b, __half * __restrict__ out) {
@@ -382,7 +555,7 @@ static bool make_map(CUtensorMap * m, const void * base, int rows, int cols, int
 
 template <int BN>
 static bool launch_gemm(const __half * A, int lda, const __half * W, int ldw, int M, int N, int K, const FastEpi & ep, cudaStream_t s) {
-    constexpr int kStages = BN >= 128 ? 6 : 8;
+    constexpr int kStages = BN >= 256 ? 4 : BN >= 128 ? 6 : 8;
     const size_t smem = (size_t) kStages * (kBM * kBK * 2 + BN * kBK * 2) + (2 * kStages + 1) * 8 + 16 + 1024;
     static std::atomic<unsigned long long> configured{0};     // kernel attributes are per device (one host thread per GPU may share this process)
     if (first_use_on_this_device(configured)) BARK_CUDA_CHECK(cudaFuncSetAttribute(umma_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
@@ -398,26 +571,43 @@ static bool launch_gemm(const __half * A, int lda, const __half * W, int ldw, in
 // C = A W^T on the tensor cores.  A [M][lda] f16, W [N][ldw] f16 (both K-contiguous), K % 64 == 0.
 bool fast_gemm(const __half * A, int lda, const __half * W, int ldw, int M, int N, int K, const FastEpi & ep, int n_sm, cudaStream_t s) {
     if (K % kBK != 0 || K < kBK || M < 1 || N < 1) { fprintf(stderr, "bark_b200 fast mode: unsupported GEMM shape %d x %d x %d\n", M, N, K); return false; }
-    // tile width: the widest N tile that still gives every SM a CTA (these GEMMs are 2-10 us of tensor time; occupancy of the
-    // 148 SMs matters more than per-CTA efficiency)
+    // Tile width.  These GEMMs are a few microseconds each, so the choice is about filling 148 SMs, one CTA per SM at a time:
+    //   time(BN) ~ waves x (fixed per-CTA cost + operand bytes of one CTA / per-SM fill rate)
+    // with the measured ~3 us of prologue + epilogue drain per CTA and ~120 GB/s (64 B/clk) from L2 into one SM's shared memory
+    // (profiles/r02_fast_mode.md).  Narrow tiles re-read the 128 activation rows for every column tile, wide tiles leave SMs idle.
     const int tiles_m = (M + kBM - 1) / kBM;
-    if (tiles_m * ((N + 127) / 128) >= n_sm) return launch_gemm<128>(A, lda, W, ldw, M, N, K, ep, s);
-    if (tiles_m * ((N + 63) / 64) >= n_sm || N % 32 != 0 || ep.mode == FEPI_QKV16) return launch_gemm<64>(A, lda, W, ldw, M, N, K, ep, s);
+    auto cost = [&](int bn) {
+        const int tiles = tiles_m * ((N + bn - 1) / bn);
+        return (double)((tiles + n_sm - 1) / n_sm) * (3.0 + (double)(kBM + bn) * K * 2.0 / 120e3);
+    };
+    int best = 256;
+    for (int bn : {128, 64, 32}) {
+        if (bn == 32 && (N % 32 != 0 || ep.mode == FEPI_QKV16)) continue;
+        if (cost(bn) < cost(best) - 1e-9) best = bn;
+    }
+    if (best == 256) return launch_gemm<256>(A, lda, W, ldw, M, N, K, ep, s);
+    if (best == 128) return launch_gemm<128>(A, lda, W, ldw, M, N, K, ep, s);
+    if (best == 64) return launch_gemm<64>(A, lda, W, ldw, M, N, K, ep, s);
     return launch_gemm<32>(A, lda, W, ldw, M, N, K, ep, s);
 }
 
 // att[N][E] (f16) = soft_max(Q K^T / sqrt(64)) V per head; qk: [N][ldq] f16 with Q at column h*64 and K at k_col0 + h*64; vt: V^T [E][N] f16
 bool fast_attention(const __half * qk, int ldq, int k_col0, const __half * vt, int n, int E, int H, __half * out, cudaStream_t s) {
     if (E / H != kHeadD || n % kKeyBlk != 0 || n < kKeyBlk) { fprintf(stderr, "bark_b200 fast mode: attention needs head size 64 and a multiple of 256 positions (got %d heads of %d, %d positions)\n", H, E / H, n); return false; }
-    const size_t smem = FlashSmem::total + 1024;
+    static const bool v1 = [] { const char * e = getenv("BARK_B200_FLASH"); return e && !strcmp(e, "v1"); }();       // the serial first version, for A-B runs
+    const size_t smem = (v1 ? (size_t) FlashSmem::total : (size_t) Flash2Smem::total) + 1024;
     static std::atomic<unsigned long long> configured{0};
-    if (first_use_on_this_device(configured)) BARK_CUDA_CHECK(cudaFuncSetAttribute(flash_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    if (first_use_on_this_device(configured)) {
+        BARK_CUDA_CHECK(cudaFuncSetAttribute(flash_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FlashSmem::total + 1024));
+        BARK_CUDA_CHECK(cudaFuncSetAttribute(flash_attn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) Flash2Smem::total + 1024));
+    }
     CUtensorMap tqk, tvt;
     if (!make_map(&tqk, qk, n, k_col0 + E, ldq, 128) || !make_map(&tvt, vt, E, n, n, 64)) return false;
     const float scale_log2e = (1.0f / sqrtf((float) kHeadD)) * 1.4426950408889634f;
     g_next_flops = 4.0 * (double) n * n * E;
     g_next_bytes = 2.0 * 4.0 * (double) n * E;
-    BARK_LAUNCH(flash_attn_kernel, dim3(n / 128, H), kGemmThreads, smem, s, tqk, tvt, n, k_col0, scale_log2e, out, E);
+    if (v1) BARK_LAUNCH(flash_attn_kernel, dim3(n / 128, H), kGemmThreads, smem, s, tqk, tvt, n, k_col0, scale_log2e, out, E);
+    else    BARK_LAUNCH(flash_attn2_kernel, dim3(n / 128, H), kGemmThreads, smem, s, tqk, tvt, n, k_col0, scale_log2e, out, E);
     return true;
 }
 

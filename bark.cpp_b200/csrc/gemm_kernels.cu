@@ -217,7 +217,7 @@ void lane_gemm_tiled(const DMat & W, const void * act, int act_gs, int rows, con
         BARK_CUDA_CHECK(cudaFuncSetAttribute((lane_gemm_tiled_kernel<__half, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         BARK_CUDA_CHECK(cudaFuncSetAttribute((lane_gemm_tiled_kernel<float, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     }
-    if (!W.p_gm) { fprintf(stderr, "bark_b200: matrix has no group-major copy for the tiled mat-mul\n"); abort(); }
+    if (!W.p_gm) { fprintf(stderr, "bark_b200: matrix has no group-major copy for the tiled mat-mul\n"); throw std::runtime_error("unsupported configuration (see the message above)"); }
     const int n_tiles = ((W.n_out + kBO - 1) / kBO) * ((rows + kBM - 1) / kBM);
     const int grid = min(n_tiles, 2 * n_sm);                   // persistent: two CTAs per SM (registers and shared memory allow exactly that)
     const int w_gs = W.o_pad * kGmGroup;

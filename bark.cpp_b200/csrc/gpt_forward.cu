@@ -55,11 +55,10 @@ static void run_layers(bark_context * ctx, GPTModel & m, int N, int n_past, bool
 void build_decode_tables(bark_context * ctx, GPTModel & m) {
     const int L = m.n_layer, E = m.n_embd;
     // Fixed capacities of gpt_decode_step_kernel: shared-memory vectors of 1024 (x, q / probabilities) and 4096 (activation operand)
-    // floats, 128 phase slots, one soft_max tile per CTA (H * head/16 tiles), 6 score tasks per warp.  A model outside them steps
+    // floats, 128 phase slots, one soft_max tile per CTA (H * head/16 tiles).  A model outside them steps
     // through the per-op kernels instead (same results, slower) — never through a kernel it would overrun.
     const int D = E / m.n_head;
-    m.decode_ok = E <= 1024 && 4 * E <= 4096 && 4 * L + 1 <= 128 && m.block_size <= 1024 && m.n_head * (D / 16) <= ctx->n_sm &&
-                  (long long) m.n_head * m.block_size <= 6ll * ctx->n_sm * 16;
+    m.decode_ok = E <= 1024 && 4 * E <= 4096 && 4 * L + 1 <= 128 && m.block_size <= 1024 && m.n_head * (D / 16) <= ctx->n_sm;
     if (!m.decode_ok) {
         fprintf(stderr, "bark_b200: model (n_embd %d, n_layer %d, n_head %d, block_size %d) exceeds the persistent decode kernel's capacities; decoding with the per-op kernels\n", E, L, m.n_head, m.block_size);
         return;
@@ -83,6 +82,12 @@ void build_decode_tables(bark_context * ctx, GPTModel & m) {
     m.gx = tagged(R * E); m.gq = tagged(R * E); m.gk = tagged((size_t) E); m.gv = tagged((size_t) E); m.gatt = tagged(R * E);
     m.gff = tagged(R * 4 * E); m.gscores = tagged((size_t) m.n_head * m.block_size);
     m.glogits = (float *) ctx_alloc(ctx, (size_t) m.n_out_vocab * 4);
+    {   // adaptive head starts, [n_cta][8] (XT_* order: q, att, x1, ff, x2, scores): start from the measured fixed knobs
+        std::vector<unsigned> init((size_t) ctx->n_sm_total * 8, 0u);
+        for (int c = 0; c < ctx->n_sm_total; c++) { init[(size_t) c * 8 + 1] = ctx->att_ns; init[(size_t) c * 8 + 2] = ctx->first_ns; init[(size_t) c * 8 + 4] = ctx->first_ns; }
+        m.d_adapt = (unsigned *) ctx_alloc(ctx, init.size() * 4);
+        BARK_CUDA_CHECK(cudaMemcpy(m.d_adapt, init.data(), init.size() * 4, cudaMemcpyHostToDevice));
+    }
 }
 
 // one decode token through the persistent kernel
@@ -111,6 +116,7 @@ static void decode_step(bark_context * ctx, GPTModel & m, int token, const int32
     a.E = m.n_embd; a.H = m.n_head; a.L = m.n_layer; a.block_size = m.block_size; a.n_past = n_past; a.token = token; a.lm_lo = lm_lo; a.lm_hi = lm_hi;
     a.token_ptr = d_token; a.n_vocab_in = m.n_in_vocab;
     a.inv_E = 1.0 / (double) m.n_embd;
+    a.adapt = ctx->adapt_on ? m.d_adapt : nullptr;
     a.timing_tid = ctx->timing_tid; a.poll_ns = ctx->poll_ns; a.first_ns = ctx->first_ns; a.att_ns = ctx->att_ns;
     const double es = m.wtype == W_F16 ? 2.0 : 4.0;
     const double E = m.n_embd, L = m.n_layer;

@@ -242,7 +242,7 @@ void lane_matmul(const DMat & W, const void * act, int act_gs, int rows, const M
         if (rows == 1) BARK_LAUNCH((lane_matmul_kernel<float, 1>), dim3(gx, 1), 256, 0, s, (const float *) W.p, W.K, W.Kp, W.n_out, (const float *) act, act_gs, rows, ep);
         else           BARK_LAUNCH((lane_matmul_kernel<float, 8>), dim3(gx, (rows + 7) / 8), 256, 0, s, (const float *) W.p, W.K, W.Kp, W.n_out, (const float *) act, act_gs, rows, ep);
     } else {
-        fprintf(stderr, "bark_b200: q4_0 mul_mat is not built in this revision\n"); abort();
+        fprintf(stderr, "bark_b200: q4_0 mul_mat is not built in this revision\n"); throw std::runtime_error("unsupported configuration (see the message above)");
     }
 }
 
@@ -361,7 +361,7 @@ void attention(const float * Q, const float * Kc, const float * Vc, int N, int n
     else if (D == 32)  BARK_LAUNCH(attn_scores_kernel<1>, (rows + 7) / 8, 256, 0, s, Q, Kc, N, n_kv, n_past, E, H, scale, causal ? 1 : 0, scores);
     else if (D == 96)  BARK_LAUNCH(attn_scores_kernel<3>, (rows + 7) / 8, 256, 0, s, Q, Kc, N, n_kv, n_past, E, H, scale, causal ? 1 : 0, scores);
     else if (D == 128) BARK_LAUNCH(attn_scores_kernel<4>, (rows + 7) / 8, 256, 0, s, Q, Kc, N, n_kv, n_past, E, H, scale, causal ? 1 : 0, scores);
-    else { fprintf(stderr, "bark_b200: unsupported head size %d (need a multiple of 32, <= 128)\n", D); abort(); }
+    else { fprintf(stderr, "bark_b200: unsupported head size %d (need a multiple of 32, <= 128)\n", D); throw std::runtime_error("unsupported configuration (see the message above)"); }
     g_next_bytes = 8.0 * (double) rows * n_kv;
     BARK_LAUNCH(attn_softmax_kernel, (rows + 7) / 8, 256, 0, s, scores, rows, n_kv);
     const int qy = max(1, 256 / D);

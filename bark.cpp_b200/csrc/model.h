@@ -41,6 +41,7 @@ struct GPTModel {
     void * d_phases = nullptr, * d_layer_vecs = nullptr;
     unsigned long long * gx = nullptr, * gq = nullptr, * gk = nullptr, * gv = nullptr, * gatt = nullptr, * gff = nullptr, * gscores = nullptr;
     float * glogits = nullptr;
+    unsigned * d_adapt = nullptr;     // per-CTA adaptive head starts of the exchanges (decode_kernels.cu)
     // per-model statistics, same meaning as gpt_model::t_* (bark.cpp:114-118)
     int64_t t_sample_us = 0, t_predict_us = 0, t_main_us = 0, n_sample = 0;
 };

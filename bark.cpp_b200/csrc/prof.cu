@@ -45,7 +45,7 @@ extern "C" void bark_b200_profile_enable(int on) {
 }
 
 // JSON: {"kernel": {"launches": n, "ms": t, "bytes": b, "flops": f}, ...}; returns the length needed
-extern "C" int bark_b200_profile_report(char * buf, int cap) {
+static int bark_b200_profile_report_impl(char * buf, int cap) {
     BARK_CUDA_CHECK(cudaDeviceSynchronize());
     struct Agg { long n = 0; double ms = 0, bytes = 0, flops = 0; };
     std::map<std::string, Agg> agg;
@@ -66,6 +66,7 @@ extern "C" int bark_b200_profile_report(char * buf, int cap) {
     if (buf && cap > 0) { snprintf(buf, (size_t) cap, "%s", out.c_str()); }
     return (int) out.size() + 1;
 }
+extern "C" int bark_b200_profile_report(char * buf, int cap) { return guarded((int) 0, [&] { return bark_b200_profile_report_impl(buf, cap); }); }
 
 extern "C" void bark_b200_io_counters(unsigned long long * h2d, unsigned long long * d2h, int reset) {
     if (h2d) *h2d = g_h2d_bytes.load();

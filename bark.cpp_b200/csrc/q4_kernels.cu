@@ -99,7 +99,7 @@ void q4_set_scratch(void * q8, void * q8_scales) { g_q8 = (int8_t *) q8; g_q8d =
 
 // act: f32 rows [rows][ld_act] as store_act(W_Q4_0) leaves them
 void q4_matmul(const DMat & W, const void * act, int ld_act, int rows, const MatmulEpilogue & ep, cudaStream_t s) {
-    if (!g_q8 || !g_q8d) { fprintf(stderr, "bark_b200: q4_0 scratch buffers are not set\n"); abort(); }
+    if (!g_q8 || !g_q8d) { fprintf(stderr, "bark_b200: q4_0 scratch buffers are not set\n"); throw std::runtime_error("unsupported configuration (see the message above)"); }
     const int nb = W.K / 32;
     const size_t warps = (size_t) rows * nb;
     BARK_LAUNCH(quantize_q8_kernel, (unsigned)((warps * 32 + 255) / 256), 256, 0, s, (const float *) act, ld_act, rows, W.K, g_q8, g_q8d);

@@ -169,7 +169,7 @@ void qx_embed_fine(const GPTModel & m, const int32_t * d_ids, int nn, float * x,
 
 // act: f32 rows [rows][ld_act] as store_act(W_Q4_0) leaves them
 void qx_matmul(const DMat & W, const void * act, int ld_act, int rows, const MatmulEpilogue & ep, cudaStream_t s) {
-    if (!g_qx_q8 || !g_qx_d || !g_qx_s) { fprintf(stderr, "bark_b200: quantised-weight scratch buffers are not set\n"); abort(); }
+    if (!g_qx_q8 || !g_qx_d || !g_qx_s) { fprintf(stderr, "bark_b200: quantised-weight scratch buffers are not set\n"); throw std::runtime_error("unsupported configuration (see the message above)"); }
     const int nb = W.K / 32;
     const size_t warps = (size_t) rows * nb;
     const bool q81 = W.type == W_Q4_1 || W.type == W_Q5_1;
@@ -183,7 +183,7 @@ void qx_matmul(const DMat & W, const void * act, int ld_act, int rows, const Mat
         case W_Q5_0: BARK_LAUNCH((qx_matmul_kernel<W_Q5_0>), grid, 256, 0, s, qs, qh, wd, wm, W.K, W.n_out, g_qx_q8, g_qx_d, g_qx_s, rows, ep); break;
         case W_Q5_1: BARK_LAUNCH((qx_matmul_kernel<W_Q5_1>), grid, 256, 0, s, qs, qh, wd, wm, W.K, W.n_out, g_qx_q8, g_qx_d, g_qx_s, rows, ep); break;
         case W_Q8_0: BARK_LAUNCH((qx_matmul_kernel<W_Q8_0>), grid, 256, 0, s, qs, qh, wd, wm, W.K, W.n_out, g_qx_q8, g_qx_d, g_qx_s, rows, ep); break;
-        default: fprintf(stderr, "bark_b200: unsupported quantised type %d\n", (int) W.type); abort();
+        default: fprintf(stderr, "bark_b200: unsupported quantised type %d\n", (int) W.type); throw std::runtime_error("unsupported configuration (see the message above)");
     }
 }
 

@@ -155,7 +155,7 @@ bool sample_shard(bark_context * ctx, int n, float temp, int32_t * out_all /*[10
 using namespace bark;
 
 // rank / world of this context in a row-sharded fine stage; writes this rank's 64-byte CUDA IPC handle to handle_out
-extern "C" int bark_b200_shard_init(struct bark_context * ctx, int rank, int world, void * handle_out) {
+static int bark_b200_shard_init_impl(struct bark_context * ctx, int rank, int world, void * handle_out) {
     if (!ctx || !handle_out || world < 1 || world > 8 || rank < 0 || rank >= world || 1024 % world) return 0;
     BARK_CUDA_CHECK(cudaSetDevice(ctx->device));
     ShardState & S = ctx->shard;
@@ -172,9 +172,10 @@ extern "C" int bark_b200_shard_init(struct bark_context * ctx, int rank, int wor
     S.peer[rank] = S.local;
     return 1;
 }
+extern "C" int bark_b200_shard_init(struct bark_context * ctx, int rank, int world, void * handle_out) { return guarded((int) 0, [&] { return bark_b200_shard_init_impl(ctx, rank, world, handle_out); }); }
 
 // all_handles: world x 64 bytes, rank order (what every rank's bark_b200_shard_init returned, all-gathered by the caller)
-extern "C" int bark_b200_shard_connect(struct bark_context * ctx, const void * all_handles) {
+static int bark_b200_shard_connect_impl(struct bark_context * ctx, const void * all_handles) {
     if (!ctx || !all_handles || !ctx->shard.local) return 0;
     BARK_CUDA_CHECK(cudaSetDevice(ctx->device));
     ShardState & S = ctx->shard;
@@ -189,6 +190,7 @@ extern "C" int bark_b200_shard_connect(struct bark_context * ctx, const void * a
     S.on = true;
     return 1;
 }
+extern "C" int bark_b200_shard_connect(struct bark_context * ctx, const void * all_handles) { return guarded((int) 0, [&] { return bark_b200_shard_connect_impl(ctx, all_handles); }); }
 
 extern "C" unsigned long long bark_b200_shard_nvlink_bytes(struct bark_context * ctx, int reset) {
     if (!ctx) return 0;

@@ -20,7 +20,7 @@ MAX_DLOGIT = 0.08                          # fine logits are O(1-5); f16 activat
 MIN_TOP1 = 0.97
 
 
-@pytest.mark.parametrize("M,N,K", [(1024, 2304, 768), (1024, 768, 768), (1024, 768, 3072), (1024, 1056, 768), (257, 2304, 768), (128, 64, 64), (100, 96, 128), (1024, 1024, 4096)])
+@pytest.mark.parametrize("M,N,K", [(1024, 3072, 768), (1024, 2304, 768), (1024, 768, 768), (1024, 768, 3072), (1024, 1056, 768), (257, 2304, 768), (128, 64, 64), (100, 96, 128), (1024, 1024, 4096)])
 def test_umma_gemm_matches_numpy(pkg, M, N, K):
     rng = np.random.default_rng(M * 7 + N * 3 + K)
     A = (rng.standard_normal((M, K)) * 0.5).astype(np.float16)

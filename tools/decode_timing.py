@@ -38,11 +38,16 @@ def measure(pkg, path, pasts, tid, poll, first=0):
         for n_past in pasts:
             toks = rng.integers(10000, 12048, n_past).astype(np.int32)
             _, p = b.gpt_eval(1, toks, 0, False)
-            for _ in range(6):                                   # warm, then keep the last step's stamps
+            for _ in range(int(os.environ.get("WARM_STEPS", "48"))):   # warm (the adaptive head starts settle within ~20 tokens), then keep the last step's stamps
                 _, p = b.gpt_eval(1, np.array([10001], np.int32), p, False)
             t = np.zeros(256 * 32, np.uint64)
             pkg.lib().bark_b200_decode_timing(b.ctx, t.ctypes.data_as(C.c_void_p), t.size)
             t = t.reshape(256, 32).astype(np.int64)
+            ad = np.zeros(148 * 8, np.uint32)
+            if pkg.lib().bark_b200_decode_adapt(b.ctx, 1, ad.ctypes.data_as(C.c_void_p), ad.size) > 0:
+                ad = ad.reshape(148, 8)
+                print("   adaptive head starts (ns), median over CTAs [q, att, x1, ff, x2, scores]:", np.median(ad[:, :6], axis=0).astype(int).tolist(),
+                      " soft_max CTAs (0..47):", np.median(ad[:48, :6], axis=0).astype(int).tolist())
             tag = f"tid{tid}_poll{poll}_first{first}"
             np.save(os.path.join(ROOT, "gpurun_out", f"decode_timing_{p}_{tag}.npy"), t)
             lay = t[:L + 1]
