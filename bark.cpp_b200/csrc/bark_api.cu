@@ -412,7 +412,7 @@ void alloc_workspace(bark_context * ctx) {
     int E = 0, H = 0; size_t kp_bytes = 0, n_logits = 0;
     for (GPTModel * m : {&ctx->semantic, &ctx->coarse, &ctx->fine}) {
         E = std::max(E, (int) m->n_embd); H = std::max(H, (int) m->n_head);
-        const size_t es = m->wtype == W_F16 ? 2 : 4;
+        const size_t es = (m->wtype == W_F16 && !ctx->gemm_f32c) ? 2 : 4;
         kp_bytes = std::max(kp_bytes, (size_t) li_padded_k(4 * m->n_embd, (int) es) * es);
     }
     n_logits = std::max<size_t>({(size_t) ctx->semantic.n_out_vocab, (size_t) ctx->coarse.n_out_vocab, (size_t) 1024 * ctx->fine.n_out_vocab});
@@ -516,6 +516,7 @@ extern "C" struct bark_context * bark_load_model(const char * model_path, struct
     { const char * e = getenv("BARK_B200_POLL_NS"); if (e && atoi(e) >= 0 && atoi(e) <= 100000) ctx->poll_ns = (unsigned) atoi(e); }
     { const char * e = getenv("BARK_B200_POLL_ATT_NS"); if (e && atoi(e) >= 0 && atoi(e) <= 100000) ctx->att_ns = (unsigned) atoi(e); }
     { const char * e = getenv("BARK_B200_POLL_FIRST_NS"); if (e && atoi(e) >= 0 && atoi(e) <= 100000) ctx->first_ns = (unsigned) atoi(e); }
+    { const char * e = getenv("BARK_B200_GEMM_F32C"); ctx->gemm_f32c = e && !strcmp(e, "1"); }
     { const char * e = getenv("BARK_B200_ADAPT"); ctx->adapt_on = e && !strcmp(e, "1"); }                     // "1": self-tuning head starts (experiment; measured WORSE: the feedback is collective and runs away)
     ctx->params = params;
     const bool loaded = guarded(false, [&] {                  // a CUDA failure while loading (out of memory, ...) is a failed load, not an abort

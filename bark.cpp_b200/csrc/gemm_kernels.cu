@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(256, 2) lane_gemm_tiled_kernel(const T * __res
 // packed-FMA variants of the three tiled kernels (see the header comment) unless BARK_B200_FFMA2=0
 static bool use_ffma2() { const char * e = getenv("BARK_B200_FFMA2"); return !(e && e[0] == '0' && e[1] == 0); }   // read per launch so one process can A-B the two
 
-void lane_gemm_tiled(const DMat & W, const void * act, int act_gs, int rows, const MatmulEpilogue & ep, cudaStream_t s) {
+void lane_gemm_tiled(const DMat & W, const void * act, int act_gs, int rows, const MatmulEpilogue & ep, cudaStream_t s, bool f32_containers) {
     const size_t smem = (size_t) kStages * kStageBytes + kStages * 8 + kStages * 4 + 64;
     int dev = 0, n_sm = 0;
     BARK_CUDA_CHECK(cudaGetDevice(&dev));
@@ -216,6 +216,14 @@ void lane_gemm_tiled(const DMat & W, const void * act, int act_gs, int rows, con
         BARK_CUDA_CHECK(cudaFuncSetAttribute(lane_gemm_tiled_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         BARK_CUDA_CHECK(cudaFuncSetAttribute((lane_gemm_tiled_kernel<__half, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         BARK_CUDA_CHECK(cudaFuncSetAttribute((lane_gemm_tiled_kernel<float, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    }
+    if (f32_containers && W.type == W_F16) {                 // f16 values in f32 containers on both sides: the float kernel, bit-identical results
+        if (!W.p_gm32) { fprintf(stderr, "bark_b200: matrix has no f32-expanded copy\n"); throw std::runtime_error("unsupported configuration (see the message above)"); }
+        const int n_tiles32 = ((W.n_out + kBO - 1) / kBO) * ((rows + kBM - 1) / kBM);
+        const int grid32 = min(n_tiles32, 2 * n_sm);
+        if (use_ffma2()) BARK_LAUNCH((lane_gemm_tiled_kernel<float, true>), grid32, 256, smem, s, (const float *) W.p_gm32, W.K, W.o_pad * kGmGroup, W.n_out, (const float *) act, act_gs, rows, ep);
+        else             BARK_LAUNCH((lane_gemm_tiled_kernel<float>), grid32, 256, smem, s, (const float *) W.p_gm32, W.K, W.o_pad * kGmGroup, W.n_out, (const float *) act, act_gs, rows, ep);
+        return;
     }
     if (!W.p_gm) { fprintf(stderr, "bark_b200: matrix has no group-major copy for the tiled mat-mul\n"); throw std::runtime_error("unsupported configuration (see the message above)"); }
     const int n_tiles = ((W.n_out + kBO - 1) / kBO) * ((rows + kBM - 1) / kBM);

@@ -26,12 +26,13 @@ static void run_layers(bark_context * ctx, GPTModel & m, int N, int n_past, bool
     cudaStream_t s = ctx->stream;
     const int E = m.n_embd, H = m.n_head;
     const bool q4 = is_quant(m.wtype);                       // quantised weights: f32 activation rows, quantised to q8 blocks in front of each mat-mul
-    const WType awt = q4 ? W_Q4_0 : m.wtype;                 // what the activation producers are told (store_act)
+    const bool c32 = ctx->gemm_f32c && m.wtype == W_F16 && N >= 16;      // f16 values in f32 containers (tiled mat-mul only)
+    const int awt = q4 ? (int) W_Q4_0 : c32 ? W_F16R32 : (int) m.wtype;  // what the activation producers are told (store_act)
     const int kpE = q4 ? E : ws.max_rows * kGmGroup, kp4E = q4 ? 4 * E : kpE;      // group stride of the group-major activation operands; q4_0: f32 row stride
     if (q4) { q4_set_scratch(ctx->d_q8, ctx->d_q8_scales); qx_set_scratch(ctx->d_q8, ctx->d_q8_scales, ctx->d_q8_sums); }
     for (int il = 0; il < m.n_layer; il++) {
         const GPTLayer & L = m.layers[(size_t) il];
-        layernorm_act(ws.x, N, E, L.ln_1_g, L.ln_1_b, ws.act, awt, kpE, ctx->d_ln_fallbacks, s);
+        layernorm_act(ws.x, N, E, L.ln_1_g, L.ln_1_b, ws.act, (WType) awt, kpE, ctx->d_ln_fallbacks, s);
         float * k_all, * v_all, * k_dst, * v_dst; int n_kv;
         if (causal) {
             k_all = m.mem_k + (size_t) il * m.block_size * E; v_all = m.mem_v + (size_t) il * m.block_size * E;
@@ -40,14 +41,14 @@ static void run_layers(bark_context * ctx, GPTModel & m, int N, int n_past, bool
             k_all = k_dst = ws.kbuf; v_all = v_dst = ws.vbuf; n_kv = N;
         }
         MatmulEpilogue qkv; qkv.mode = EPI_QKV; qkv.out = ws.q; qkv.ldo = E; qkv.k_out = k_dst; qkv.v_out = v_dst;
-        lane_matmul(L.c_attn, ws.act, kpE, N, qkv, s);
-        attention(ws.q, k_all, v_all, N, n_kv, n_past, E, H, causal, ws.scores, ws.act, awt, kpE, s);
+        lane_matmul(L.c_attn, ws.act, kpE, N, qkv, s, c32);
+        attention(ws.q, k_all, v_all, N, n_kv, n_past, E, H, causal, ws.scores, ws.act, (WType) awt, kpE, s);
         MatmulEpilogue res; res.mode = EPI_RESID; res.out = ws.x; res.ldo = E;
-        lane_matmul(L.c_proj, ws.act, kpE, N, res, s);                                                              // + inpL
-        layernorm_act(ws.x, N, E, L.ln_2_g, L.ln_2_b, ws.act, awt, kpE, ctx->d_ln_fallbacks, s);
+        lane_matmul(L.c_proj, ws.act, kpE, N, res, s, c32);                                                             // + inpL
+        layernorm_act(ws.x, N, E, L.ln_2_g, L.ln_2_b, ws.act, (WType) awt, kpE, ctx->d_ln_fallbacks, s);
         MatmulEpilogue ge; ge.mode = EPI_GELU_ACT; ge.act_out = ws.act2; ge.act_wt = (int) awt; ge.act_Kp = kp4E; ge.gelu_tab = ctx->d_gelu_tab;
-        lane_matmul(L.fc, ws.act, kpE, N, ge, s);
-        lane_matmul(L.proj, ws.act2, kp4E, N, res, s);                                                                // + inpFF
+        lane_matmul(L.fc, ws.act, kpE, N, ge, s, c32);
+        lane_matmul(L.proj, ws.act2, kp4E, N, res, s, c32);                                                               // + inpFF
     }
 }
 
@@ -206,9 +207,10 @@ bool fine_eval(bark_context * ctx, const int32_t * in_buffer, int nn, float * lo
     gpt_embed_fine(m, ws.tok, nn, ws.x, s);
     run_layers(ctx, m, N, 0, false);
     const int kpE = is_quant(m.wtype) ? E : ws.max_rows * kGmGroup;
-    layernorm_act(ws.x, N, E, m.ln_f_g, m.ln_f_b, ws.act, is_quant(m.wtype) ? W_Q4_0 : m.wtype, kpE, ctx->d_ln_fallbacks, s);
+    const bool c32 = ctx->gemm_f32c && m.wtype == W_F16;
+    layernorm_act(ws.x, N, E, m.ln_f_g, m.ln_f_b, ws.act, is_quant(m.wtype) ? W_Q4_0 : c32 ? (WType) W_F16R32 : m.wtype, kpE, ctx->d_ln_fallbacks, s);
     MatmulEpilogue st; st.mode = EPI_STORE; st.out = ws.logits; st.ldo = m.n_out_vocab;
-    lane_matmul(m.lm_head[nn - 1], ws.act, kpE, N, st, s);                                                           // n_codes_given = 1 (bark.cpp:61,1573)
+    lane_matmul(m.lm_head[nn - 1], ws.act, kpE, N, st, s, c32);                                                           // n_codes_given = 1 (bark.cpp:61,1573)
     ctx->last_logits = ws.logits;
     if (logits_host) {
         const size_t nb = (size_t) N * m.n_out_vocab * sizeof(float);
