@@ -199,7 +199,7 @@ bool run_chain(bark_context * ctx, GPTModel & m, const std::vector<int32_t> & fi
         for (int j = 0; j < n; j++) ctx->h_u[j] = std::generate_canonical<double, 53>(ctx->rng);     // one draw per sample, as discrete_distribution::operator() makes
         BARK_CUDA_CHECK(cudaMemcpyAsync(ctx->d_u, ctx->h_u, (size_t) n * sizeof(double), cudaMemcpyHostToDevice, s)); bark::g_h2d_bytes += (size_t) n * sizeof(double);
     }
-    const bool chain = ctx->use_decode_kernel && m.decode_ok && !is_quant(m.wtype);
+    const bool chain = ctx->use_decode_kernel && m.decode_ok;
     std::vector<int> past_before((size_t) n);
     std::vector<int32_t> cur_in = first_in;
     std::vector<float> host_logits;
@@ -511,7 +511,7 @@ extern "C" struct bark_context * bark_load_model(const char * model_path, struct
     { const char * e = getenv("BARK_B200_SAMPLE_FLAG_EVERY"); ctx->debug_flag_every = e ? atoi(e) : 0; }
     { const char * e = getenv("BARK_B200_SAMPLE"); ctx->sample_on_device = !(e && !strcmp(e, "host")); }      // "host": read logits back and sample on the CPU (A-B)
     { const char * e = getenv("BARK_B200_KV_REUSE"); ctx->kv_reuse = !(e && !strcmp(e, "0")); }              // "0": re-prefill every coarse window like the reference (A-B)
-    { const char * e = getenv("BARK_B200_DECODE"); ctx->use_decode_kernel = !(e && !strcmp(e, "multi")); }   // "multi": one kernel per op (debug / A-B)
+    { const char * e = getenv("BARK_B200_DECODE"); ctx->use_decode_kernel = !(e && !strcmp(e, "multi")); ctx->decode_cluster = e && !strcmp(e, "cluster"); }   // "multi": one kernel per op (debug / A-B)
     { const char * e = getenv("BARK_B200_DECODE_TIMING_TID"); if (e && atoi(e) >= 0 && atoi(e) < 512) ctx->timing_tid = atoi(e) & ~31; }
     { const char * e = getenv("BARK_B200_POLL_NS"); if (e && atoi(e) >= 0 && atoi(e) <= 100000) ctx->poll_ns = (unsigned) atoi(e); }
     { const char * e = getenv("BARK_B200_POLL_ATT_NS"); if (e && atoi(e) >= 0 && atoi(e) <= 100000) ctx->att_ns = (unsigned) atoi(e); }

@@ -61,13 +61,14 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm vo
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) return;
+    const long long t0 = clock64();                          // slow path only: a protocol bug must trap, not hang the GPU
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (!done && clock64() - t0 > 4000000000ll) __trap();
+    }
 }
 // one bulk copy global -> shared, completion counted on `bar`, L2 evict-first (the weight stream is read once per token)
 __device__ __forceinline__ void tma_bulk_g2s_stream(uint32_t dst, const void * src, uint32_t bytes, uint32_t bar, unsigned long long policy) {
@@ -224,7 +225,7 @@ __device__ __forceinline__ double approx_rcp(double x) {
 // takes the rounding decision itself (identical inputs, identical arithmetic -> identical result), instead of funnelling
 // through warp 0 and a second barrier.  red: [0,16) double mean partials, [16,24) 16 float |x| partials, [24,40) double
 // variance partials.
-template <bool ROUND16, bool TM>
+template <bool ROUND16, bool TM, bool NATURAL = false>
 __device__ __noinline__ void block_layernorm(const float * xs, int E, double inv_E, const float * __restrict__ g, const float * __restrict__ b, float * act,
                                              double * red, unsigned * fallback_counter, int sb) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -296,14 +297,14 @@ __device__ __noinline__ void block_layernorm(const float * xs, int E, double inv
         }
         scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(variance, 1e-5f)));
     }
-    if (h0) { float y = __fmul_rn(__fmul_rn(v0, scale), g0); if (b) y = __fadd_rn(y, b0); act[act_index(i0)] = ROUND16 ? round_f16(y) : y; }
-    if (h1) { float y = __fmul_rn(__fmul_rn(v1, scale), g1); if (b) y = __fadd_rn(y, b1); act[act_index(i1)] = ROUND16 ? round_f16(y) : y; }
+    if (h0) { float y = __fmul_rn(__fmul_rn(v0, scale), g0); if (b) y = __fadd_rn(y, b0); act[NATURAL ? i0 : act_index(i0)] = ROUND16 ? round_f16(y) : y; }
+    if (h1) { float y = __fmul_rn(__fmul_rn(v1, scale), g1); if (b) y = __fadd_rn(y, b1); act[NATURAL ? i1 : act_index(i1)] = ROUND16 ? round_f16(y) : y; }
     __syncthreads();
 }
 
 // Per-CTA row ranges of every phase, built once per launch in shared memory (the divisions and table look-ups they replace
 // cost ~2 us of single-thread time per phase when done on the fly).
-struct PhaseSched { int r0, r1, K, row_bytes; const unsigned char * w; int pad[2]; };   // rows [r0, r1) of this phase belong to this CTA
+struct PhaseSched { int r0, r1, K, row_bytes; const unsigned char * w; const unsigned char * ws; };   // rows [r0, r1) of this phase belong to this CTA
 
 enum { EP_QKV = 0, EP_RESID = 1, EP_GELU = 2, EP_LOGITS = 3 };
 
@@ -390,6 +391,70 @@ __device__ __forceinline__ void row_dot(const unsigned char * row, int row_bytes
     for (int n = 0; n < NR; n++) out[n] = lane_tree_reduce(acc[n]);
 }
 
+// ---- q4_0 weights (BASELINE configs[3]) ---------------------------------------------------------------------------------------------
+// WT = Q4: the phase streams 16-byte nibble words [rows][K/32] plus f16 block scales [rows][K/32]; the activation operand is the
+// q8_0 quantisation of the f32 vector (quantize_row_q8_0, ggml-quants.c:944-1000); a dot product is ggml_vec_dot_q4_0_q8_0's AVX2
+// flavour (ggml-quants.c:4191-4214): eight float accumulators per output, one fused multiply-add per block, hsum_float_8.  Same
+// arithmetic as q4_kernels.cu (the per-op path), here inside the persistent step: eight lanes own one output, a warp four rows.
+struct Q4 {};
+template <typename WT> struct IsQ4 { static constexpr bool v = false; };
+template <> struct IsQ4<Q4> { static constexpr bool v = true; };
+
+// act (f32, natural order) -> int8 q[K] + f32 d[K/32] (the f16-rounded scale, widened back); block-wide, one warp per 32-element block
+__device__ __forceinline__ void quantize_act_q8(const float * act, int K, int8_t * q, float * d) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int b = warp; b < (K >> 5); b += kWarps) {
+        const float v = act[b * 32 + lane];
+        float amax = fabsf(v);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        const float id = amax != 0.0f ? __fdiv_rn(127.0f, amax) : 0.0f;
+        q[b * 32 + lane] = (int8_t) __float2int_rn(__fmul_rn(v, id));
+        if (lane == 0) d[b] = __half2float(__float2half_rn(__fdiv_rn(amax, 127.0f)));
+    }
+    __syncthreads();
+}
+
+// up to 4 adjacent q4_0 rows against the q8 operand; every lane of group g = lane / 8 returns the result of row g
+template <bool SH>
+__device__ __forceinline__ float row_dot_q4(const unsigned char * qrows, const unsigned char * srows, int nrows, int nb, const int8_t * aq, const float * ad, int lane) {
+    const int l = lane & 7, row = min(lane >> 3, nrows - 1);
+    const bool high = l >= 4;
+    const unsigned char * wq = qrows + (size_t) row * nb * 16 + (l & 3) * 4;
+    const unsigned char * ws = srows + (size_t) row * nb * 2;
+    const int * a32 = reinterpret_cast<const int *>(aq);
+    float acc = 0.0f;
+    constexpr int UB = 8;
+    for (int b0 = 0; b0 < nb; b0 += UB) {
+        uint32_t wr[UB]; float dwr[UB];
+#pragma unroll
+        for (int u = 0; u < UB; u++) if (b0 + u < nb) {
+            if (SH) { asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wr[u]) : "r"(smem_u32(wq) + (b0 + u) * 16) : "memory"); dwr[u] = __half2float(*reinterpret_cast<const __half *>(ws + (b0 + u) * 2)); }
+            else    { wr[u] = __ldg(reinterpret_cast<const uint32_t *>(wq + (size_t)(b0 + u) * 16)); dwr[u] = __half2float(__ldg(reinterpret_cast<const __half *>(ws + (size_t)(b0 + u) * 2))); }
+        }
+#pragma unroll
+        for (int u = 0; u < UB; u++) {
+            const int b = b0 + u;
+            if (b < nb) {
+                const uint32_t w = (high ? (wr[u] >> 4) : wr[u]) & 0x0f0f0f0fu;
+                const int wi = (int) __vsub4(w, 0x08080808u);
+                acc = __fmaf_rn(__fmul_rn(dwr[u], ad[b]), (float) __dp4a(wi, a32[b * 8 + l], 0), acc);
+            }
+        }
+    }
+    acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 4));      // hsum_float_8 (ggml-quants.c:48-54)
+    acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 2));
+    acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 1));
+    return acc;
+}
+// dequantize_row_q4_0 (ggml-quants.c:1515-1533) of one element of a wte row kept in the file's 18-byte blocks
+__device__ __forceinline__ float wte_q4_value(const void * wte, int E, int row, int i) {
+    const unsigned char * blk = (const unsigned char *) wte + ((size_t) row * (E >> 5) + (i >> 5)) * 18;
+    const float d = __half2float(__ushort_as_half((unsigned short)(blk[0] | (blk[1] << 8))));
+    const int j = i & 31, q = j < 16 ? (blk[2 + j] & 0x0f) : (blk[2 + j - 16] >> 4);
+    return __fmul_rn((float)(q - 8), d);
+}
+
 constexpr int kMaxTasks = 8;        // (h, k) score tasks per warp with their K rows prefetched: H * block_size / (n_score_cta * kWarps) = 12 * 1024 / (100 * 16) < 8 (bark-small);
                                     // beyond that (bark-large past n_kv = 672) the remaining tasks run without the prefetch
 
@@ -413,6 +478,12 @@ __device__ __forceinline__ void warp_rows(const PhaseSched & p, int warp, int & 
     a = p.r0 + ((warp * n) >> 4); b = p.r0 + (((warp + 1) * n) >> 4);
 }
 
+// q4_0 rows are staged when both pieces fit a half and satisfy the bulk copy's 16-byte size / address granularity (tiny test models
+// with K < 256 have 8-byte scale rows: those phases read from global memory instead)
+__device__ __forceinline__ bool q4_staged(uint32_t qbytes, uint32_t sbytes, const unsigned char * ssrc) {
+    return qbytes != 0 && qbytes + sbytes <= (uint32_t) kHalfSlotBytes && (sbytes & 15u) == 0 && (reinterpret_cast<uintptr_t>(ssrc) & 15u) == 0;
+}
+
 // Lane 0: start the bulk copy of this warp's rows of `phase` into half (phase & 1) of its staging area and arm that half's
 // mbarrier.  The barrier is armed exactly once per phase (with or without bytes), so use k of a half completes barrier
 // phase k and run_phase waits on parity (phase >> 1) & 1.  Rows that do not fit (lm_head over the whole vocabulary, K = 4096
@@ -424,10 +495,24 @@ __device__ __forceinline__ void stage_rows(int phase) {
     int a, b; warp_rows(p, warp, a, b);
     const uint32_t bytes = (uint32_t)((b - a) * p.row_bytes);
     const uint32_t bar = smem_u32(&s_bar[warp][half]);
+    const uint32_t dst = smem_u32(dsm + SmemLayout::wslot) + warp * kWarpSlotBytes + half * kHalfSlotBytes;
+    if (p.ws) {                                              // q4_0: nibble words, then the f16 block scales behind them (two bulk copies, one barrier)
+        const uint32_t sbytes = (uint32_t)((b - a) * (p.K >> 5) * 2);
+        const unsigned char * ssrc = p.ws + (size_t) a * (p.K >> 5) * 2;
+        if (q4_staged(bytes, sbytes, ssrc)) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(bar, bytes + sbytes);
+            tma_bulk_g2s_stream(dst, p.w + (size_t) a * p.row_bytes, bytes, bar, s_bc.policy);
+            tma_bulk_g2s_stream(dst + bytes, ssrc, sbytes, bar, s_bc.policy);
+        } else {
+            mbar_arrive(bar);
+        }
+        return;
+    }
     if (bytes != 0 && bytes <= (uint32_t) kHalfSlotBytes) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // this half was just read through the generic proxy
         mbar_expect_tx(bar, bytes);
-        tma_bulk_g2s_stream(smem_u32(dsm + SmemLayout::wslot) + warp * kWarpSlotBytes + half * kHalfSlotBytes, p.w + (size_t) a * p.row_bytes, bytes, bar, s_bc.policy);
+        tma_bulk_g2s_stream(dst, p.w + (size_t) a * p.row_bytes, bytes, bar, s_bc.policy);
     } else {
         mbar_arrive(bar);
     }
@@ -466,6 +551,33 @@ __device__ __noinline__ void run_phase(int phase, int ep, int layer, uint32_t ot
         }
     };
     auto gelu_sel = [](float v, __half t) { return v <= -10.0f ? 0.0f : v >= 10.0f ? v : __half2float(t); };   // ggml_vec_gelu_f32, ggml.c:2557-2571
+    if constexpr (IsQ4<WT>::v) {
+        // four adjacent rows per pass (eight lanes per row); operand = the q8 blocks quantize_act_q8 left in shared memory
+        const int nb = p.K >> 5;
+        const int8_t * aq = reinterpret_cast<const int8_t *>(dsm + SmemLayout::q);
+        const float * ad = reinterpret_cast<const float *>(dsm + SmemLayout::part) + 512;
+        const uint32_t sbytes = (uint32_t)((b - a) * nb * 2);
+        const unsigned char * ssrc = p.ws + (size_t) a * nb * 2;
+        const bool st4 = q4_staged(bytes, sbytes, ssrc);
+        for (int r = a; r < b; r += 4) {
+            const int n = min(4, b - r);
+            const float t = st4 ? row_dot_q4<true>(slot + (size_t)(r - a) * p.row_bytes, slot + bytes + (size_t)(r - a) * nb * 2, n, nb, aq, ad, lane)
+                                : row_dot_q4<false>(p.w + (size_t) r * p.row_bytes, p.ws + (size_t) r * nb * 2, n, nb, aq, ad, lane);
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+                const float v = __shfl_sync(0xffffffffu, t, g * 8);
+                if (g < n && lane < kReplicas) {
+                    if (ep == EP_GELU) publish_all(s_bc.gff, 4 * E, r + g, gelu_sel(v, s_bc.gelu_tab[__half_as_ushort(__float2half_rn(v))]), otag, lane);
+                    else emit(r + g, v);
+                }
+            }
+        }
+        __syncwarp();
+        tstamp<TM>(sb + 1);
+        stage_rows(phase + 2);
+        tstamp<TM>(sb + 2);
+        return;
+    } else {
     int j = 0;
     for (int r = a; r < b;) {
         const unsigned char * row = staged ? slot + (size_t) j * p.row_bytes : p.w + (size_t) r * p.row_bytes;
@@ -494,6 +606,7 @@ __device__ __noinline__ void run_phase(int phase, int ep, int layer, uint32_t ot
     tstamp<TM>(sb + 1);
     stage_rows(phase + 2);
     tstamp<TM>(sb + 2);
+    }
 }
 
 }  // namespace
@@ -509,8 +622,11 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int D = DSTEPS * 32;
     const int E = A.E, H = A.H, L = A.L, ctx = A.block_size, n_past = A.n_past, n_kv = n_past + 1;
-    constexpr bool kRound = sizeof(WT) == 2;
-    constexpr int kSinkAct = kRound ? SINK_ACT_R16 : SINK_ACT;
+    constexpr bool kQ4 = IsQ4<WT>::v;
+    constexpr bool kRound = !kQ4 && sizeof(WT) == 2;
+    constexpr int kSinkAct = kQ4 ? SINK_PLAIN : kRound ? SINK_ACT_R16 : SINK_ACT;     // q4_0: the f32 vector in natural order, quantised to q8 blocks below
+    int8_t * act_q = reinterpret_cast<int8_t *>(dsm + SmemLayout::q);                  // q4_0 operand: aliases the q / probabilities row (free during the row phases)
+    float * act_d = reinterpret_cast<float *>(dsm + SmemLayout::part) + 512;
 
     // ---- per-CTA row ranges, block context and the staging barriers in shared memory ----
     PhaseSched * sched = reinterpret_cast<PhaseSched *>(dsm + SmemLayout::sched);
@@ -522,7 +638,7 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
         const int n = hi - lo, G = gridDim.x, base = n / G, rem = n % G, cta = blockIdx.x;
         PhaseSched e;
         e.r0 = lo + cta * base + min(cta, rem); e.r1 = e.r0 + base + (cta < rem ? 1 : 0);      // balanced split: floor or ceil of n / G rows
-        e.K = ph.K; e.row_bytes = ph.row_bytes; e.w = (const unsigned char *) ph.w; e.pad[0] = e.pad[1] = 0;
+        e.K = ph.K; e.row_bytes = ph.row_bytes; e.w = (const unsigned char *) ph.w; e.ws = (const unsigned char *) ph.ws;
         sched[tid] = e;
     }
     if (tid == kThreads - 1) {
@@ -550,7 +666,7 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
     // embedding of the one new token (bark.cpp:1226-1228, 1259): every CTA keeps its own copy of the residual stream
     const int token = A.token_ptr ? min(max(__ldcg(A.token_ptr), 0), A.n_vocab_in - 1) : A.token;
     for (int i = tid; i < E; i += kThreads) {
-        const float t = kRound ? __half2float(((const __half *) A.wte)[(size_t) token * E + i]) : ((const float *) A.wte)[(size_t) token * E + i];
+        const float t = kQ4 ? wte_q4_value(A.wte, E, token, i) : kRound ? __half2float(((const __half *) A.wte)[(size_t) token * E + i]) : ((const float *) A.wte)[(size_t) token * E + i];
         xs[i] = __fadd_rn(t, A.wpe[(size_t) n_past * E + i]);
     }
     __syncthreads();
@@ -574,7 +690,8 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
         if (tid == A.timing_tid) s_tim_layer = il;           // (the stamping thread is the only reader)
         tstamp<TM>(0);
         // ---- P1: LN1 -> QKV ----
-        block_layernorm<kRound, TM>(xs, E, inv_E, lv.ln_1_g, lv.ln_1_b, act, red, A.ln_fallbacks, 1);
+        block_layernorm<kRound, TM, kQ4>(xs, E, inv_E, lv.ln_1_g, lv.ln_1_b, act, red, A.ln_fallbacks, 1);
+        if constexpr (kQ4) quantize_act_q8(act, E, act_q, act_d);
         tstamp<TM>(2);
         run_phase<WT, TM>(4 * il + 0, EP_QKV, il, t_qkv, 3);
 
@@ -593,6 +710,7 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
         // ---- P2: scores.  K rows of older positions are fetched before q arrives.  The CTAs that own a soft_max tile (P3) take no
         // score tasks when enough other CTAs exist: they are the critical path of the layer (they still have the whole of P3 to do
         // once the scores exist), and the V prefetch above already keeps their load queues busy. ----
+        if constexpr (kQ4) __syncthreads();                    // the q8 operand aliases `qs`: every warp must be done with its QKV rows before q lands there
         if (score_cta) {
             const float * Kc = A.mem_k + (size_t) il * ctx * E;
             const int total = H * n_kv, gw = (int)(blockIdx.x - score_cta0) * kWarps + warp, nw = (int)(gridDim.x - score_cta0) * kWarps;
@@ -754,13 +872,15 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
 
         // ---- P4: c_proj + residual ----
         consume_to_smem<2>(s_bc.gatt, E, t_att, act, kSinkAct, XT_ATT);    // (CTAs without a soft_max tile would otherwise poll for the whole of P3)
+        if constexpr (kQ4) quantize_act_q8(act, E, act_q, act_d);
         tstamp<TM>(17);
         run_phase<WT, TM>(4 * il + 1, EP_RESID, il, t_x1, 18);
 
         // ---- P5: LN2 -> c_fc -> GELU ----
         consume_to_smem<2>(s_bc.gx, E, t_x1, xs, SINK_PLAIN, XT_X1);
         tstamp<TM>(21);
-        block_layernorm<kRound, TM>(xs, E, inv_E, lv.ln_2_g, lv.ln_2_b, act, red, A.ln_fallbacks, 22);
+        block_layernorm<kRound, TM, kQ4>(xs, E, inv_E, lv.ln_2_g, lv.ln_2_b, act, red, A.ln_fallbacks, 22);
+        if constexpr (kQ4) quantize_act_q8(act, E, act_q, act_d);
         tstamp<TM>(23);
         run_phase<WT, TM>(4 * il + 2, EP_GELU, il, t_ff, 24);
         __syncthreads();                                         // the ff vector lands in `act`, which slower warps may still be reading
@@ -768,6 +888,7 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
 
         // ---- P6: mlp/c_proj + residual ----
         consume_to_smem<8>(s_bc.gff, 4 * E, t_ff, act, kSinkAct, XT_FF);
+        if constexpr (kQ4) quantize_act_q8(act, 4 * E, act_q, act_d);
         tstamp<TM>(28);
         run_phase<WT, TM>(4 * il + 3, EP_RESID, il, t_x2, 29);
 
@@ -776,10 +897,386 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
     if (tid == A.timing_tid) s_tim_layer = L;                 // row L: start of the final norm
     // ---- final norm + lm_head window ----
     tstamp<TM>(0);
-    block_layernorm<kRound, TM>(xs, E, inv_E, A.ln_f_g, A.ln_f_b, act, red, A.ln_fallbacks, 1);
+    block_layernorm<kRound, TM, kQ4>(xs, E, inv_E, A.ln_f_g, A.ln_f_b, act, red, A.ln_fallbacks, 1);
+    if constexpr (kQ4) quantize_act_q8(act, E, act_q, act_d);
     tstamp<TM>(2);
     run_phase<WT, TM>(4 * L, EP_LOGITS, 0, 0, 3);
     if (A.adapt && tid < XT_COUNT) A.adapt[blockIdx.x * XT_COUNT + tid] = s_adapt[tid];      // (last changed a whole phase ago, by thread 0)
+}
+
+// =====================================================================================================================
+// Decode step, CLUSTER version (BARK_B200_DECODE=cluster, bark-small-sized f16 models): the whole token inside ONE thread-block
+// cluster of 16 CTAs.
+//
+// Why: in the 148-CTA kernel above every grid-wide dependency costs 1.3-2 us through L2 (store -> visible -> polled; 7 per layer,
+// ~45 % of the token) and polling itself slows the producers.  Inside a cluster a dependency is "store into the 16 CTAs' shared
+// memory (DSMEM) + barrier.cluster" = 0.3-0.5 us, with no polling at all.  The price is bandwidth: 16 SMs pull 94 GB/s each
+// (profiles/r02_stream_bw_per_sm.txt) = 1.5 TB/s, so the 188 MB of weights bound a token at ~125 us instead of 31 us.  At today's
+// 270 us per token that trade is a clear win; the kernel is bandwidth-bound on purpose.
+//
+//   * CTA h owns head h: its warps compute exactly the q / k / v rows of that head (4 + 4 + 4 rows per warp for 64-wide heads), so
+//     LN1 -> QKV -> scores -> soft_max -> P.V runs inside one CTA with block barriers only.  The 64 attention outputs are stored into
+//     all 16 CTAs' operand buffers (DSMEM), then ONE cluster barrier.
+//   * c_proj, c_fc and mlp/c_proj rows are split evenly over the 16 CTAs; every result is stored into all 16 copies of the vector it
+//     belongs to (residual stream, MLP activations), then a cluster barrier: 4 barriers per layer, no tagged words, no polling.
+//   * Weights stream per warp in batches of <= 6 KB (<= 4 rows) through the same two-half staging area, two batches ahead of use,
+//     continuously across phase boundaries (the stream does not depend on activations).
+//   * Arithmetic, orders and rounding are those of the kernel above (same row_dot, LayerNorm, soft_max code): results are bit-identical.
+// =====================================================================================================================
+namespace {
+
+constexpr int kCl = 16;                                   // CTAs of the cluster
+struct Smem2 {
+    static constexpr int wslot = 0;                                   // kWarps x 12 KB staging
+    static constexpr int act_ln = wslot + kWarps * kWarpSlotBytes;    // LayerNorm output operand (two-plane LI), <= 1024 floats, local
+    static constexpr int act_att = act_ln + 1024 * 4;                 // attention output operand, gathered from the head CTAs
+    static constexpr int act_ff = act_att + 1024 * 4;                 // GELU(fc) operand, <= 4096 floats; the attention scratch (probabilities) aliases it
+    static constexpr int x = act_ff + 4096 * 4;                       // residual stream
+    static constexpr int qkv = x + 1024 * 4;                          // q | k_new | v_new of this CTA's head, 3 x 128 floats
+    static constexpr int red = qkv + 3 * 128 * 4;
+    static constexpr int plan = red + (kWarps + kWarps / 2 + kWarps + 4) * 8;
+    static constexpr int phases = plan + 64 * 4;                      // copy of the phase table (<= 128 x 32 B): one L2 round trip per batch otherwise
+    static constexpr int total = phases + 128 * 32;
+};
+static_assert(sizeof(DecodePhase) == 32, "phase table entry size");
+
+__device__ __forceinline__ uint32_t mapa(uint32_t saddr, uint32_t rank) { uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank)); return r; }
+__device__ __forceinline__ void st_cluster_f32(uint32_t raddr, float v) { asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(raddr), "f"(v) : "memory"); }
+__device__ __forceinline__ void cluster_sync_all() { asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+// lanes 0..15 store v at the same shared-memory offset of all 16 CTAs
+__device__ __forceinline__ void bcast_f32(uint32_t laddr, float v, int lane) { if (lane < kCl) st_cluster_f32(mapa(laddr, (uint32_t) lane), v); }
+
+// Per-CTA plan: row ranges of the evenly split phases and batch counts, in shared memory (ints):
+//   [0] rq (q/k/v rows per warp per segment), [1] maxr_E, [2] maxr_4E, [3] nb_qkv, [4] nb_cproj, [5] nb_fc, [6] nb_proj, [7] nb_layer, [8] nb_lm,
+//   [9] head0 row (h * D), [10..11] c_proj r0 r1, [12..13] fc r0 r1, [14..15] proj r0 r1, [16..17] lm r0 r1 (CTA ranges; warps slice them)
+struct Batch { const unsigned char * src; int r0, n, bytes; };
+__device__ __forceinline__ void split16(int r0, int r1, int w, int & a, int & b) { const int n = r1 - r0; a = r0 + ((w * n) >> 4); b = r0 + (((w + 1) * n) >> 4); }
+__device__ __forceinline__ int nbatches(int rows, int maxr) { return (rows + maxr - 1) / maxr; }
+
+// batch `seq` of warp `warp` in stream order: per layer QKV (3 segments) | c_proj | fc | proj, then the lm_head window
+__device__ __forceinline__ int decode_batch(const int * P, const DecodePhase * ph, int L, int E, int warp, int seq, Batch & bt, int & kind, int & layer) {
+    const int nbL = P[7];
+    int p;
+    if (seq < L * nbL) {
+        layer = seq / nbL; int r = seq - layer * nbL;
+        const int rq = P[0], per_seg = nbatches(rq, P[1]);
+        if (r < P[3]) {                                       // QKV: segment s, batch i
+            const int s = r / per_seg, i = r - s * per_seg;
+            p = 4 * layer; kind = 0;
+            bt.r0 = s * E + P[9] + warp * rq + i * P[1]; bt.n = min(P[1], rq - i * P[1]);
+        } else {
+            r -= P[3];
+            int a, b, maxr;
+            if (r < P[4]) { p = 4 * layer + 1; kind = 1; split16(P[10], P[11], warp, a, b); maxr = P[1]; }
+            else if ((r -= P[4]) < P[5]) { p = 4 * layer + 2; kind = 2; split16(P[12], P[13], warp, a, b); maxr = P[1]; }
+            else { r -= P[5]; p = 4 * layer + 3; kind = 3; split16(P[14], P[15], warp, a, b); maxr = P[2]; }
+            bt.r0 = a + r * maxr; bt.n = min(maxr, b - bt.r0);
+        }
+    } else {
+        const int r = seq - L * nbL; layer = L; p = 4 * L; kind = 4;
+        int a, b; split16(P[16], P[17], warp, a, b);
+        bt.r0 = a + r * P[1]; bt.n = min(P[1], b - bt.r0);
+    }
+    const DecodePhase d = ph[p];
+    bt.src = (const unsigned char *) d.w + (size_t) bt.r0 * d.row_bytes; bt.bytes = bt.n * d.row_bytes;
+    return p;
+}
+
+}  // namespace
+
+template <typename WT, int DSTEPS>
+__global__ void __launch_bounds__(kThreads, 1) gpt_decode_cluster_kernel(DecodeArgs A) {
+    float * act_ln = reinterpret_cast<float *>(dsm + Smem2::act_ln);
+    float * act_att = reinterpret_cast<float *>(dsm + Smem2::act_att);
+    float * act_ff = reinterpret_cast<float *>(dsm + Smem2::act_ff);
+    float * xs = reinterpret_cast<float *>(dsm + Smem2::x);
+    float * qkv = reinterpret_cast<float *>(dsm + Smem2::qkv);
+    double * red = reinterpret_cast<double *>(dsm + Smem2::red);
+    float * bc = reinterpret_cast<float *>(red + kWarps + kWarps / 2 + kWarps);
+    int * P = reinterpret_cast<int *>(dsm + Smem2::plan);
+    DecodePhase * phs = reinterpret_cast<DecodePhase *>(dsm + Smem2::phases);
+    float * probs = act_ff;                                   // attention scratch: [1024] scores -> exp(score - max)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int D = DSTEPS * 32;
+    const int E = A.E, H = A.H, L = A.L, ctx = A.block_size, n_past = A.n_past, n_kv = n_past + 1;
+    constexpr bool kRound = sizeof(WT) == 2;
+    const int cr = (int) cluster_rank();
+    const bool head_cta = cr < H;
+
+    if (tid == 0) {
+        const int rowb_E = A.phases[0].row_bytes, rowb_4E = A.phases[3].row_bytes;
+        P[0] = D / 16; P[1] = max(1, kHalfSlotBytes / rowb_E); P[2] = max(1, kHalfSlotBytes / rowb_4E);
+        P[9] = cr * D;
+        auto even = [&](int n, int lo, int & r0, int & r1) { const int base = n / kCl, rem = n % kCl; r0 = lo + cr * base + min(cr, rem); r1 = r0 + base + (cr < rem ? 1 : 0); };
+        even(E, 0, P[10], P[11]); even(4 * E, 0, P[12], P[13]); even(E, 0, P[14], P[15]); even(A.lm_hi - A.lm_lo, A.lm_lo, P[16], P[17]);
+        s_bc.policy = l2_evict_first_policy();
+        s_bc.gelu_tab = A.gelu_tab; s_bc.mem_k = A.mem_k; s_bc.mem_v = A.mem_v; s_bc.logits = A.logits;
+        s_bc.E = E; s_bc.ctx = ctx; s_bc.n_past = n_past; s_bc.n_phases = 4 * L + 1;
+    }
+    if (lane == 0) {
+        mbar_init(smem_u32(&s_bar[warp][0]), 1); mbar_init(smem_u32(&s_bar[warp][1]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < 4 * L + 1; i += kThreads) phs[i] = A.phases[i];
+    __syncthreads();
+    // per-warp batch counts (every warp of a CTA has the same: the even splits differ by at most one row, which nbatches absorbs only
+    // if we take the maximum -> count per WARP instead)
+    int wa, wb;
+    split16(P[10], P[11], warp, wa, wb); const int nb_cproj = nbatches(wb - wa, P[1]);
+    split16(P[12], P[13], warp, wa, wb); const int nb_fc = nbatches(wb - wa, P[1]);
+    split16(P[14], P[15], warp, wa, wb); const int nb_proj = nbatches(wb - wa, P[2]);
+    split16(P[16], P[17], warp, wa, wb); const int nb_lm = nbatches(wb - wa, P[1]);
+    const int nb_qkv = head_cta ? 3 * nbatches(P[0], P[1]) : 0;
+    const int nb_layer = nb_qkv + nb_cproj + nb_fc + nb_proj, nb_total = L * nb_layer + nb_lm;
+    // the plan entries decode_batch reads are per warp: keep them in registers and pass a local copy
+    int Pw[18];
+#pragma unroll
+    for (int i = 0; i < 18; i++) Pw[i] = P[i];
+    Pw[3] = nb_qkv; Pw[4] = nb_cproj; Pw[5] = nb_fc; Pw[6] = nb_proj; Pw[7] = nb_layer; Pw[8] = nb_lm;
+
+    const uint32_t slot_base = smem_u32(dsm + Smem2::wslot) + warp * kWarpSlotBytes;
+    auto issue = [&](int seq) {                               // lane 0: start batch `seq` into half (seq & 1)
+        if (seq >= nb_total || lane != 0) return;
+        Batch bt; int kind, layer;
+        decode_batch(Pw, phs, L, E, warp, seq, bt, kind, layer);
+        const uint32_t bar = smem_u32(&s_bar[warp][seq & 1]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(bar, (uint32_t) bt.bytes);
+        tma_bulk_g2s_stream(slot_base + (seq & 1) * kHalfSlotBytes, bt.src, (uint32_t) bt.bytes, bar, s_bc.policy);
+    };
+    issue(0); issue(1);
+    int seq = 0;                                              // next batch this warp consumes
+
+    // embedding of the one new token: every CTA keeps its own copy of the residual stream
+    const int token = A.token_ptr ? min(max(__ldcg(A.token_ptr), 0), A.n_vocab_in - 1) : A.token;
+    for (int i = tid; i < E; i += kThreads) {
+        const float t = kRound ? __half2float(((const __half *) A.wte)[(size_t) token * E + i]) : ((const float *) A.wte)[(size_t) token * E + i];
+        xs[i] = __fadd_rn(t, A.wpe[(size_t) n_past * E + i]);
+    }
+    cluster_sync_all();                                       // every CTA of the cluster is running (DSMEM may be addressed from here on)
+
+    const float scale = 1.0f / sqrtf((float) E / (float) H);
+    const double inv_E = A.inv_E;
+    const int np = n_kv & ~31;
+    auto gelu_sel = [](float v, __half t) { return v <= -10.0f ? 0.0f : v >= 10.0f ? v : __half2float(t); };
+
+    // all batches of one phase for this warp: row dots against `operand`, results handed to `emit(row, value)` (every lane holds the value)
+    auto run_batches = [&](int count, const float * operand, auto emit) {
+        for (int bi = 0; bi < count; bi++, seq++) {
+            Batch bt; int kind, layer;
+            const int p = decode_batch(Pw, phs, L, E, warp, seq, bt, kind, layer);
+            const DecodePhase ph = phs[p];
+            mbar_wait(smem_u32(&s_bar[warp][seq & 1]), (uint32_t)(seq >> 1) & 1u);
+            const unsigned char * slot = dsm + Smem2::wslot + (size_t) warp * kWarpSlotBytes + (size_t)(seq & 1) * kHalfSlotBytes;
+            int j = 0;
+            for (; j + 1 < bt.n; j += 2) {
+                float v[2];
+                row_dot<WT, true, 2>(slot + (size_t) j * ph.row_bytes, ph.row_bytes, operand, ph.K, lane, v);
+                emit(bt.r0 + j, v[0]); emit(bt.r0 + j + 1, v[1]);
+            }
+            if (j < bt.n) { float v[1]; row_dot<WT, true, 1>(slot + (size_t) j * ph.row_bytes, ph.row_bytes, operand, ph.K, lane, v); emit(bt.r0 + j, v[0]); }
+            __syncwarp();
+            issue(seq + 2);
+        }
+    };
+
+#pragma unroll 1
+    for (int il = 0; il < L; il++) {
+        const DecodeLayerVec lv = A.layer_vecs[il];
+        // ---- LN1 (every CTA, on its own copy of x) -> q, k, v rows of this CTA's head ----
+        block_layernorm<kRound, false>(xs, E, inv_E, lv.ln_1_g, lv.ln_1_b, act_ln, red, A.ln_fallbacks, 1);
+        if (head_cta) {
+            const size_t slot_off = ((size_t) il * ctx + n_past) * E;
+            run_batches(nb_qkv, act_ln, [&](int r, float v) {
+                if (lane != 0) return;
+                const int s = r / E, c = r - s * E;            // segment (q, k, v) and column of the model dimension
+                qkv[s * 128 + (c - cr * D)] = v;
+                if (s == 1) s_bc.mem_k[slot_off + c] = v; else if (s == 2) s_bc.mem_v[slot_off + c] = v;
+            });
+            __syncthreads();
+            // ---- scores: one key per warp pass, lanes = virtual lanes (bark.cpp:1302-1323; ggml_vec_dot_f32 order) ----
+            {
+                const float * Kc = A.mem_k + (size_t) il * ctx * E + cr * D;
+                float qv[DSTEPS];
+#pragma unroll
+                for (int c = 0; c < DSTEPS; c++) qv[c] = qkv[c * 32 + lane];
+                for (int k0 = warp * 4; k0 < n_kv; k0 += kWarps * 4) {
+                    float kf[4][DSTEPS];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int k = k0 + u;
+#pragma unroll
+                        for (int c = 0; c < DSTEPS; c++) kf[u][c] = k < n_past ? __ldcg(Kc + (size_t) k * E + c * 32 + lane) : (k == n_past ? qkv[128 + c * 32 + lane] : 0.0f);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        float acc = 0.0f;
+#pragma unroll
+                        for (int c = 0; c < DSTEPS; c++) acc = __fmaf_rn(kf[u][c], qv[c], acc);
+                        const float r = lane_tree_reduce(acc);
+                        if (lane == 0 && k0 + u < n_kv) probs[k0 + u] = __fmul_rn(r, scale);
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- soft_max (ggml.c:13953-14042), same decisions as the 148-CTA kernel ----
+            float * p = probs;
+            float mx = __int_as_float(0xff800000);
+            for (int i = tid; i < n_kv; i += kThreads) mx = fmaxf(mx, p[i]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            float * fred = reinterpret_cast<float *>(red);
+            if (lane == 0) fred[warp] = mx;
+            __syncthreads();
+            mx = fred[0];
+#pragma unroll
+            for (int w = 1; w < kWarps; w++) mx = fmaxf(mx, fred[w]);
+            const int nchunks = n_kv >> 3, n8 = nchunks << 3;
+            for (int i = tid; i < n_kv; i += kThreads) {
+                const float d = __fsub_rn(p[i], mx);
+                p[i] = i < n8 ? ggml_v_expf_dev(d) : glibc_expf_dev(d);
+            }
+            __syncthreads();
+            if (warp == 0) {
+                auto chunk_sum = [&](int c) {
+                    const float4 lo4 = *reinterpret_cast<const float4 *>(p + c * 8), hi4 = *reinterpret_cast<const float4 *>(p + c * 8 + 4);
+                    const float t0 = __fadd_rn(hi4.x, lo4.x), t1 = __fadd_rn(hi4.y, lo4.y), t2 = __fadd_rn(hi4.z, lo4.z), t3 = __fadd_rn(hi4.w, lo4.w);
+                    return __fadd_rn(__fadd_rn(t0, t2), __fadd_rn(t1, t3));
+                };
+                double s = 0.0;
+                for (int c = lane; c < nchunks; c += 32) s += (double) chunk_sum(c);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                if (lane == 0) {
+                    const double dl = 2.0 * (double)(nchunks + 8) * 0x1p-53 * s * (1.0 + 1e-6);
+                    double lo = s - dl, hi = s + dl;
+                    for (int i = n8; i < n_kv; i++) { const double tl = (double) p[i]; lo = __dadd_rn(lo, tl); hi = __dadd_rn(hi, tl); }
+                    const double mid = 0.5 * (lo + hi), y = approx_rcp(mid);
+                    const double rw = (hi - lo) * y * 0.5 + 0x1p-48;
+                    float f_lo = __double2float_rn(y * (1.0 - rw));
+                    const float f_hi = __double2float_rn(y * (1.0 + rw));
+                    if (f_lo != f_hi) {
+                        double q2 = 0.0;
+                        for (int c = 0; c < nchunks; c++) q2 = __dadd_rn(q2, (double) chunk_sum(c));
+                        for (int i = n8; i < n_kv; i++) q2 = __dadd_rn(q2, (double) p[i]);
+                        f_lo = __double2float_rn(__ddiv_rn(1.0, q2));
+                        if (A.ln_fallbacks) atomicAdd(A.ln_fallbacks + 1, 1u);
+                    }
+                    bc[2] = f_lo;
+                }
+            }
+            __syncthreads();
+            const float sc_f = bc[2];
+            // ---- P.V: warp w < D/8 owns head columns [8w, 8w+8), lane v walks k = v, v+32, ... (ggml_vec_dot_f32 lane order);
+            // the 32 partials of a column are combined by the shuffle tree, the n_kv % 32 leftovers follow in the compiled order ----
+            if (warp < D / 8) {
+                const float * Vc = A.mem_v + (size_t) il * ctx * E + cr * D + warp * 8;
+                float acc[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) acc[i] = 0.0f;
+                for (int k = lane; k < np; k += 32) {
+                    float vf[8];
+                    if (k < n_past) {
+                        const float4 v0 = __ldcg(reinterpret_cast<const float4 *>(Vc + (size_t) k * E)), v1 = __ldcg(reinterpret_cast<const float4 *>(Vc + (size_t) k * E) + 1);
+                        vf[0] = v0.x; vf[1] = v0.y; vf[2] = v0.z; vf[3] = v0.w; vf[4] = v1.x; vf[5] = v1.y; vf[6] = v1.z; vf[7] = v1.w;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; i++) vf[i] = qkv[256 + warp * 8 + i];
+                    }
+                    const float pk = __fmul_rn(p[k], sc_f);
+#pragma unroll
+                    for (int i = 0; i < 8; i++) acc[i] = __fmaf_rn(vf[i], pk, acc[i]);
+                }
+                float sum[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) sum[i] = lane_tree_reduce(acc[i]);
+                const int r = n_kv - np, r8 = r & ~7, n4 = r8 + ((r - r8) >= 4 ? 4 : 0);
+                for (int j = 0; j < r; j++) {                 // leftovers k = np + j: rounded multiply + add for the 8- and 4-groups, fused for the last <= 3
+                    const int k = np + j;
+                    const float pk = __fmul_rn(p[k], sc_f);
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const float vv = k < n_past ? __ldcg(Vc + (size_t) k * E + i) : qkv[256 + warp * 8 + i];
+                        sum[i] = j < n4 ? __fadd_rn(sum[i], __fmul_rn(vv, pk)) : __fmaf_rn(vv, pk, sum[i]);
+                    }
+                }
+                // attention output of this head -> the c_proj operand of all 16 CTAs
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int col = cr * D + warp * 8 + i;
+                    bcast_f32(smem_u32(act_att + act_index(col)), kRound ? round_f16(sum[i]) : sum[i], lane);
+                }
+            }
+        }
+        cluster_sync_all();                                   // (1) the attention output is complete in every CTA
+
+        // ---- c_proj + residual -> x, in all 16 copies ----
+        run_batches(nb_cproj, act_att, [&](int r, float v) {
+            const float nx = __fadd_rn(v, xs[r]);
+            __syncwarp();
+            bcast_f32(smem_u32(xs + r), nx, lane);
+        });
+        cluster_sync_all();                                   // (2)
+
+        // ---- LN2 -> c_fc -> GELU -> MLP operand, in all 16 copies ----
+        block_layernorm<kRound, false>(xs, E, inv_E, lv.ln_2_g, lv.ln_2_b, act_ln, red, A.ln_fallbacks, 1);
+        run_batches(nb_fc, act_ln, [&](int r, float v) {
+            const float g = gelu_sel(v, s_bc.gelu_tab[__half_as_ushort(__float2half_rn(v))]);
+            bcast_f32(smem_u32(act_ff + act_index(r)), kRound ? round_f16(g) : g, lane);
+        });
+        cluster_sync_all();                                   // (3)
+
+        // ---- mlp/c_proj + residual -> x ----
+        run_batches(nb_proj, act_ff, [&](int r, float v) {
+            const float nx = __fadd_rn(v, xs[r]);
+            __syncwarp();
+            bcast_f32(smem_u32(xs + r), nx, lane);
+        });
+        cluster_sync_all();                                   // (4)
+    }
+    // ---- final norm + lm_head window ----
+    block_layernorm<kRound, false>(xs, E, inv_E, A.ln_f_g, A.ln_f_b, act_ln, red, A.ln_fallbacks, 1);
+    run_batches(nb_lm, act_ln, [&](int r, float v) { if (lane == 0) s_bc.logits[r] = v; });
+    cluster_sync_all();                                       // no CTA may exit while others can still address its shared memory
+}
+
+static size_t decode2_smem_bytes() { return (size_t) Smem2::total + 128; }
+
+// the cluster kernel covers f16 / f32 models whose rows fit a staging half (row bytes <= 6 KB) with at most 16 heads of width 32..128
+bool decode_cluster_supported(const DecodeArgs & a, WType wt, int max_row_bytes) {
+    const int D = a.E / a.H;
+    return (wt == W_F16 || wt == W_F32) && a.H <= kCl && D % 32 == 0 && D <= 128 && (D / 16) * 1 >= 1 && max_row_bytes <= kHalfSlotBytes && a.E <= 1024 && 4 * a.E <= 4096;
+}
+
+template <typename WT, int DSTEPS>
+static void launch_cluster_variant(DecodeArgs a, cudaStream_t s) {
+    static std::atomic<unsigned long long> configured{0};
+    if (first_use_on_this_device(configured)) {
+        BARK_CUDA_CHECK(cudaFuncSetAttribute(gpt_decode_cluster_kernel<WT, DSTEPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) decode2_smem_bytes()));
+        BARK_CUDA_CHECK(cudaFuncSetAttribute(gpt_decode_cluster_kernel<WT, DSTEPS>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(kCl); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = decode2_smem_bytes(); cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = kCl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    BARK_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gpt_decode_cluster_kernel<WT, DSTEPS>, a));
+}
+
+void launch_decode_cluster(const DecodeArgs & args, WType wt, cudaStream_t s) {
+    const int dsteps = args.E / args.H / 32;
+    if (g_prof_on) prof_begin("gpt_decode_cluster_kernel", s, g_next_bytes, g_next_flops);
+    if (wt == W_F16) {
+        switch (dsteps) { case 1: launch_cluster_variant<__half, 1>(args, s); break; case 2: launch_cluster_variant<__half, 2>(args, s); break;
+                          case 3: launch_cluster_variant<__half, 3>(args, s); break; default: launch_cluster_variant<__half, 4>(args, s); }
+    } else {
+        switch (dsteps) { case 1: launch_cluster_variant<float, 1>(args, s); break; case 2: launch_cluster_variant<float, 2>(args, s); break;
+                          case 3: launch_cluster_variant<float, 3>(args, s); break; default: launch_cluster_variant<float, 4>(args, s); }
+    }
+    if (g_prof_on) prof_end(s);
+    g_next_bytes = g_next_flops = 0.0;
+    ++g_kernel_launches;
 }
 
 static size_t decode_smem_bytes() { return (size_t) SmemLayout::total + 128; }
@@ -802,7 +1299,10 @@ static void launch_one(DecodeArgs a, int n_sm, cudaStream_t s) {
 void launch_decode_step(const DecodeArgs & args, WType wt, int n_sm, cudaStream_t s) {
     const int dsteps = args.E / args.H / 32;
     if (g_prof_on) prof_begin("gpt_decode_step_kernel", s, g_next_bytes, g_next_flops);
-    if (wt == W_F16) {
+    if (wt == W_Q4_0) {
+        switch (dsteps) { case 1: launch_one<Q4, 1>(args, n_sm, s); break; case 2: launch_one<Q4, 2>(args, n_sm, s); break;
+                          case 3: launch_one<Q4, 3>(args, n_sm, s); break; default: launch_one<Q4, 4>(args, n_sm, s); }
+    } else if (wt == W_F16) {
         switch (dsteps) { case 1: launch_one<__half, 1>(args, n_sm, s); break; case 2: launch_one<__half, 2>(args, n_sm, s); break;
                           case 3: launch_one<__half, 3>(args, n_sm, s); break; default: launch_one<__half, 4>(args, n_sm, s); }
     } else {

@@ -65,9 +65,12 @@ void build_decode_tables(bark_context * ctx, GPTModel & m) {
         return;
     }
     const size_t es = m.wtype == W_F16 ? 2 : 4;
+    const bool q4 = m.wtype == W_Q4_0;
     std::vector<DecodePhase> ph((size_t) 4 * L + 1);
     std::vector<DecodeLayerVec> lv((size_t) L);
-    auto set = [&](DecodePhase & p, const DMat & d) { p.w = d.p; p.n_out = d.n_out; p.K = d.K; p.row_bytes = (int)(d.Kp * es); p.pad = 0; };
+    auto set = [&](DecodePhase & p, const DMat & d) {        // q4_0: 16 nibble bytes per 32-element block, block scales in a second array
+        p.w = d.p; p.n_out = d.n_out; p.K = d.K; p.row_bytes = q4 ? d.K / 2 : (int)(d.Kp * es); p.pad = 0; p.ws = q4 ? d.scales : nullptr;
+    };
     for (int l = 0; l < L; l++) {
         const GPTLayer & G = m.layers[(size_t) l];
         set(ph[(size_t) 4 * l], G.c_attn); set(ph[(size_t) 4 * l + 1], G.c_proj); set(ph[(size_t) 4 * l + 2], G.fc); set(ph[(size_t) 4 * l + 3], G.proj);
@@ -119,11 +122,14 @@ static void decode_step(bark_context * ctx, GPTModel & m, int token, const int32
     a.inv_E = 1.0 / (double) m.n_embd;
     a.adapt = ctx->adapt_on ? m.d_adapt : nullptr;
     a.timing_tid = ctx->timing_tid; a.poll_ns = ctx->poll_ns; a.first_ns = ctx->first_ns; a.att_ns = ctx->att_ns;
-    const double es = m.wtype == W_F16 ? 2.0 : 4.0;
+    const double es = m.wtype == W_Q4_0 ? 18.0 / 32.0 : m.wtype == W_F16 ? 2.0 : 4.0;
     const double E = m.n_embd, L = m.n_layer;
     g_next_bytes = (12.0 * L * E * E + (double)(lm_hi - lm_lo) * E) * es + 2.0 * L * (double)(n_past + 1) * E * 4.0 + 2.0 * L * E * 4.0 + (double)(lm_hi - lm_lo) * 4.0;   // SURVEY §8d B_tok
     g_next_flops = 2.0 * (12.0 * L * E * E + (double)(lm_hi - lm_lo) * E) + 4.0 * L * (double)(n_past + 1) * E;
-    launch_decode_step(a, m.wtype, ctx->n_sm, ctx->stream);
+    int max_row_bytes = 0;
+    for (const DMat * d : {&m.layers[0].c_attn, &m.layers[0].c_proj, &m.layers[0].fc, &m.layers[0].proj, &m.lm_head[0]}) max_row_bytes = std::max(max_row_bytes, (int)(d->Kp * (m.wtype == W_F16 ? 2 : 4)));   // (cluster kernel: f16 / f32 only)
+    if (ctx->decode_cluster && decode_cluster_supported(a, m.wtype, max_row_bytes)) launch_decode_cluster(a, m.wtype, ctx->stream);
+    else launch_decode_step(a, m.wtype, ctx->n_sm, ctx->stream);
     ctx->tag_base += (unsigned) decode_tags_per_step(m.n_layer);
 }
 
@@ -141,7 +147,7 @@ bool gpt_eval(bark_context * ctx, GPTModel & m, const int32_t * tokens, int n, i
         fprintf(stderr, "%s: token id %d at position %d is outside the model's input vocabulary (%d)\n", __func__, tokens[i], i, m.n_in_vocab); return false;
     }
     if (*n_past > 0 && N == 1) {
-        if (ctx->use_decode_kernel && m.decode_ok && !is_quant(m.wtype) && *n_past + 1 <= m.block_size) {
+        if (ctx->use_decode_kernel && m.decode_ok && *n_past + 1 <= m.block_size) {
             decode_step(ctx, m, tokens[0], nullptr, *n_past, lm_lo, lm_hi);
             ctx->last_logits = m.glogits;
             if (logits_host) {
@@ -182,7 +188,7 @@ bool gpt_eval(bark_context * ctx, GPTModel & m, const int32_t * tokens, int n, i
 // One decode step whose input token is read from device memory (the previous step's sample): nothing to wait for on the
 // host, so a whole window of steps is enqueued back to back.
 bool gpt_decode_chained(bark_context * ctx, GPTModel & m, const int32_t * d_token, int * n_past, int lm_lo, int lm_hi) {
-    if (!ctx->use_decode_kernel || !m.decode_ok || is_quant(m.wtype) || *n_past < 1) { fprintf(stderr, "%s: needs the persistent decode kernel and a filled KV cache\n", __func__); return false; }
+    if (!ctx->use_decode_kernel || !m.decode_ok || *n_past < 1) { fprintf(stderr, "%s: needs the persistent decode kernel and a filled KV cache\n", __func__); return false; }
     if (*n_past + 1 > m.block_size) { fprintf(stderr, "%s: context overflow (n_past %d + 1 > %d)\n", __func__, *n_past, m.block_size); return false; }
     if (lm_hi <= 0 || lm_hi > m.n_out_vocab || lm_lo < 0 || lm_lo >= lm_hi) { lm_lo = 0; lm_hi = m.n_out_vocab; }
     decode_step(ctx, m, 0, d_token, *n_past, lm_lo, lm_hi);

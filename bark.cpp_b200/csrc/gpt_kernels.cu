@@ -355,7 +355,9 @@ void attention(const float * Q, const float * Kc, const float * Vc, int N, int n
     const int D = E / H;
     const float scale = 1.0f / sqrtf((float) E / (float) H);                 // bark.cpp:1318
     const int rows = H * N;
-    if (N >= 8 && use_tiled() && D % 32 == 0 && D <= 128) {
+    // (any N: for a single decode row the tiled kernels still spread the keys over ~130 CTAs, where the one-warp-per-(head, query)
+    // kernels below walk all keys on 12 warps — 100 us + 77 us per layer in the per-op decode path of quantised models)
+    if (use_tiled() && D % 32 == 0 && D <= 128) {
         g_next_bytes = 4.0 * ((double) n_kv * E + (double) N * E + (double) H * N * n_kv); g_next_flops = 2.0 * (double) N * n_kv * E;
         attention_tiled_scores(Q, Kc, N, n_kv, n_past, E, H, scale, causal, scores, s);
         g_next_bytes = 8.0 * (double) rows * n_kv;

@@ -66,7 +66,7 @@ void fast_layernorm(const float * x, int rows, int E, const float * g, const flo
 
 // ---- persistent decode step (decode_kernels.cu) -----------------------------------------------------------------
 constexpr int kDecodeReplicas = 8;        // copies of each all-to-all exchange vector (gx, gq, gatt, gff): CTA c reads copy c % 8
-struct DecodePhase { const void * w; int n_out, row_bytes, K, pad; };            // one streamed matrix: LI rows
+struct DecodePhase { const void * w; int n_out, row_bytes, K, pad; const void * ws; };   // one streamed matrix: LI rows (f32 / f16), or q4_0 nibble words (16 B per block) with f16 block scales in ws
 struct DecodeLayerVec { const float * ln_1_g, * ln_1_b, * ln_2_g, * ln_2_b; };
 struct DecodeArgs {
     const DecodePhase * phases;          // [4L + 1]: per layer c_attn, c_proj, c_fc, mlp/c_proj; then lm_head
@@ -86,5 +86,8 @@ struct DecodeArgs {
 };
 int  decode_tags_per_step(int n_layer);
 void launch_decode_step(const DecodeArgs & args, WType wt, int n_sm, cudaStream_t s);
+// the same token inside one 16-CTA cluster (DSMEM exchanges, no polling); see decode_kernels.cu
+bool decode_cluster_supported(const DecodeArgs & args, WType wt, int max_row_bytes);
+void launch_decode_cluster(const DecodeArgs & args, WType wt, cudaStream_t s);
 
 }  // namespace bark

@@ -350,8 +350,9 @@ bool load_model_file(const std::string & path, bark_context * ctx) {
     }
     ctx->d_ln_fallbacks = (unsigned *) ctx_alloc(ctx, 4 * sizeof(unsigned));
     BARK_CUDA_CHECK(cudaMemset(ctx->d_ln_fallbacks, 0, 4 * sizeof(unsigned)));
-    if (!is_quant(ctx->semantic.wtype)) build_decode_tables(ctx, ctx->semantic);   // quantised models step through the per-op kernels
-    if (!is_quant(ctx->coarse.wtype)) build_decode_tables(ctx, ctx->coarse);
+    // f32, f16 and q4_0 models decode in the persistent kernel; the other quantised types step through the per-op kernels (decode_ok stays false)
+    if (!is_quant(ctx->semantic.wtype) || ctx->semantic.wtype == W_Q4_0) build_decode_tables(ctx, ctx->semantic);
+    if (!is_quant(ctx->coarse.wtype) || ctx->coarse.wtype == W_Q4_0) build_decode_tables(ctx, ctx->coarse);
     return true;
 }
 

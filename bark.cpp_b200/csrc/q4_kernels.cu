@@ -47,9 +47,10 @@ __global__ void quantize_q8_kernel(const float * __restrict__ x, int ldx, int ro
     if (lane == 0) d_out[(size_t) r * nb + b] = __half2float(__float2half_rn(d));          // y[i].d = GGML_FP32_TO_FP16(d)
 }
 
-constexpr int kQ4MT = 8;        // activation rows per warp
+// activation rows per warp: 8 for the multi-row passes, 1 for a single decode row (the 8-row kernel repeats a lone row 8 times)
 
 // out[m][o] = vec_dot_q4_0_q8_0(W[o], A[m]); warp = 4 outputs x kQ4MT rows; block = 8 warps = 32 outputs
+template <int kQ4MT>
 __global__ void __launch_bounds__(256) q4_matmul_kernel(const uint4 * __restrict__ qs, const __half * __restrict__ scales, int K, int O,
                                                         const int8_t * __restrict__ aq, const float * __restrict__ ad, int M, MatmulEpilogue ep) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -64,17 +65,27 @@ __global__ void __launch_bounds__(256) q4_matmul_kernel(const uint4 * __restrict
     float acc[kQ4MT];
 #pragma unroll
     for (int mi = 0; mi < kQ4MT; mi++) acc[mi] = 0.0f;
-    for (int b = 0; b < nb; b++) {
-        uint32_t w = __ldg(wq + (size_t) b * 4);
-        w = (high ? (w >> 4) : w) & 0x0f0f0f0fu;
-        const int wi = (int) __vsub4(w, 0x08080808u);             // nibble - 8 per byte
-        const float dw = __half2float(__ldg(ws + b));
+    // the weight words and scales of 8 blocks are fetched together (the chain itself is sequential in b, its loads need not be: a
+    // single-row decode step was ~60 us of dependent L2 round trips per mat-mul before)
+    constexpr int UB = 8;
+    for (int b0 = 0; b0 < nb; b0 += UB) {
+        uint32_t wr[UB]; float dwr[UB];
 #pragma unroll
-        for (int mi = 0; mi < kQ4MT; mi++) {
-            const int m = min(m0 + mi, M - 1);
-            const int yi = __ldg(reinterpret_cast<const int *>(aq + (size_t) m * K + b * 32) + l);
-            const float d = __fmul_rn(dw, __ldg(ad + (size_t) m * nb + b));
-            acc[mi] = __fmaf_rn(d, (float) __dp4a(wi, yi, 0), acc[mi]);
+        for (int u = 0; u < UB; u++) if (b0 + u < nb) { wr[u] = __ldg(wq + (size_t)(b0 + u) * 4); dwr[u] = __half2float(__ldg(ws + b0 + u)); }
+#pragma unroll
+        for (int u = 0; u < UB; u++) {
+            const int b = b0 + u;
+            if (b < nb) {
+                const uint32_t w = (high ? (wr[u] >> 4) : wr[u]) & 0x0f0f0f0fu;
+                const int wi = (int) __vsub4(w, 0x08080808u);     // nibble - 8 per byte
+#pragma unroll
+                for (int mi = 0; mi < kQ4MT; mi++) {
+                    const int m = min(m0 + mi, M - 1);
+                    const int yi = __ldg(reinterpret_cast<const int *>(aq + (size_t) m * K + b * 32) + l);
+                    const float d = __fmul_rn(dwr[u], __ldg(ad + (size_t) m * nb + b));
+                    acc[mi] = __fmaf_rn(d, (float) __dp4a(wi, yi, 0), acc[mi]);
+                }
+            }
         }
     }
 #pragma unroll
@@ -105,8 +116,8 @@ void q4_matmul(const DMat & W, const void * act, int ld_act, int rows, const Mat
     BARK_LAUNCH(quantize_q8_kernel, (unsigned)((warps * 32 + 255) / 256), 256, 0, s, (const float *) act, ld_act, rows, W.K, g_q8, g_q8d);
     g_next_bytes = (double) W.n_out * nb * 18.0 + (double) rows * (W.K * 1.0 + nb * 4.0 + W.n_out * 4.0);
     g_next_flops = 2.0 * rows * (double) W.n_out * W.K;
-    BARK_LAUNCH(q4_matmul_kernel, dim3((W.n_out + 31) / 32, (rows + kQ4MT - 1) / kQ4MT), 256, 0, s, (const uint4 *) W.p, (const __half *) W.scales, W.K, W.n_out,
-                g_q8, g_q8d, rows, ep);
+    if (rows == 1) BARK_LAUNCH(q4_matmul_kernel<1>, dim3((W.n_out + 31) / 32, 1), 256, 0, s, (const uint4 *) W.p, (const __half *) W.scales, W.K, W.n_out, g_q8, g_q8d, rows, ep);
+    else           BARK_LAUNCH(q4_matmul_kernel<8>, dim3((W.n_out + 31) / 32, (rows + 7) / 8), 256, 0, s, (const uint4 *) W.p, (const __half *) W.scales, W.K, W.n_out, g_q8, g_q8d, rows, ep);
 }
 
 }  // namespace bark
