@@ -67,6 +67,23 @@ extern thread_local double g_next_bytes, g_next_flops;
         ++::bark::g_kernel_launches;                                                                  \
     } while (0)
 
+// Same, with programmatic dependent launch (PDL): the kernel may start while its predecessor in the stream is still draining and
+// runs its own prologue (barrier init, TMEM allocation, tensor-map prefetch) meanwhile; it MUST execute griddepcontrol.wait before it
+// touches anything the predecessor wrote.  Used by the fast-mode chain of 2-20 us kernels (fast_kernels.cu).
+#define BARK_LAUNCH_PDL(kernel, grid, block, smem, strm__, ...)                                       \
+    do {                                                                                              \
+        if (::bark::g_prof_on) ::bark::prof_begin(#kernel, (strm__), ::bark::g_next_bytes, ::bark::g_next_flops);            \
+        cudaLaunchConfig_t cfg__ = {};                                                                \
+        cfg__.gridDim = (grid); cfg__.blockDim = (block); cfg__.dynamicSmemBytes = (smem); cfg__.stream = (strm__);          \
+        cudaLaunchAttribute at__[1];                                                                  \
+        at__[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at__[0].val.programmaticStreamSerializationAllowed = 1; \
+        cfg__.attrs = at__; cfg__.numAttrs = 1;                                                       \
+        BARK_CUDA_CHECK(cudaLaunchKernelEx(&cfg__, kernel, __VA_ARGS__));                             \
+        if (::bark::g_prof_on) ::bark::prof_end((strm__));                                            \
+        ::bark::g_next_bytes = ::bark::g_next_flops = 0.0;                                                                    \
+        ++::bark::g_kernel_launches;                                                                  \
+    } while (0)
+
 // weight element types as stored in ggml_weights.bin (ggml_type values)
 enum WType : int { W_F32 = 0, W_F16 = 1, W_Q4_0 = 2, W_Q4_1 = 3, W_Q5_0 = 6, W_Q5_1 = 7, W_Q8_0 = 8 };   // 3..8: qx_kernels.cu
 // activation-operand format only (never a file type): f16-rounded values kept in f32 containers, for f16 weight matrices whose tiled-GEMM

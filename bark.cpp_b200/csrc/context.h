@@ -35,6 +35,7 @@ struct bark_context {
     bool decode_cluster = false;                     // BARK_B200_DECODE=cluster: the decode step inside one 16-CTA cluster (decode_kernels.cu) where the model fits
     bool gemm_f32c = false;                          // BARK_B200_GEMM_F32C=1: multi-row passes of f16 models keep operands as f16 values in f32 containers
     bool adapt_on = false;                           // BARK_B200_ADAPT=1: self-tuning head starts instead of the fixed knobs below (measured worse, see decode_kernels.cu)
+    unsigned headstart[6] = {0, 2000, 500, 400, 500, 0};   // BARK_B200_HEADSTART=q:att:x1:ff:x2:scores (ns): sleep before the first poll of each exchange
     int timing_tid = 0; unsigned poll_ns = 40, first_ns = 500, att_ns = 2000;   // att_ns (BARK_B200_POLL_ATT_NS): head start before CTAs without a soft_max tile poll for the attention output
     unsigned long long * d_timing = nullptr;         // optional phase timestamps of the decode kernel (BARK_B200_DECODE_TIMING=1)
 

@@ -422,23 +422,27 @@ __device__ __forceinline__ float row_dot_q4(const unsigned char * qrows, const u
     const bool high = l >= 4;
     const unsigned char * wq = qrows + (size_t) row * nb * 16 + (l & 3) * 4;
     const unsigned char * ws = srows + (size_t) row * nb * 2;
-    const int * a32 = reinterpret_cast<const int *>(aq);
+    // every operand through ld.shared (a generic-pointer load of shared memory is tracked like a global load: long scoreboard)
+    const uint32_t s_wq = SH ? smem_u32(wq) : 0u, s_ws = SH ? smem_u32(ws) : 0u, s_aq = smem_u32(aq) + l * 4, s_ad = smem_u32(ad);
     float acc = 0.0f;
     constexpr int UB = 8;
     for (int b0 = 0; b0 < nb; b0 += UB) {
-        uint32_t wr[UB]; float dwr[UB];
+        uint32_t wr[UB]; float dr[UB]; int yr[UB];
 #pragma unroll
         for (int u = 0; u < UB; u++) if (b0 + u < nb) {
-            if (SH) { asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wr[u]) : "r"(smem_u32(wq) + (b0 + u) * 16) : "memory"); dwr[u] = __half2float(*reinterpret_cast<const __half *>(ws + (b0 + u) * 2)); }
-            else    { wr[u] = __ldg(reinterpret_cast<const uint32_t *>(wq + (size_t)(b0 + u) * 16)); dwr[u] = __half2float(__ldg(reinterpret_cast<const __half *>(ws + (size_t)(b0 + u) * 2))); }
+            unsigned short hs; float da;
+            if (SH) { asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wr[u]) : "r"(s_wq + (b0 + u) * 16) : "memory"); asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hs) : "r"(s_ws + (b0 + u) * 2) : "memory"); }
+            else    { wr[u] = __ldg(reinterpret_cast<const uint32_t *>(wq + (size_t)(b0 + u) * 16)); hs = __ldg(reinterpret_cast<const unsigned short *>(ws + (size_t)(b0 + u) * 2)); }
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(da) : "r"(s_ad + (b0 + u) * 4) : "memory");
+            asm volatile("ld.shared.s32 %0, [%1];" : "=r"(yr[u]) : "r"(s_aq + (b0 + u) * 32) : "memory");
+            dr[u] = __fmul_rn(__half2float(__ushort_as_half(hs)), da);
         }
 #pragma unroll
         for (int u = 0; u < UB; u++) {
-            const int b = b0 + u;
-            if (b < nb) {
+            if (b0 + u < nb) {
                 const uint32_t w = (high ? (wr[u] >> 4) : wr[u]) & 0x0f0f0f0fu;
                 const int wi = (int) __vsub4(w, 0x08080808u);
-                acc = __fmaf_rn(__fmul_rn(dwr[u], ad[b]), (float) __dp4a(wi, a32[b * 8 + l], 0), acc);
+                acc = __fmaf_rn(dr[u], (float) __dp4a(wi, yr[u], 0), acc);
             }
         }
     }
@@ -651,7 +655,8 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
         s_adapt_on = A.adapt != nullptr;
     }
     if (tid < XT_COUNT) {                                    // head starts: carried over from the previous token, or the fixed knobs
-        const unsigned fixed = tid == XT_X1 || tid == XT_X2 ? A.first_ns : (tid == XT_ATT && (int) blockIdx.x >= A.H * ((A.E / A.H) >> 4)) ? A.att_ns : 0u;
+        const bool pv = (int) blockIdx.x < A.H * ((A.E / A.H) >> 4);
+        const unsigned fixed = tid >= 6 ? 0u : (tid == XT_ATT && pv) ? 0u : A.headstart[tid];      // (CTAs with a soft_max tile reach the att exchange right behind their own tile)
         s_adapt[tid] = A.adapt ? A.adapt[blockIdx.x * XT_COUNT + tid] : fixed;
         s_obs[tid] = 0;
     }

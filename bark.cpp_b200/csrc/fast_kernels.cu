@@ -44,6 +44,9 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap * ma
                  ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap * map) { asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory"); }
+// programmatic dependent launch: wait for the preceding kernel's results / let the following kernel start its prologue
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {      // whole warp
@@ -124,6 +127,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    pdl_launch_dependents();                                  // the next kernel of the chain may begin its prologue on SMs as they free up
+    pdl_wait();                                               // everything above overlapped the previous kernel's tail; its outputs are needed from here on
 
     if (warp == 0) {
         if (lane == 0) {                                      // ===== TMA producer =====
@@ -241,6 +246,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) flash_attn_kernel(const __gri
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    pdl_launch_dependents();
+    pdl_wait();
     const uint32_t sQ = smem_u32(smem + FlashSmem::q), sK = smem_u32(smem + FlashSmem::k), sV = smem_u32(smem + FlashSmem::v), sP = smem_u32(smem + FlashSmem::p);
 
     if (warp == 0) {
@@ -386,6 +393,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) flash_attn2_kernel(const __gr
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    pdl_launch_dependents();
+    pdl_wait();
     const uint32_t sQ = smem_u32(smem + Flash2Smem::q), sK = smem_u32(smem + Flash2Smem::k), sV = smem_u32(smem + Flash2Smem::v), sP = smem_u32(smem + Flash2Smem::p);
     constexpr uint32_t kStage = kKeyBlk2 * 128, kPBuf = 2 * 128 * 128;
 
@@ -507,6 +516,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) flash_attn2_kernel(const __gr
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) ln_rows_f16_kernel(const float * __restrict__ x, int rows, int E, const float * __restrict__ g, const float * __restrict__ b, __half * __restrict__ out) {
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    pdl_launch_dependents();
+    pdl_wait();
     if (row >= rows) return;
     const float * xr = x + (size_t) row * E;
     float s = 0.0f;
@@ -564,7 +575,7 @@ static bool launch_gemm(const __half * A, int lda, const __half * W, int ldw, in
     const dim3 grid((N + BN - 1) / BN, (M + kBM - 1) / kBM);
     g_next_flops = 2.0 * M * N * (double) K;
     g_next_bytes = 2.0 * ((double) M * K + (double) N * K) + (double) M * N * (ep.mode == FEPI_F32 ? 4 : ep.mode == FEPI_RESID ? 8 : 2);
-    BARK_LAUNCH((umma_gemm_kernel<BN>), grid, kGemmThreads, smem, s, ta, tb, M, N, K, ep);
+    BARK_LAUNCH_PDL((umma_gemm_kernel<BN>), grid, dim3(kGemmThreads), smem, s, ta, tb, M, N, K, ep);
     return true;
 }
 
@@ -606,13 +617,13 @@ bool fast_attention(const __half * qk, int ldq, int k_col0, const __half * vt, i
     const float scale_log2e = (1.0f / sqrtf((float) kHeadD)) * 1.4426950408889634f;
     g_next_flops = 4.0 * (double) n * n * E;
     g_next_bytes = 2.0 * 4.0 * (double) n * E;
-    if (v1) BARK_LAUNCH(flash_attn_kernel, dim3(n / 128, H), kGemmThreads, smem, s, tqk, tvt, n, k_col0, scale_log2e, out, E);
-    else    BARK_LAUNCH(flash_attn2_kernel, dim3(n / 128, H), kGemmThreads, smem, s, tqk, tvt, n, k_col0, scale_log2e, out, E);
+    if (v1) BARK_LAUNCH_PDL(flash_attn_kernel, dim3(n / 128, H), dim3(kGemmThreads), smem, s, tqk, tvt, n, k_col0, scale_log2e, out, E);
+    else    BARK_LAUNCH_PDL(flash_attn2_kernel, dim3(n / 128, H), dim3(kGemmThreads), smem, s, tqk, tvt, n, k_col0, scale_log2e, out, E);
     return true;
 }
 
 void fast_layernorm(const float * x, int rows, int E, const float * g, const float * b, __half * out, cudaStream_t s) {
-    BARK_LAUNCH(ln_rows_f16_kernel, (rows + 7) / 8, 256, 0, s, x, rows, E, g, b, out);
+    BARK_LAUNCH_PDL(ln_rows_f16_kernel, dim3((rows + 7) / 8), dim3(256), (size_t) 0, s, x, rows, E, g, b, out);
 }
 
 }  // namespace bark

@@ -121,6 +121,7 @@ static void decode_step(bark_context * ctx, GPTModel & m, int token, const int32
     a.token_ptr = d_token; a.n_vocab_in = m.n_in_vocab;
     a.inv_E = 1.0 / (double) m.n_embd;
     a.adapt = ctx->adapt_on ? m.d_adapt : nullptr;
+    for (int i = 0; i < 6; i++) a.headstart[i] = ctx->headstart[i];
     a.timing_tid = ctx->timing_tid; a.poll_ns = ctx->poll_ns; a.first_ns = ctx->first_ns; a.att_ns = ctx->att_ns;
     const double es = m.wtype == W_Q4_0 ? 18.0 / 32.0 : m.wtype == W_F16 ? 2.0 : 4.0;
     const double E = m.n_embd, L = m.n_layer;

@@ -81,6 +81,7 @@ struct DecodeArgs {
     int E, H, L, block_size, n_past, token, lm_lo, lm_hi;
     const int32_t * token_ptr; int n_vocab_in;   // token_ptr != null: read the input token from device memory (written by sample_rows_kernel), clamped to the vocabulary
     double inv_E;                        // 1.0 / E (double), for the division-free LayerNorm decision
+    unsigned headstart[6];               // fixed head start (ns) before the first poll of each exchange: q, att (CTAs without a soft_max tile), x1, ff, x2, scores
     unsigned * adapt;                    // [n_cta][8] adaptive head starts of the exchanges, carried from token to token (null: fixed knobs)
     int timing_tid; unsigned poll_ns, first_ns, att_ns;   // debug: stamping thread; back-off between polls of the tagged words; delay before the first poll of the residual exchanges (ns)
 };
