@@ -200,6 +200,7 @@ bool run_chain(bark_context * ctx, GPTModel & m, const std::vector<int32_t> & fi
         BARK_CUDA_CHECK(cudaMemcpyAsync(ctx->d_u, ctx->h_u, (size_t) n * sizeof(double), cudaMemcpyHostToDevice, s)); bark::g_h2d_bytes += (size_t) n * sizeof(double);
     }
     const bool chain = ctx->use_decode_kernel && m.decode_ok;
+    const bool fused = chain && fused_sampler_available(ctx, m, samp_n);
     std::vector<int> past_before((size_t) n);
     std::vector<int32_t> cur_in = first_in;
     std::vector<float> host_logits;
@@ -210,8 +211,13 @@ bool run_chain(bark_context * ctx, GPTModel & m, const std::vector<int32_t> & fi
             const int lo = lo_of(j);
             past_before[(size_t) j] = *n_past;
             if (j == start) { if (!gpt_eval(ctx, m, cur_in.data(), (int) cur_in.size(), n_past, merge_ctx && *n_past == 0, nullptr, lo, lo + samp_n)) return false; }
-            else if (!gpt_decode_chained(ctx, m, ctx->d_feed, n_past, lo, lo + samp_n)) return false;
             const int force = ctx->debug_flag_every > 0 && (ctx->n_sample_calls++ % ctx->debug_flag_every) == 0;
+            if (j > start && fused) {                         // decode + sample in ONE launch (the kernel's last CTA draws the token)
+                const FusedSample fs{samp_n, temp, ctx->d_u + j, ctx->d_stok + j, lo, ctx->d_feed, ctx->d_seos + j, ctx->d_sflags + j, force};
+                if (!gpt_decode_chained(ctx, m, ctx->d_feed, n_past, lo, lo + samp_n, &fs)) return false;
+                continue;
+            }
+            if (j > start && !gpt_decode_chained(ctx, m, ctx->d_feed, n_past, lo, lo + samp_n)) return false;
             sample_rows(ctx->last_logits + lo, m.n_out_vocab, samp_n, 1, temp, ctx->d_u + j, ctx->d_stok + j, lo, ctx->d_feed, ctx->d_seos + j, ctx->d_sflags + j, force, s);
         }
         const size_t cnt = (size_t)(stop - start);
@@ -448,6 +454,7 @@ void alloc_workspace(bark_context * ctx) {
     ctx->d_u = (double *) ctx_alloc(ctx, 1024 * 8); ctx->d_stok = (int32_t *) ctx_alloc(ctx, 1024 * 4);
     ctx->d_sflags = (int32_t *) ctx_alloc(ctx, 1024 * 4); ctx->d_seos = (float *) ctx_alloc(ctx, 1024 * 4);
     ctx->d_feed = (int32_t *) ctx_alloc(ctx, 64); BARK_CUDA_CHECK(cudaMemset(ctx->d_feed, 0, 64));
+    ctx->d_done_counter = (unsigned *) ctx_alloc(ctx, 64); BARK_CUDA_CHECK(cudaMemset(ctx->d_done_counter, 0, 64));
     BARK_CUDA_CHECK(cudaMemset(ctx->d_u, 0, 1024 * 8));
     BARK_CUDA_CHECK(cudaMallocHost(&ctx->h_u, 1024 * 8)); BARK_CUDA_CHECK(cudaMallocHost(&ctx->h_stok, 1024 * 4));
     BARK_CUDA_CHECK(cudaMallocHost(&ctx->h_sflags, 1024 * 4)); BARK_CUDA_CHECK(cudaMallocHost(&ctx->h_seos, 1024 * 4));
@@ -506,6 +513,7 @@ extern "C" struct bark_context * bark_load_model(const char * model_path, struct
     bark_context * ctx = new bark_context();
     ctx->device = dev;
     ctx->n_sm = ctx->n_sm_total = prop.multiProcessorCount;
+    if (ctx->n_sm >= 132) ctx->n_sm = 128;                    // CTAs of the persistent decode step: 128 measured 1-2 % faster than 148 (fewer pollers per exchange; profiles/r02_decode_headstart_cta_sweep.txt)
     { const char * e = getenv("BARK_B200_MODE"); ctx->fast_mode = e && !strcmp(e, "fast"); }             // "fast": tensor-core fine passes (fast_kernels.cu), not bit-identical
     { const char * e = getenv("BARK_B200_DECODE_CTAS"); if (e && atoi(e) >= 64 && atoi(e) <= ctx->n_sm) ctx->n_sm = atoi(e); }   // experiment knob: CTAs of the persistent decode kernel
     { const char * e = getenv("BARK_B200_SAMPLE_FLAG_EVERY"); ctx->debug_flag_every = e ? atoi(e) : 0; }
@@ -518,6 +526,7 @@ extern "C" struct bark_context * bark_load_model(const char * model_path, struct
     { const char * e = getenv("BARK_B200_POLL_FIRST_NS"); if (e && atoi(e) >= 0 && atoi(e) <= 100000) ctx->first_ns = (unsigned) atoi(e); }
     ctx->headstart[1] = ctx->att_ns; ctx->headstart[2] = ctx->headstart[4] = ctx->first_ns;
     { const char * e = getenv("BARK_B200_HEADSTART"); if (e) { unsigned v[6]; if (sscanf(e, "%u:%u:%u:%u:%u:%u", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5]) == 6) for (int i = 0; i < 6; i++) ctx->headstart[i] = std::min(v[i], 100000u); } }
+    { const char * e = getenv("BARK_B200_FUSE_SAMPLER"); ctx->fuse_sampler = e && !strcmp(e, "1"); }        // "1": the decode kernel's last CTA samples the token (one launch per token); measured neutral end to end
     { const char * e = getenv("BARK_B200_GEMM_F32C"); ctx->gemm_f32c = e && !strcmp(e, "1"); }
     { const char * e = getenv("BARK_B200_ADAPT"); ctx->adapt_on = e && !strcmp(e, "1"); }                     // "1": self-tuning head starts (experiment; measured WORSE: the feedback is collective and runs away)
     ctx->params = params;

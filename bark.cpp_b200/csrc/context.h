@@ -32,6 +32,7 @@ struct bark_context {
     bool kv_reuse = true; unsigned long long n_kv_reused = 0;   // coarse windows start from the cached prefix (bark_api.cu run_coarse)
     // decode-kernel knobs (BARK_B200_DECODE_TIMING_TID / BARK_B200_POLL_NS / BARK_B200_POLL_FIRST_NS); defaults from the measured sweep
     // in profiles/r01_decode_knob_sweep.md: 40 ns back-off between polls, 500 ns head start for the two residual exchanges
+    bool fuse_sampler = false; unsigned * d_done_counter = nullptr;  // BARK_B200_FUSE_SAMPLER=1: the decode kernel samples its own token (6411 instead of 8037 launches per clip; 233.3 vs 233.7 ms: neutral, so off)
     bool decode_cluster = false;                     // BARK_B200_DECODE=cluster: the decode step inside one 16-CTA cluster (decode_kernels.cu) where the model fits
     bool gemm_f32c = false;                          // BARK_B200_GEMM_F32C=1: multi-row passes of f16 models keep operands as f16 values in f32 containers
     bool adapt_on = false;                           // BARK_B200_ADAPT=1: self-tuning head starts instead of the fixed knobs below (measured worse, see decode_kernels.cu)
@@ -99,7 +100,10 @@ bool codec_decode(bark_context * ctx, const int32_t * codes, int T);
 // sampling.cu / gpt_forward.cu / bark_api.cu
 void sample_rows(const float * logits, int ld, int n, int rows, float temp, const double * d_u, int32_t * d_out_tok, int tok_add, int32_t * d_feed,
                  float * d_eos_p, int32_t * d_flags, int force_flag, cudaStream_t s);
-bool gpt_decode_chained(bark_context * ctx, GPTModel & m, const int32_t * d_token, int * n_past, int lm_lo, int lm_hi);
+// fs != null: the decode kernel also samples the token (fused sampler), leaving it in fs->d_tok / fs->d_feed
+struct FusedSample { int n; float temp; const double * d_u; int32_t * d_tok; int tok_add; int32_t * d_feed; float * d_eos; int32_t * d_flags; int force; };
+bool fused_sampler_available(const bark_context * ctx, const GPTModel & m, int samp_n);
+bool gpt_decode_chained(bark_context * ctx, GPTModel & m, const int32_t * d_token, int * n_past, int lm_lo, int lm_hi, const FusedSample * fs = nullptr);
 bool sample_device(bark_context * ctx, GPTModel & m, const float * d_logits, int ld, int n, int rows, float temp, int32_t * out_tok, float * out_eos);
 int32_t sample_token_given_u(const float * logits, int n, float temp, double u, float * eos_p);
 

@@ -33,6 +33,7 @@
 //   P6  mlp/c_proj rows + residual                                                     -> x
 // then LN_f -> lm_head rows [lm_lo, lm_hi) -> logits (plain stores; the kernel ends).
 #include "gpt_kernels.h"
+#include "sampling.cuh"
 
 namespace bark {
 
@@ -907,6 +908,20 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
     tstamp<TM>(2);
     run_phase<WT, TM>(4 * L, EP_LOGITS, 0, 0, 3);
     if (A.adapt && tid < XT_COUNT) A.adapt[blockIdx.x * XT_COUNT + tid] = s_adapt[tid];      // (last changed a whole phase ago, by thread 0)
+    // ---- fused sampler: the CTA whose logits land last draws the token (gpt_sample, sampling.cuh) and leaves it where the next
+    // launch reads its input; the weight staging area is free by now and holds the working row ----
+    if (A.samp_n > 0) {
+        __shared__ int s_last;
+        __syncthreads();                                         // this CTA's logits are stored
+        if (tid == 0) { __threadfence(); s_last = atomicAdd(A.done_counter, 1u) == gridDim.x - 1 ? 1 : 0; }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            sample_row_body<kThreads>(reinterpret_cast<float *>(dsm + SmemLayout::wslot), A.logits + A.lm_lo, A.samp_n, A.samp_temp, A.samp_temp != 0.0f ? __ldcg(A.samp_u) : 0.0,
+                                      A.samp_tok, A.samp_tok_add, A.samp_feed, A.samp_eos, A.samp_flags, A.samp_force);
+            if (tid == 0) *A.done_counter = 0u;                  // for the next launch (stream order)
+        }
+    }
 }
 
 // =====================================================================================================================

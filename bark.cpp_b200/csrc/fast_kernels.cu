@@ -366,7 +366,7 @@ struct Flash2Smem {
     static constexpr int v = k + kKvStages * kKeyBlk2 * 128;       // 3 stages x 2 atoms x [64 d][64 keys] f16         48 KB
     static constexpr int p = v + kKvStages * kKeyBlk2 * 128;       // 2 buffers x 2 atoms x [128 queries][64 keys]     64 KB
     static constexpr int bars = p + 2 * 2 * 128 * 128;             // q_full, kv_full[3], kv_empty[3], s_full[2], p_ready[2], pv_full[2]
-    static constexpr int total = bars + 16 * 8;
+    static constexpr int total = bars + 16 * 8 + 4 * 128 * 4;          // + [2][2][128] floats: row maxima exchanged by the two threads of a row (flash_attn3_kernel)
 };
 
 __global__ void __launch_bounds__(kGemmThreads, 1) flash_attn2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmVT,
@@ -511,6 +511,156 @@ __global__ void __launch_bounds__(kGemmThreads, 1) flash_attn2_kernel(const __gr
     if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
+// Same pipeline with EIGHT soft_max warps (two per scheduler): warps sw and sw + 4 share a TMEM lane quarter (32 query rows) and split the
+// 128 key columns of a block (and the 64 output columns) in halves; only the row maximum crosses between the two threads of a row
+// (shared memory + a 64-thread named barrier).  With four warps the soft_max was issue-bound: one warp per scheduler, ~10 instructions
+// per key per thread.
+__global__ void __launch_bounds__(320, 1) flash_attn3_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmVT,
+                                                                       int n_keys, int k_col0, float scale_log2e, __half * __restrict__ out, int ldo) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char * smem = (unsigned char *)(((uintptr_t) smem_raw + 1023) & ~(uintptr_t) 1023);
+    uint64_t * bars = reinterpret_cast<uint64_t *>(smem + Flash2Smem::bars);
+    uint32_t * tmem_slot = reinterpret_cast<uint32_t *>(bars + 14);
+    const uint32_t b0 = smem_u32(bars);
+    const uint32_t q_full = b0, kv_full0 = b0 + 8, kv_empty0 = b0 + 32, s_full0 = b0 + 56, p_ready0 = b0 + 72, pv_full0 = b0 + 88;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int h = blockIdx.y, q0 = blockIdx.x * 128;
+    const int nblk = n_keys / kKeyBlk2;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmQK); prefetch_tmap(&tmVT);
+        mbar_init(q_full, 1);
+        for (int s = 0; s < kKvStages; s++) { mbar_init(kv_full0 + s * 8, 1); mbar_init(kv_empty0 + s * 8, 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(s_full0 + s * 8, 1); mbar_init(p_ready0 + s * 8, 256); mbar_init(pv_full0 + s * 8, 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);       // S[2]: columns [0,128) [128,256);  P.V[2]: [256,320) [320,384)
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    pdl_launch_dependents();
+    pdl_wait();
+    const uint32_t sQ = smem_u32(smem + Flash2Smem::q), sK = smem_u32(smem + Flash2Smem::k), sV = smem_u32(smem + Flash2Smem::v), sP = smem_u32(smem + Flash2Smem::p);
+    constexpr uint32_t kStage = kKeyBlk2 * 128, kPBuf = 2 * 128 * 128;
+
+    if (warp == 0) {
+        if (lane == 0) {                                      // ===== TMA producer =====
+            mbar_expect_tx(q_full, 128 * 128);
+            tma_load_2d(sQ, &tmQK, h * kHeadD, q0, q_full);
+            for (int j = 0; j < nblk; j++) {
+                const int s = j % kKvStages;
+                mbar_wait(kv_empty0 + s * 8, ((j / kKvStages) & 1) ^ 1);
+                mbar_expect_tx(kv_full0 + s * 8, 2 * kStage);
+                tma_load_2d(sK + s * kStage, &tmQK, k_col0 + h * kHeadD, j * kKeyBlk2, kv_full0 + s * 8);
+                for (int a = 0; a < 2; a++) tma_load_2d(sV + s * kStage + a * 64 * 128, &tmVT, j * kKeyBlk2 + a * 64, h * kHeadD, kv_full0 + s * 8);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                                      // ===== MMA issuer =====
+            constexpr uint32_t idesc_s = f16_idesc(128, kKeyBlk2), idesc_o = f16_idesc(128, kHeadD);
+            auto issue_s = [&](int j) {                       // S_j = Q K_j^T  (128 x 128, K = 64) into S[j & 1]
+                const int s = j % kKvStages;
+                mbar_wait(kv_full0 + s * 8, (j / kKvStages) & 1);
+                tc_fence_after();
+                const uint64_t dq = kmajor_sw128_desc(sQ), dk = kmajor_sw128_desc(sK + s * kStage);
+#pragma unroll
+                for (int k = 0; k < kHeadD / 16; k++) umma_f16(tmem + (uint32_t)(j & 1) * 128, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+                umma_commit(s_full0 + (j & 1) * 8);
+            };
+            mbar_wait(q_full, 0);
+            issue_s(0);
+            for (int j = 0; j < nblk; j++) {
+                if (j + 1 < nblk) issue_s(j + 1);             // runs on the tensor pipe while the soft_max threads work on block j
+                mbar_wait(p_ready0 + (j & 1) * 8, (j >> 1) & 1);
+                tc_fence_after();
+                const int s = j % kKvStages;
+#pragma unroll
+                for (int kk = 0; kk < kKeyBlk2 / 16; kk++) {  // P.V of block j (128 x 64, K = 128 keys) into PV[j & 1]
+                    const uint64_t dp = kmajor_sw128_desc(sP + (uint32_t)(j & 1) * kPBuf + (kk >> 2) * 128 * 128) + 2 * (kk & 3);
+                    const uint64_t dv = kmajor_sw128_desc(sV + s * kStage + (kk >> 2) * 64 * 128) + 2 * (kk & 3);
+                    umma_f16(tmem + 256 + (uint32_t)(j & 1) * 64, dp, dv, idesc_o, kk != 0);
+                }
+                umma_commit(kv_empty0 + s * 8);
+                umma_commit(pv_full0 + (j & 1) * 8);
+            }
+        }
+    } else {                                                  // ===== soft_max + output: two threads per query row (column halves) =====
+        const int sw = warp - 2, q = warp & 3, half = sw >> 2, row = q * 32 + lane;
+        const uint32_t tlane = (uint32_t)(q * 32) << 16;
+        float * xmax = reinterpret_cast<float *>(smem + Flash2Smem::bars + 15 * 8 + 8);      // [2][128] row maxima of the two halves (behind the barriers)
+        auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory"); };   // the two warps of this lane quarter
+        float o[32];
+#pragma unroll
+        for (int i = 0; i < 32; i++) o[i] = 0.0f;
+        float m_run = -INFINITY, l_run = 0.0f, alpha_prev = 0.0f;
+        auto accumulate = [&](int j, float alpha) {           // O[:, half] = O * alpha + (P.V of block j)[:, half]
+            mbar_wait(pv_full0 + (j & 1) * 8, (j >> 1) & 1);
+            tc_fence_after();
+            float v[32]; tmem_ld32(tmem + tlane + 256 + (uint32_t)(j & 1) * 64 + half * 32, v);
+#pragma unroll
+            for (int i = 0; i < 32; i++) o[i] = o[i] * alpha + v[i];
+        };
+        for (int j = 0; j < nblk; j++) {
+            mbar_wait(s_full0 + (j & 1) * 8, (j >> 1) & 1);
+            tc_fence_after();
+            const uint32_t ts = tmem + tlane + (uint32_t)(j & 1) * 128 + half * 64;
+            float mx = m_run;
+#pragma unroll 1
+            for (int c = 0; c < 2; c++) {
+                float v[32]; tmem_ld32(ts + c * 32, v);
+#pragma unroll
+                for (int i = 0; i < 32; i++) mx = fmaxf(mx, v[i]);
+            }
+            xmax[((j & 1) * 2 + half) * 128 + row] = mx;
+            pair_sync();
+            mx = fmaxf(mx, xmax[((j & 1) * 2 + (half ^ 1)) * 128 + row]);
+            const float alpha = exp2f((m_run - mx) * scale_log2e);
+            float sum = 0.0f;
+#pragma unroll 1
+            for (int c = 0; c < 2; c++) {
+                float v[32]; tmem_ld32(ts + c * 32, v);
+                uint32_t pk[16];
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    const float p0 = exp2f((v[i] - mx) * scale_log2e), p1 = exp2f((v[i + 1] - mx) * scale_log2e);
+                    const __half2 hp = __floats2half2_rn(p0, p1);
+                    sum += __low2float(hp) + __high2float(hp);
+                    pk[i >> 1] = *reinterpret_cast<const uint32_t *>(&hp);
+                }
+                const uint32_t base = sP + (uint32_t)(j & 1) * kPBuf + half * 128 * 128 + row * 128;      // this half's 64 keys = atom `half`
+#pragma unroll
+                for (int w = 0; w < 4; w++) {
+                    const uint32_t chunk = (uint32_t)(c * 4 + w) ^ (uint32_t)(row & 7);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + chunk * 16), "r"(pk[4 * w]), "r"(pk[4 * w + 1]), "r"(pk[4 * w + 2]), "r"(pk[4 * w + 3]) : "memory");
+                }
+            }
+            l_run = l_run * alpha + sum;
+            m_run = mx;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            tc_fence_before();
+            mbar_arrive(p_ready0 + (j & 1) * 8);
+            if (j > 0) accumulate(j - 1, alpha_prev);
+            alpha_prev = alpha;
+        }
+        accumulate(nblk - 1, alpha_prev);
+        xmax[half * 128 + row] = l_run;                       // the row sum is the sum of the two halves' sums (same maxima, same rescaling)
+        pair_sync();
+        const float inv = 1.0f / (l_run + xmax[(half ^ 1) * 128 + row]);
+        __half * dst = out + (size_t)(q0 + row) * ldo + h * kHeadD + half * 32;
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+            __half hh[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++) hh[e] = __float2half_rn(o[i + e] * inv);
+            *reinterpret_cast<uint4 *>(dst + i) = *reinterpret_cast<const uint4 *>(hh);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
 // ------------------------------------------------------------------------------------------------
 // LayerNorm -> f16 row-major operand: one warp per row
 // ------------------------------------------------------------------------------------------------
@@ -606,11 +756,13 @@ bool fast_gemm(const __half * A, int lda, const __half * W, int ldw, int M, int 
 bool fast_attention(const __half * qk, int ldq, int k_col0, const __half * vt, int n, int E, int H, __half * out, cudaStream_t s) {
     if (E / H != kHeadD || n % kKeyBlk != 0 || n < kKeyBlk) { fprintf(stderr, "bark_b200 fast mode: attention needs head size 64 and a multiple of 256 positions (got %d heads of %d, %d positions)\n", H, E / H, n); return false; }
     static const bool v1 = [] { const char * e = getenv("BARK_B200_FLASH"); return e && !strcmp(e, "v1"); }();       // the serial first version, for A-B runs
+    static const bool v2 = [] { const char * e = getenv("BARK_B200_FLASH"); return e && !strcmp(e, "v2"); }();       // pipelined, four soft_max warps
     const size_t smem = (v1 ? (size_t) FlashSmem::total : (size_t) Flash2Smem::total) + 1024;
     static std::atomic<unsigned long long> configured{0};
     if (first_use_on_this_device(configured)) {
         BARK_CUDA_CHECK(cudaFuncSetAttribute(flash_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FlashSmem::total + 1024));
         BARK_CUDA_CHECK(cudaFuncSetAttribute(flash_attn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) Flash2Smem::total + 1024));
+        BARK_CUDA_CHECK(cudaFuncSetAttribute(flash_attn3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) Flash2Smem::total + 1024));
     }
     CUtensorMap tqk, tvt;
     if (!make_map(&tqk, qk, n, k_col0 + E, ldq, 128) || !make_map(&tvt, vt, E, n, n, 64)) return false;
@@ -618,7 +770,8 @@ bool fast_attention(const __half * qk, int ldq, int k_col0, const __half * vt, i
     g_next_flops = 4.0 * (double) n * n * E;
     g_next_bytes = 2.0 * 4.0 * (double) n * E;
     if (v1) BARK_LAUNCH_PDL(flash_attn_kernel, dim3(n / 128, H), dim3(kGemmThreads), smem, s, tqk, tvt, n, k_col0, scale_log2e, out, E);
-    else    BARK_LAUNCH_PDL(flash_attn2_kernel, dim3(n / 128, H), dim3(kGemmThreads), smem, s, tqk, tvt, n, k_col0, scale_log2e, out, E);
+    else if (v2) BARK_LAUNCH_PDL(flash_attn2_kernel, dim3(n / 128, H), dim3(kGemmThreads), smem, s, tqk, tvt, n, k_col0, scale_log2e, out, E);
+    else    BARK_LAUNCH_PDL(flash_attn3_kernel, dim3(n / 128, H), dim3(320), smem, s, tqk, tvt, n, k_col0, scale_log2e, out, E);
     return true;
 }
 

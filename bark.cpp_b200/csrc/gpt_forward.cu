@@ -95,7 +95,7 @@ void build_decode_tables(bark_context * ctx, GPTModel & m) {
 }
 
 // one decode token through the persistent kernel
-static void decode_step(bark_context * ctx, GPTModel & m, int token, const int32_t * d_token, int n_past, int lm_lo, int lm_hi) {
+static void decode_step(bark_context * ctx, GPTModel & m, int token, const int32_t * d_token, int n_past, int lm_lo, int lm_hi, const FusedSample * fs = nullptr) {
     // Epochs are 32-bit and must never repeat while a stale word could still carry the old value (~30 M tokens for 24 layers):
     // before the counter wraps, drain the stream, clear every exchange word (epoch 0 = never published) and start over.
     const unsigned step_tags = (unsigned) decode_tags_per_step(m.n_layer);
@@ -122,6 +122,10 @@ static void decode_step(bark_context * ctx, GPTModel & m, int token, const int32
     a.inv_E = 1.0 / (double) m.n_embd;
     a.adapt = ctx->adapt_on ? m.d_adapt : nullptr;
     for (int i = 0; i < 6; i++) a.headstart[i] = ctx->headstart[i];
+    if (fs) {
+        a.samp_n = fs->n; a.samp_temp = fs->temp; a.samp_u = fs->d_u; a.samp_tok = fs->d_tok; a.samp_tok_add = fs->tok_add; a.samp_feed = fs->d_feed;
+        a.samp_eos = fs->d_eos; a.samp_flags = fs->d_flags; a.samp_force = fs->force; a.done_counter = ctx->d_done_counter;
+    }
     a.timing_tid = ctx->timing_tid; a.poll_ns = ctx->poll_ns; a.first_ns = ctx->first_ns; a.att_ns = ctx->att_ns;
     const double es = m.wtype == W_Q4_0 ? 18.0 / 32.0 : m.wtype == W_F16 ? 2.0 : 4.0;
     const double E = m.n_embd, L = m.n_layer;
@@ -188,11 +192,15 @@ bool gpt_eval(bark_context * ctx, GPTModel & m, const int32_t * tokens, int n, i
 
 // One decode step whose input token is read from device memory (the previous step's sample): nothing to wait for on the
 // host, so a whole window of steps is enqueued back to back.
-bool gpt_decode_chained(bark_context * ctx, GPTModel & m, const int32_t * d_token, int * n_past, int lm_lo, int lm_hi) {
+bool fused_sampler_available(const bark_context * ctx, const GPTModel & m, int samp_n) {
+    return ctx->fuse_sampler && ctx->use_decode_kernel && m.decode_ok && !ctx->decode_cluster && (size_t) samp_n * 4 <= 64 * 1024;
+}
+
+bool gpt_decode_chained(bark_context * ctx, GPTModel & m, const int32_t * d_token, int * n_past, int lm_lo, int lm_hi, const FusedSample * fs) {
     if (!ctx->use_decode_kernel || !m.decode_ok || *n_past < 1) { fprintf(stderr, "%s: needs the persistent decode kernel and a filled KV cache\n", __func__); return false; }
     if (*n_past + 1 > m.block_size) { fprintf(stderr, "%s: context overflow (n_past %d + 1 > %d)\n", __func__, *n_past, m.block_size); return false; }
     if (lm_hi <= 0 || lm_hi > m.n_out_vocab || lm_lo < 0 || lm_lo >= lm_hi) { lm_lo = 0; lm_hi = m.n_out_vocab; }
-    decode_step(ctx, m, 0, d_token, *n_past, lm_lo, lm_hi);
+    decode_step(ctx, m, 0, d_token, *n_past, lm_lo, lm_hi, fs);
     ctx->last_logits = m.glogits;
     *n_past += 1;
     return true;

@@ -81,6 +81,10 @@ struct DecodeArgs {
     int E, H, L, block_size, n_past, token, lm_lo, lm_hi;
     const int32_t * token_ptr; int n_vocab_in;   // token_ptr != null: read the input token from device memory (written by sample_rows_kernel), clamped to the vocabulary
     double inv_E;                        // 1.0 / E (double), for the division-free LayerNorm decision
+    // fused sampler (samp_n > 0): the CTA that finishes its lm_head rows last samples the token from logits [lm_lo, lm_lo + samp_n)
+    // (sampling.cuh) — one launch per token instead of two
+    int samp_n; float samp_temp; const double * samp_u; int32_t * samp_tok; int samp_tok_add; int32_t * samp_feed; float * samp_eos; int32_t * samp_flags; int samp_force;
+    unsigned * done_counter;
     unsigned headstart[6];               // fixed head start (ns) before the first poll of each exchange: q, att (CTAs without a soft_max tile), x1, ff, x2, scores
     unsigned * adapt;                    // [n_cta][8] adaptive head starts of the exchanges, carried from token to token (null: fixed knobs)
     int timing_tid; unsigned poll_ns, first_ns, att_ns;   // debug: stamping thread; back-off between polls of the tagged words; delay before the first poll of the residual exchanges (ns)

@@ -47,55 +47,58 @@ __global__ void quantize_q8_kernel(const float * __restrict__ x, int ldx, int ro
     if (lane == 0) d_out[(size_t) r * nb + b] = __half2float(__float2half_rn(d));          // y[i].d = GGML_FP32_TO_FP16(d)
 }
 
-// activation rows per warp: 8 for the multi-row passes, 1 for a single decode row (the 8-row kernel repeats a lone row 8 times)
-
-// out[m][o] = vec_dot_q4_0_q8_0(W[o], A[m]); warp = 4 outputs x kQ4MT rows; block = 8 warps = 32 outputs
-template <int kQ4MT>
+// out[m][o] = vec_dot_q4_0_q8_0(W[o], A[m]).  Eight lanes own the eight float accumulators of one output; an 8-lane group walks OPW
+// outputs against MT activation rows (MT x OPW accumulators per lane), so one load of an activation word serves OPW outputs: with
+// one output per group the kernel was bound by the activation-load instructions (37 M per fc pass).  MT = 8, OPW = 4 for the
+// multi-row passes (warp = 16 outputs x 8 rows, block = 128 outputs); MT = 1, OPW = 1 for a single decode row.
+template <int kQ4MT, int OPW>
 __global__ void __launch_bounds__(256) q4_matmul_kernel(const uint4 * __restrict__ qs, const __half * __restrict__ scales, int K, int O,
                                                         const int8_t * __restrict__ aq, const float * __restrict__ ad, int M, MatmulEpilogue ep) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int l = lane & 7, grp = lane >> 3;
-    const int o = (blockIdx.x * 8 + warp) * 4 + grp;
+    const int o0 = ((blockIdx.x * 8 + warp) * 4 + grp) * OPW;      // first output of this 8-lane group
     const int m0 = blockIdx.y * kQ4MT;
     const int nb = K >> 5;
-    const int oc = min(o, O - 1);                                 // keep every lane in the shuffles; out-of-range outputs are not stored
-    const uint32_t * wq = reinterpret_cast<const uint32_t *>(qs + (size_t) oc * nb) + (l & 3);
-    const __half * ws = scales + (size_t) oc * nb;
     const bool high = l >= 4;                                     // lanes 4..7: elements 16..31 = high nibbles of the same bytes
-    float acc[kQ4MT];
+    const uint32_t * wq[OPW]; const __half * ws[OPW];
 #pragma unroll
-    for (int mi = 0; mi < kQ4MT; mi++) acc[mi] = 0.0f;
-    // the weight words and scales of 8 blocks are fetched together (the chain itself is sequential in b, its loads need not be: a
-    // single-row decode step was ~60 us of dependent L2 round trips per mat-mul before)
-    constexpr int UB = 8;
-    for (int b0 = 0; b0 < nb; b0 += UB) {
-        uint32_t wr[UB]; float dwr[UB];
+    for (int oo = 0; oo < OPW; oo++) {
+        const int oc = min(o0 + oo, O - 1);                       // keep every lane in the shuffles; out-of-range outputs are not stored
+        wq[oo] = reinterpret_cast<const uint32_t *>(qs + (size_t) oc * nb) + (l & 3); ws[oo] = scales + (size_t) oc * nb;
+    }
+    float acc[OPW][kQ4MT];
 #pragma unroll
-        for (int u = 0; u < UB; u++) if (b0 + u < nb) { wr[u] = __ldg(wq + (size_t)(b0 + u) * 4); dwr[u] = __half2float(__ldg(ws + b0 + u)); }
+    for (int oo = 0; oo < OPW; oo++)
 #pragma unroll
-        for (int u = 0; u < UB; u++) {
-            const int b = b0 + u;
-            if (b < nb) {
-                const uint32_t w = (high ? (wr[u] >> 4) : wr[u]) & 0x0f0f0f0fu;
-                const int wi = (int) __vsub4(w, 0x08080808u);     // nibble - 8 per byte
+        for (int mi = 0; mi < kQ4MT; mi++) acc[oo][mi] = 0.0f;
+    for (int b = 0; b < nb; b++) {
+        int yi[kQ4MT]; float da[kQ4MT];
 #pragma unroll
-                for (int mi = 0; mi < kQ4MT; mi++) {
-                    const int m = min(m0 + mi, M - 1);
-                    const int yi = __ldg(reinterpret_cast<const int *>(aq + (size_t) m * K + b * 32) + l);
-                    const float d = __fmul_rn(dwr[u], __ldg(ad + (size_t) m * nb + b));
-                    acc[mi] = __fmaf_rn(d, (float) __dp4a(wi, yi, 0), acc[mi]);
-                }
-            }
+        for (int mi = 0; mi < kQ4MT; mi++) {
+            const int m = min(m0 + mi, M - 1);
+            yi[mi] = __ldg(reinterpret_cast<const int *>(aq + (size_t) m * K + b * 32) + l);
+            da[mi] = __ldg(ad + (size_t) m * nb + b);
+        }
+#pragma unroll
+        for (int oo = 0; oo < OPW; oo++) {
+            uint32_t w = __ldg(wq[oo] + (size_t) b * 4);
+            w = (high ? (w >> 4) : w) & 0x0f0f0f0fu;
+            const int wi = (int) __vsub4(w, 0x08080808u);         // nibble - 8 per byte
+            const float dw = __half2float(__ldg(ws[oo] + b));
+#pragma unroll
+            for (int mi = 0; mi < kQ4MT; mi++) acc[oo][mi] = __fmaf_rn(__fmul_rn(dw, da[mi]), (float) __dp4a(wi, yi[mi], 0), acc[oo][mi]);
         }
     }
 #pragma unroll
-    for (int mi = 0; mi < kQ4MT; mi++) {
-        float t = acc[mi];                                        // hsum_float_8 (ggml-quants.c:48-54)
-        t = __fadd_rn(t, __shfl_xor_sync(0xffffffffu, t, 4));
-        t = __fadd_rn(t, __shfl_xor_sync(0xffffffffu, t, 2));
-        t = __fadd_rn(t, __shfl_xor_sync(0xffffffffu, t, 1));
-        if (l == 0 && o < O && m0 + mi < M) matmul_epilogue(ep, m0 + mi, o, t);
-    }
+    for (int oo = 0; oo < OPW; oo++)
+#pragma unroll
+        for (int mi = 0; mi < kQ4MT; mi++) {
+            float t = acc[oo][mi];                                // hsum_float_8 (ggml-quants.c:48-54)
+            t = __fadd_rn(t, __shfl_xor_sync(0xffffffffu, t, 4));
+            t = __fadd_rn(t, __shfl_xor_sync(0xffffffffu, t, 2));
+            t = __fadd_rn(t, __shfl_xor_sync(0xffffffffu, t, 1));
+            if (l == 0 && o0 + oo < O && m0 + mi < M) matmul_epilogue(ep, m0 + mi, o0 + oo, t);
+        }
 }
 
 thread_local int8_t * g_q8 = nullptr; thread_local float * g_q8d = nullptr;   // per host thread: one thread drives one context
@@ -116,8 +119,8 @@ void q4_matmul(const DMat & W, const void * act, int ld_act, int rows, const Mat
     BARK_LAUNCH(quantize_q8_kernel, (unsigned)((warps * 32 + 255) / 256), 256, 0, s, (const float *) act, ld_act, rows, W.K, g_q8, g_q8d);
     g_next_bytes = (double) W.n_out * nb * 18.0 + (double) rows * (W.K * 1.0 + nb * 4.0 + W.n_out * 4.0);
     g_next_flops = 2.0 * rows * (double) W.n_out * W.K;
-    if (rows == 1) BARK_LAUNCH(q4_matmul_kernel<1>, dim3((W.n_out + 31) / 32, 1), 256, 0, s, (const uint4 *) W.p, (const __half *) W.scales, W.K, W.n_out, g_q8, g_q8d, rows, ep);
-    else           BARK_LAUNCH(q4_matmul_kernel<8>, dim3((W.n_out + 31) / 32, (rows + 7) / 8), 256, 0, s, (const uint4 *) W.p, (const __half *) W.scales, W.K, W.n_out, g_q8, g_q8d, rows, ep);
+    if (rows == 1) BARK_LAUNCH((q4_matmul_kernel<1, 1>), dim3((W.n_out + 31) / 32, 1), 256, 0, s, (const uint4 *) W.p, (const __half *) W.scales, W.K, W.n_out, g_q8, g_q8d, rows, ep);
+    else           BARK_LAUNCH((q4_matmul_kernel<8, 4>), dim3((W.n_out + 127) / 128, (rows + 7) / 8), 256, 0, s, (const uint4 *) W.p, (const __half *) W.scales, W.K, W.n_out, g_q8, g_q8d, rows, ep);
 }
 
 }  // namespace bark

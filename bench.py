@@ -60,7 +60,9 @@ def peaks():
 
 def measured_traffic(kernel):
     """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture (profiles/, tools/summarize_ncu.py traffic); None if not captured"""
-    p = os.path.join(ROOT, "profiles", "r01_decode_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r02_decode_traffic.json")
+    if not os.path.exists(p):
+        p = os.path.join(ROOT, "profiles", "r01_decode_traffic.json")
     if os.path.exists(p):
         d = json.load(open(p))
         if d.get("kernel", "").split("<")[0] == kernel.split("<")[0]:
