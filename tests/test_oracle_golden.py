@@ -15,7 +15,8 @@ def sha(a):
     return hashlib.sha1(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
-GOLDENS = sorted(p for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")) if "gelu" not in p and "small_" not in os.path.basename(p))   # small_*: tests/test_baseline_config0.py
+# small_* / large_*: true-size fixtures (tests/test_baseline_config0.py, tests/test_true_size_gpu.py); minutes of CPU time each on the oracle
+GOLDENS = sorted(p for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")) if "gelu" not in p and not os.path.basename(p).startswith(("small_", "large_")))
 
 
 def test_goldens_present():
