@@ -203,9 +203,11 @@ def run_ours(args):
         torch.cuda.set_device(local)
         dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
         dist = dist_mod
-    path = weights_path()
+    if rank == 0:
+        weights_path()                                        # one writer; the other ranks find the file after the barrier
     if dist:
         dist.barrier()
+    path = weights_path()
     device = local if world > 1 else int(os.environ.get("BARK_B200_DEVICE", "0"))
     pinned = pin_to_gpu_numa(device) if world > 1 else None
     wl = rank_workload(rank)
