@@ -93,9 +93,9 @@ bool load_gpt(bark_context * ctx, std::ifstream & f, GPTModel & m, const char * 
     }
     m.wtype = (WType) wt;
     const int E = m.n_embd;
-    if (m.n_layer <= 0 || m.n_head <= 0 || E <= 0 || E % 32 != 0 || E % m.n_head != 0 || (E / m.n_head) % 32 != 0 || (E / m.n_head) > 128 ||
+    if (m.n_layer <= 0 || m.n_head <= 0 || E <= 0 || E > 1024 || E % 32 != 0 || E % m.n_head != 0 || (E / m.n_head) % 32 != 0 || (E / m.n_head) > 128 ||
         m.block_size <= 0 || m.block_size > 1024 || m.n_wtes < 1 || m.n_wtes > 8 || m.n_lm_heads < 1 || m.n_lm_heads > 8) {
-        fprintf(stderr, "%s: unsupported %s model dimensions (need n_embd %% 32 == 0, head size in {32,64,96,128}, block_size <= 1024)\n", __func__, what);
+        fprintf(stderr, "%s: unsupported %s model dimensions (need n_embd %% 32 == 0 and <= 1024, head size in {32,64,96,128}, block_size <= 1024)\n", __func__, what);
         return false;
     }
     const bool causal = (m.n_lm_heads == 1 && m.n_wtes == 1);
