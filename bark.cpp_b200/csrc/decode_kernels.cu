@@ -720,16 +720,14 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
         if (score_cta) {
             const float * Kc = A.mem_k + (size_t) il * ctx * E;
             const int total = H * n_kv, gw = (int)(blockIdx.x - score_cta0) * kWarps + warp, nw = (int)(gridDim.x - score_cta0) * kWarps;
-            // t / n_kv without the ~30-instruction integer division (16 of them per warp per layer sat between "q arrived" and "scores done"):
-            // float estimate + one correction step each way; exact for t < 2^23
-            const float inv_nkv = 1.0f / (float) n_kv;
-            auto head_of = [&](int t) { int h = (int)((float) t * inv_nkv); h -= (h * n_kv > t); h += ((h + 1) * n_kv <= t); return h; };
+            // (t / n_kv stays an integer division: a float-reciprocal version cost 216 bytes of extra spills in this register-capped kernel
+            // and +19 % per token — measured, round 2)
             float kf[kMaxTasks][DSTEPS];
 #pragma unroll
             for (int i = 0; i < kMaxTasks; i++) {
                 const int t = gw + i * nw;
                 if (t < total) {
-                    const int h = head_of(t), k = t - h * n_kv;
+                    const int h = t / n_kv, k = t - h * n_kv;
                     if (k < n_past) {
 #pragma unroll
                         for (int c = 0; c < DSTEPS; c++) kf[i][c] = __ldcg(Kc + (size_t) k * E + h * D + c * 32 + lane);
@@ -743,7 +741,7 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
             for (int i = 0; i < kMaxTasks; i++) {
                 const int t = gw + i * nw;
                 if (t < total) {
-                    const int h = head_of(t), k = t - h * n_kv;
+                    const int h = t / n_kv, k = t - h * n_kv;
                     float acc = 0.0f;
 #pragma unroll
                     for (int c = 0; c < DSTEPS; c++) {
@@ -756,7 +754,7 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
             }
 #pragma unroll 1
             for (int t = gw + kMaxTasks * nw; t < total; t += nw) {   // (not reached for the supported shapes; keeps the kernel total)
-                const int h = head_of(t), k = t - h * n_kv;
+                const int h = t / n_kv, k = t - h * n_kv;
                 float acc = 0.0f;
 #pragma unroll
                 for (int c = 0; c < DSTEPS; c++) {
