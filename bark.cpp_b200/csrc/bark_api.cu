@@ -526,6 +526,7 @@ extern "C" struct bark_context * bark_load_model(const char * model_path, struct
     { const char * e = getenv("BARK_B200_POLL_FIRST_NS"); if (e && atoi(e) >= 0 && atoi(e) <= 100000) ctx->first_ns = (unsigned) atoi(e); }
     ctx->headstart[1] = ctx->att_ns; ctx->headstart[2] = ctx->headstart[4] = ctx->first_ns;
     { const char * e = getenv("BARK_B200_HEADSTART"); if (e) { unsigned v[6]; if (sscanf(e, "%u:%u:%u:%u:%u:%u", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5]) == 6) for (int i = 0; i < 6; i++) ctx->headstart[i] = std::min(v[i], 100000u); } }
+    { const char * e = getenv("BARK_B200_KV_PREFETCH"); ctx->kv_prefetch = e && !strcmp(e, "1"); }
     { const char * e = getenv("BARK_B200_FUSE_SAMPLER"); ctx->fuse_sampler = e && !strcmp(e, "1"); }        // "1": the decode kernel's last CTA samples the token (one launch per token); measured neutral end to end
     { const char * e = getenv("BARK_B200_GEMM_F32C"); ctx->gemm_f32c = e && !strcmp(e, "1"); }
     { const char * e = getenv("BARK_B200_ADAPT"); ctx->adapt_on = e && !strcmp(e, "1"); }                     // "1": self-tuning head starts (experiment; measured WORSE: the feedback is collective and runs away)

@@ -32,6 +32,7 @@ struct bark_context {
     bool kv_reuse = true; unsigned long long n_kv_reused = 0;   // coarse windows start from the cached prefix (bark_api.cu run_coarse)
     // decode-kernel knobs (BARK_B200_DECODE_TIMING_TID / BARK_B200_POLL_NS / BARK_B200_POLL_FIRST_NS); defaults from the measured sweep
     // in profiles/r01_decode_knob_sweep.md: 40 ns back-off between polls, 500 ns head start for the two residual exchanges
+    bool kv_prefetch = false;          // BARK_B200_KV_PREFETCH=1: bulk L2 prefetch of the next layer's K / V rows inside the decode step
     bool fuse_sampler = false; unsigned * d_done_counter = nullptr;  // BARK_B200_FUSE_SAMPLER=1: the decode kernel samples its own token (6411 instead of 8037 launches per clip; 233.3 vs 233.7 ms: neutral, so off)
     bool decode_cluster = false;                     // BARK_B200_DECODE=cluster: the decode step inside one 16-CTA cluster (decode_kernels.cu) where the model fits
     bool gemm_f32c = false;                          // BARK_B200_GEMM_F32C=1: multi-row passes of f16 models keep operands as f16 values in f32 containers

@@ -76,6 +76,10 @@ __device__ __forceinline__ void tma_bulk_g2s_stream(uint32_t dst, const void * s
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
 }
+// ask the copy engine to bring [p, p + bytes) into L2 (no destination, no completion to wait for); 16-byte aligned address and size
+__device__ __forceinline__ void l2_prefetch_bulk(const void * p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ unsigned long long l2_evict_first_policy() {
     unsigned long long pol; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     return pol;
@@ -150,6 +154,15 @@ __device__ __forceinline__ void tstamp(int i) {
     }
 }
 
+// finer stamps of CTA 0 for one code region (rows `row0 + layer` of the buffer: 32.. = row phases, 48.. = LayerNorm)
+template <bool TM>
+__device__ __forceinline__ void tstamp2(int row0, int i) {
+    if (TM && s_tim && (int) threadIdx.x == s_tim_tid && blockIdx.x == 0 && s_tim_layer < 16) {
+        unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        s_tim[(row0 + s_tim_layer) * 32 + i] = t;
+    }
+}
+
 // Fetch a published vector into shared memory.  Every thread takes entries tid, tid + 512, ... (n <= MAXJ * 512): all loads
 // go out together, stragglers are re-polled.  Deliberately NOT inlined: the kernel lives or dies by its instruction-cache
 // footprint (a 100 KB body re-fetched from L2 every layer cost 5-10x), so shared pieces are real calls.
@@ -181,7 +194,7 @@ __device__ __forceinline__ void consume_to_smem_inl(const tagged_t * g, int n, u
     if (threadIdx.x == 0) adapt_update(xt);
 }
 // one private (not replicated) vector of any length, one word per load: the score row of a head (a few consumer CTAs per head)
-__device__ __noinline__ void consume_row_to_smem(const tagged_t * g, int n, uint32_t tag, float * dst) {
+__device__ __forceinline__ void consume_row_to_smem(const tagged_t * g, int n, uint32_t tag, float * dst) {      // (inline: a call here would force the caller's prefetched V registers onto the stack)
     tagged_t w[2];
     const unsigned first_ns = s_adapt[XT_SC];
     if (first_ns) __nanosleep(first_ns);
@@ -230,6 +243,8 @@ template <bool ROUND16, bool TM, bool NATURAL = false>
 __device__ __noinline__ void block_layernorm(const float * xs, int E, double inv_E, const float * __restrict__ g, const float * __restrict__ b, float * act,
                                              double * red, unsigned * fallback_counter, int sb) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tb = sb == 1 ? 0 : 16;
+    tstamp2<TM>(48, tb + 0);
     double * sA = red, * sB = red + kWarps + kWarps / 2;
     float * fA = reinterpret_cast<float *>(red + kWarps);
     const int i0 = tid, i1 = tid + kThreads;
@@ -245,20 +260,23 @@ __device__ __noinline__ void block_layernorm(const float * xs, int E, double inv
     float a = fabsf(x0) + fabsf(x1);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); a += __shfl_xor_sync(0xffffffffu, a, o); }
+    tstamp2<TM>(48, tb + 1);
     if (lane == 0) { sA[warp] = s; fA[warp] = a; }
     __syncthreads();
+    tstamp2<TM>(48, tb + 2);
     float mean;
     {
-        // pairwise (depth 4) instead of 16 dependent adds: the double adds were the hottest instructions of this function
-        // (profiles/r02_decode.md); any order is covered by the bracket below, and every thread uses the same one
-        double qd[kWarps]; float qf[kWarps];
+        // the 16 warp partials are combined by a 4-level xor butterfly inside every warp (lane l starts from partial l & 15): every lane of
+        // every warp ends with the same bits (each level adds the same two values on both sides, addition is commutative), any order is
+        // covered by the bracket below.  The earlier form — every thread loads all 16 partials and adds them itself — cost 0.35 us per
+        // statistic (32 LDS + 30 adds per thread, FP64 issue-bound; profiles/r02_decode_fine_stamps.txt).
+        double qd[1]; float qf[1];
+        qd[0] = sA[lane & (kWarps - 1)]; qf[0] = fA[lane & (kWarps - 1)];
 #pragma unroll
-        for (int w = 0; w < kWarps; w++) { qd[w] = sA[w]; qf[w] = fA[w]; }
-#pragma unroll
-        for (int st = kWarps / 2; st > 0; st >>= 1)
-#pragma unroll
-            for (int w = 0; w < st; w++) { qd[w] += qd[w + st]; qf[w] += qf[w + st]; }
+        for (int o = kWarps / 2; o > 0; o >>= 1) { qd[0] += __shfl_xor_sync(0xffffffffu, qd[0], o); qf[0] += __shfl_xor_sync(0xffffffffu, qf[0], o); }
         const double S = qd[0]; const float A = qf[0];
+        if (S == 1.25) tstamp2<TM>(48, tb + 15);               // (forces the tree to be complete before the next stamp)
+        tstamp2<TM>(48, tb + 3);
         const double c = S * inv_E;
         const double hw = (slack * (double) A * 1.001) * inv_E + fabs(c) * 0x1p-50;     // 1.001: the float abs-sum may be low by n*2^-24
         mean = __double2float_rn(c - hw);
@@ -275,17 +293,17 @@ __device__ __noinline__ void block_layernorm(const float * xs, int E, double inv
     double s2 = (h0 ? (double) __fmul_rn(v0, v0) : 0.0) + (h1 ? (double) __fmul_rn(v1, v1) : 0.0);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    if (s2 == 1.25) tstamp2<TM>(48, tb + 15);
+    tstamp2<TM>(48, tb + 5);
     if (lane == 0) sB[warp] = s2;
     __syncthreads();
+    tstamp2<TM>(48, tb + 6);
     float scale;
     {
-        double qd[kWarps];
+        double qd[1];
+        qd[0] = sB[lane & (kWarps - 1)];
 #pragma unroll
-        for (int w = 0; w < kWarps; w++) qd[w] = sB[w];
-#pragma unroll
-        for (int st = kWarps / 2; st > 0; st >>= 1)
-#pragma unroll
-            for (int w = 0; w < st; w++) qd[w] += qd[w + st];
+        for (int o = kWarps / 2; o > 0; o >>= 1) qd[0] += __shfl_xor_sync(0xffffffffu, qd[0], o);
         const double S2 = qd[0];
         const double c = S2 * inv_E;
         const double hw = (slack * S2) * inv_E + c * 0x1p-50;
@@ -298,9 +316,13 @@ __device__ __noinline__ void block_layernorm(const float * xs, int E, double inv
         }
         scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(variance, 1e-5f)));
     }
+    if (scale == 1.25f) tstamp2<TM>(48, tb + 15);
+    tstamp2<TM>(48, tb + 7);
     if (h0) { float y = __fmul_rn(__fmul_rn(v0, scale), g0); if (b) y = __fadd_rn(y, b0); act[NATURAL ? i0 : act_index(i0)] = ROUND16 ? round_f16(y) : y; }
     if (h1) { float y = __fmul_rn(__fmul_rn(v1, scale), g1); if (b) y = __fadd_rn(y, b1); act[NATURAL ? i1 : act_index(i1)] = ROUND16 ? round_f16(y) : y; }
+    tstamp2<TM>(48, tb + 8);
     __syncthreads();
+    tstamp2<TM>(48, tb + 9);
 }
 
 // Per-CTA row ranges of every phase, built once per launch in shared memory (the divisions and table look-ups they replace
@@ -523,11 +545,28 @@ __device__ __forceinline__ void stage_rows(int phase) {
     }
 }
 
+// bytes of this warp's half of the staging slot that `phase` occupies (what stage_rows copies there)
+__device__ __forceinline__ uint32_t staged_bytes_of(int phase, int warp) {
+    const PhaseSched p = sched_tab()[phase];
+    int a, b; warp_rows(p, warp, a, b);
+    const uint32_t bytes = (uint32_t)((b - a) * p.row_bytes);
+    if (p.ws) {
+        const uint32_t sbytes = (uint32_t)((b - a) * (p.K >> 5) * 2);
+        return q4_staged(bytes, sbytes, p.ws + (size_t) a * (p.K >> 5) * 2) ? bytes + sbytes : 0u;
+    }
+    return bytes <= (uint32_t) kHalfSlotBytes ? bytes : 0u;
+}
+__device__ __forceinline__ void cp_async_f32(uint32_t dst, const float * src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // This warp's rows of `phase`: lane-order dot against the shared activation operand; outputs are published with epoch
 // `otag` (or stored, for the logits).  Then the rows of the phase after next start streaming in.  No block-wide synchronisation.
 template <typename WT, bool TM>
 __device__ __noinline__ void run_phase(int phase, int ep, int layer, uint32_t otag, int sb) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tb = sb == 3 ? 0 : sb == 18 ? 8 : sb == 24 ? 16 : 24;
+    tstamp2<TM>(32, tb + 0);
     const PhaseSched p = sched_tab()[phase];
     const float * act = reinterpret_cast<const float *>(dsm + SmemLayout::act);
     const float * xs = reinterpret_cast<const float *>(dsm + SmemLayout::x);
@@ -584,26 +623,33 @@ __device__ __noinline__ void run_phase(int phase, int ep, int layer, uint32_t ot
         return;
     } else {
     int j = 0;
+    tstamp2<TM>(32, tb + 1);
     for (int r = a; r < b;) {
         const unsigned char * row = staged ? slot + (size_t) j * p.row_bytes : p.w + (size_t) r * p.row_bytes;
         if (r + 1 < b) {                                      // two adjacent rows at once: independent chains, and both table look-ups in flight together
             float v[2];
             if (staged) row_dot<WT, true, 2>(row, p.row_bytes, act, p.K, lane, v);
             else { float u[1]; row_dot<WT, false, 1>(row, p.row_bytes, act, p.K, lane, u); v[0] = u[0]; row_dot<WT, false, 1>(row + p.row_bytes, p.row_bytes, act, p.K, lane, u); v[1] = u[0]; }
+            if (v[0] == 1.2345e30f) tstamp2<TM>(32, tb + 7);
+            tstamp2<TM>(32, tb + 2);
             if (lane < kReplicas) {
                 if (ep == EP_GELU) {
                     const __half t0 = s_bc.gelu_tab[__half_as_ushort(__float2half_rn(v[0]))], t1 = s_bc.gelu_tab[__half_as_ushort(__float2half_rn(v[1]))];
                     publish_all(s_bc.gff, 4 * E, r, gelu_sel(v[0], t0), otag, lane); publish_all(s_bc.gff, 4 * E, r + 1, gelu_sel(v[1], t1), otag, lane);
                 } else { emit(r, v[0]); emit(r + 1, v[1]); }
             }
+            tstamp2<TM>(32, tb + 3);
             r += 2; j += 2;
         } else {
             float v[1];
             if (staged) row_dot<WT, true, 1>(row, p.row_bytes, act, p.K, lane, v); else row_dot<WT, false, 1>(row, p.row_bytes, act, p.K, lane, v);
+            if (v[0] == 1.2345e30f) tstamp2<TM>(32, tb + 7);
+            tstamp2<TM>(32, tb + 4);
             if (lane < kReplicas) {
                 if (ep == EP_GELU) publish_all(s_bc.gff, 4 * E, r, gelu_sel(v[0], s_bc.gelu_tab[__half_as_ushort(__float2half_rn(v[0]))]), otag, lane);
                 else emit(r, v[0]);
             }
+            tstamp2<TM>(32, tb + 5);
             r += 1; j += 1;
         }
     }
@@ -615,6 +661,223 @@ __device__ __noinline__ void run_phase(int phase, int ep, int layer, uint32_t ot
 }
 
 }  // namespace
+
+// P2 of a layer (scores) for the CTAs that take score tasks, and P3 (soft_max + P.V) for the CTAs that own a soft_max tile, are real
+// calls with their own register allocation.  Inlined into the 128-register kernel body the "prefetched" V values were spilled right after
+// each load (LDG -> STL in the SASS: every load waited for its data, 0.3 us each, 2.2-4.6 us per layer on the soft_max CTAs —
+// profiles/r02_decode_fine_stamps.txt); here they stay in registers.
+template <int DSTEPS, bool TM>
+__device__ __noinline__ void p2_scores(int il, int H, int n_kv, float scale, uint32_t t_qkv, uint32_t t_sc, unsigned score_cta0) {
+    constexpr int D = DSTEPS * 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int E = s_bc.E, ctx = s_bc.ctx, n_past = s_bc.n_past;
+    float * qs = reinterpret_cast<float *>(dsm + SmemLayout::q);
+    struct { float * mem_k; } A{s_bc.mem_k};
+    const float * Kc = A.mem_k + (size_t) il * ctx * E;
+    const int total = H * n_kv, gw = (int)(blockIdx.x - score_cta0) * kWarps + warp, nw = (int)(gridDim.x - score_cta0) * kWarps;
+    // Task i of this warp is t = gw + i * nw = (h, k).  (h, k) advance incrementally (one division for the stride instead of two per
+    // task; a float-reciprocal divmod per task was measured at +216 bytes of spills and +19 % per token), and the eight dot products
+    // are reduced TOGETHER by a transposed butterfly: stage xor 16 swaps half of the eight partials, xor 8 a quarter, xor 4 one, then
+    // xor 1 / xor 2 on the single survivor — per task exactly the additions of lane_tree_reduce (each add sees the same two values,
+    // addition is commutative), 11 shuffles instead of 40, and eight lanes publish the eight scores at once.
+    const int sq = nw / n_kv, sr = nw - sq * n_kv;
+    const int h0 = gw / n_kv, k0 = gw - h0 * n_kv;
+    float kf[kMaxTasks][DSTEPS];
+    {
+        int h = h0, k = k0;
+#pragma unroll
+        for (int i = 0; i < kMaxTasks; i++) {
+            if (h < H && k < n_past) {
+#pragma unroll
+                for (int c = 0; c < DSTEPS; c++) kf[i][c] = __ldcg(Kc + (size_t) k * E + h * D + c * 32 + lane);
+            }
+            k += sr; h += sq; if (k >= n_kv) { k -= n_kv; h++; }
+        }
+    }
+    tstamp<TM>(6);
+    consume_to_smem<2>(s_bc.gq, E, t_qkv, qs, SINK_PLAIN, XT_Q);
+    tstamp<TM>(7);
+    float r[kMaxTasks];
+    {
+        int h = h0, k = k0;
+#pragma unroll
+        for (int i = 0; i < kMaxTasks; i++) {
+            float acc = 0.0f;
+            if (h < H) {
+#pragma unroll
+                for (int c = 0; c < DSTEPS; c++) {
+                    const float kv = (k < n_past) ? kf[i][c] : consume1(s_bc.gk + h * D + c * 32 + lane, t_qkv);   // the new position's key comes through the exchange
+                    acc = __fmaf_rn(kv, qs[h * D + c * 32 + lane], acc);
+                }
+            }
+            r[i] = acc;
+            k += sr; h += sq; if (k >= n_kv) { k -= n_kv; h++; }
+        }
+    }
+    static_assert(kMaxTasks == 8, "the transposed butterfly below is written for eight tasks");
+    {
+        const bool u16 = (lane & 16) != 0, u8 = (lane & 8) != 0, u4 = (lane & 4) != 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) { const float keep = u16 ? r[i + 4] : r[i], send = u16 ? r[i] : r[i + 4]; r[i] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, 16)); }
+#pragma unroll
+        for (int i = 0; i < 2; i++) { const float keep = u8 ? r[i + 2] : r[i], send = u8 ? r[i] : r[i + 2]; r[i] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, 8)); }
+        { const float keep = u4 ? r[1] : r[0], send = u4 ? r[0] : r[1]; r[0] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, 4)); }
+        r[0] = __fadd_rn(r[0], __shfl_xor_sync(0xffffffffu, r[0], 1));
+        r[0] = __fadd_rn(r[0], __shfl_xor_sync(0xffffffffu, r[0], 2));
+        const int mine = (u16 ? 4 : 0) + (u8 ? 2 : 0) + (u4 ? 1 : 0);          // the task whose complete sum this lane holds
+        const int t = gw + mine * nw;
+        if ((lane & 3) == 0 && t < total) {
+            const int h = t / n_kv, k = t - h * n_kv;
+            publish(s_bc.gscores + (size_t) h * ctx + k, __fmul_rn(r[0], scale), t_sc);
+        }
+    }
+#pragma unroll 1
+    for (int t = gw + kMaxTasks * nw; t < total; t += nw) {   // (not reached for the supported shapes; keeps the kernel total)
+        const int h = t / n_kv, k = t - h * n_kv;
+        float acc = 0.0f;
+#pragma unroll
+        for (int c = 0; c < DSTEPS; c++) {
+            const float kv = (k < n_past) ? __ldcg(Kc + (size_t) k * E + h * D + c * 32 + lane) : consume1(s_bc.gk + h * D + c * 32 + lane, t_qkv);
+            acc = __fmaf_rn(kv, qs[h * D + c * 32 + lane], acc);
+        }
+        const float r = lane_tree_reduce(acc);
+        if (lane == 0) publish(s_bc.gscores + (size_t) h * ctx + k, __fmul_rn(r, scale), t_sc);
+    }
+}
+
+template <int DSTEPS, bool TM>
+__device__ __noinline__ void p3_attention(int il, int n_kv, int np, int pv_h, int pv_c, uint32_t t_qkv, uint32_t t_sc, uint32_t t_att, unsigned * ln_fallbacks) {
+    constexpr int D = DSTEPS * 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int E = s_bc.E, ctx = s_bc.ctx, n_past = s_bc.n_past;
+    float * act = reinterpret_cast<float *>(dsm + SmemLayout::act);
+    float * qs = reinterpret_cast<float *>(dsm + SmemLayout::q);
+    float * part = reinterpret_cast<float *>(dsm + SmemLayout::part);
+    double * red = reinterpret_cast<double *>(dsm + SmemLayout::red);
+    float * bc = reinterpret_cast<float *>(red + kWarps + kWarps / 2 + kWarps);
+    struct { float * mem_v; unsigned * ln_fallbacks; } A{s_bc.mem_v, ln_fallbacks};
+    // This thread's chain of V values of older positions (thread (v, dd): virtual lane v of output column dd, chain steps k = v + 32 c)
+    // is copied ASYNCHRONOUSLY (cp.async, 4 bytes per step) into the unused tail of this warp's own staging half — half 1 holds the
+    // warp's c_proj rows right now, at most a third of it — so the copies drain while the scores are computed elsewhere and cost
+    // neither registers nor waiting.  (Held in registers, the 33 values were spilled right after each load — LDG -> STL in the SASS,
+    // every load waiting for its data: 2.2-4.6 us per layer on exactly the CTAs that are the critical path; profiles/r02_decode_fine_stamps.txt.)
+    // When the tail is too small (f32 weights and a long context) the P.V loop loads from global memory itself.
+    const int v = tid >> 4, dd = tid & 15, h = pv_h;
+    const int col0 = pv_h * D + pv_c * 16;
+    const int nstep = np >> 5, r = n_kv - np;
+    const float * Vc = A.mem_v + (size_t) il * ctx * E + col0 + dd;
+    const uint32_t voff = (staged_bytes_of(4 * il + 1, warp) + 127u) & ~127u;
+    const bool vs_ok = voff + (uint32_t)(nstep + (r > 0 ? 1 : 0)) * 128u <= (uint32_t) kHalfSlotBytes;
+    const float * vs = reinterpret_cast<const float *>(dsm + SmemLayout::wslot + (size_t) warp * kWarpSlotBytes + kHalfSlotBytes + voff) + lane;
+    if (vs_ok) {
+        const uint32_t dst = smem_u32(vs);
+#pragma unroll 4
+        for (int c = 0; c < nstep; c++) { const int k = v + 32 * c; if (k < n_past) cp_async_f32(dst + c * 128, Vc + (size_t) k * E); }
+        if (np + v < n_past) cp_async_f32(dst + nstep * 128, Vc + (size_t)(np + v) * E);          // one element of the leftover rows k = np + v
+        cp_async_commit();
+    }
+    const float v_new = consume1(s_bc.gv + col0 + dd, t_qkv);     // value row of the new position
+    __syncthreads();                                         // slower warps may still be reading q (in `qs`) for their score tasks
+    tstamp<TM>(9);
+    float * p = qs;                                          // scores row -> exp(score - max); the 1/sum factor is applied on use
+    consume_row_to_smem(s_bc.gscores + (size_t) h * ctx, n_kv, t_sc, p);
+    tstamp<TM>(10);
+    float mx = __int_as_float(0xff800000);
+#pragma unroll 1
+    for (int i = tid; i < n_kv; i += kThreads) mx = fmaxf(mx, p[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float * fred = reinterpret_cast<float *>(red);
+    if (lane == 0) fred[warp] = mx;
+    __syncthreads();
+    mx = fred[0];
+#pragma unroll
+    for (int w = 1; w < kWarps; w++) mx = fmaxf(mx, fred[w]);
+    tstamp<TM>(11);
+    // exp: whole chunks of 8 through the vector polynomial (ggml.c:2706-2746), the n_kv % 8 tail through libm expf
+    // (ggml.c:2880-2884) — one element per thread, every element independent of the others
+    const int nchunks = n_kv >> 3, n8 = nchunks << 3;
+#pragma unroll 1
+    for (int i = tid; i < n_kv; i += kThreads) {
+        const float d = __fsub_rn(p[i], mx);
+        p[i] = i < n8 ? ggml_v_expf_dev(d) : glibc_expf_dev(d);
+    }
+    __syncthreads();
+    tstamp<TM>(12);
+    // sum = sequential double accumulation of the chunk sums (in-chunk float tree of the 8-wide vector code), then the
+    // tail (ggml.c:2845-2888).  All terms are positive, so a tree sum S brackets the sequential one within
+    // +-2n*2^-53*S; if 1/sum rounds to the same float at both ends of the bracket the order cannot matter, else replay
+    // sequentially.  Done by warp 0, broadcast through bc[2].
+    if (warp == 0) {
+        auto chunk_sum = [&](int c) {
+            const float4 lo4 = *reinterpret_cast<const float4 *>(p + c * 8), hi4 = *reinterpret_cast<const float4 *>(p + c * 8 + 4);
+            const float t0 = __fadd_rn(hi4.x, lo4.x), t1 = __fadd_rn(hi4.y, lo4.y), t2 = __fadd_rn(hi4.z, lo4.z), t3 = __fadd_rn(hi4.w, lo4.w);
+            return __fadd_rn(__fadd_rn(t0, t2), __fadd_rn(t1, t3));
+        };
+        double s = 0.0;
+#pragma unroll 1
+        for (int c = lane; c < nchunks; c += 32) s += (double) chunk_sum(c);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) {
+            const double dl = 2.0 * (double)(nchunks + 8) * 0x1p-53 * s * (1.0 + 1e-6);
+            double lo = s - dl, hi = s + dl;
+#pragma unroll 1
+            for (int i = n8; i < n_kv; i++) { const double tl = (double) p[i]; lo = __dadd_rn(lo, tl); hi = __dadd_rn(hi, tl); }
+            // 1/sum without a double division: y ~ 1/mid to 2^-50, the bracket [lo, hi] and that error go into the half-width
+            const double mid = 0.5 * (lo + hi), y = approx_rcp(mid);
+            const double rw = (hi - lo) * y * 0.5 + 0x1p-48;                       // relative half-width
+            float f_lo = __double2float_rn(y * (1.0 - rw));
+            const float f_hi = __double2float_rn(y * (1.0 + rw));
+            if (f_lo != f_hi) {
+                double q2 = 0.0;
+#pragma unroll 1
+                for (int c = 0; c < nchunks; c++) q2 = __dadd_rn(q2, (double) chunk_sum(c));
+#pragma unroll 1
+                for (int i = n8; i < n_kv; i++) q2 = __dadd_rn(q2, (double) p[i]);
+                f_lo = __double2float_rn(__ddiv_rn(1.0, q2));
+                if (A.ln_fallbacks) atomicAdd(A.ln_fallbacks + 1, 1u);
+            }
+            bc[2] = f_lo;
+        }
+    }
+    __syncthreads();
+    tstamp<TM>(13);
+    const float sc_f = bc[2];                                // probabilities = p[k] * sc_f (ggml_vec_scale_f32), formed where they are used
+    if (vs_ok) cp_async_wait_all();                          // (each thread reads back only what it copied itself)
+    float acc = 0.0f;
+#pragma unroll 4
+    for (int c = 0; c < nstep; c++) {
+        const int k = v + 32 * c;
+        const float vv = k < n_past ? (vs_ok ? vs[c * 32] : __ldcg(Vc + (size_t) k * E)) : v_new;
+        acc = __fmaf_rn(vv, __fmul_rn(p[k], sc_f), acc);
+    }
+    part[v * 16 + dd] = acc;
+    // leftovers k = np .. n_kv-1 as the pinned build compiles them (oracle orc_vec_dot_f32): 8-groups and a 4-group of
+    // rounded multiply + add, then <= 3 fused multiply-adds.  Thread (v, dd) prepares term v: the rounded product where
+    // the chain adds one, the bare value where it fuses.
+    const int r8 = r & ~7, n4 = r8 + ((r - r8) >= 4 ? 4 : 0);
+    if (v < r) {
+        const float vv = (np + v < n_past) ? (vs_ok ? vs[nstep * 32] : __ldcg(Vc + (size_t)(np + v) * E)) : v_new;
+        act[v * 16 + dd] = v < n4 ? __fmul_rn(vv, __fmul_rn(p[np + v], sc_f)) : vv;
+    }
+    __syncthreads();
+    tstamp<TM>(15);
+    if (tid < 16) {
+        float a32[32];
+#pragma unroll
+        for (int l = 0; l < 32; l++) a32[l] = part[l * 16 + tid];
+        float sum = lane_tree_reduce_local(a32);
+#pragma unroll 4
+        for (int j = 0; j < r; j++) {
+            const float tj = act[j * 16 + tid];
+            if (j < n4) sum = __fadd_rn(sum, tj); else sum = __fmaf_rn(tj, __fmul_rn(p[np + j], sc_f), sum);
+        }
+#pragma unroll
+        for (int rep = 0; rep < kReplicas; rep++) publish(s_bc.gatt + (size_t) rep * E + col0 + tid, sum, t_att);
+    }
+    __syncthreads();                                     // `act` / `qs` are reused by the next phase
+}
 
 template <typename WT, int DSTEPS, bool TM>
 __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs A) {
@@ -688,8 +951,20 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
     const unsigned score_cta0 = (gridDim.x >= (unsigned)(H * parts + 64)) ? (unsigned)(H * parts) : 0u;      // first CTA that takes score tasks
     const bool score_cta = blockIdx.x >= score_cta0;
 
+    // K / V rows of older positions, one layer ahead into L2: thread 32 of every CTA prefetches this CTA's slice of the next layer's rows
+    auto kv_prefetch = [&](int layer) {
+        if (!A.kv_prefetch || tid != 32 || layer >= L || n_past == 0) return;
+        const size_t total = (size_t) n_past * E * sizeof(float);                        // multiple of 128 bytes
+        const size_t chunk = ((total + gridDim.x - 1) / gridDim.x + 127) & ~(size_t) 127, off = (size_t) blockIdx.x * chunk;
+        if (off >= total) return;
+        const uint32_t bytes = (uint32_t) min(chunk, total - off);
+        l2_prefetch_bulk(reinterpret_cast<const unsigned char *>(A.mem_k + (size_t) layer * ctx * E) + off, bytes);
+        l2_prefetch_bulk(reinterpret_cast<const unsigned char *>(A.mem_v + (size_t) layer * ctx * E) + off, bytes);
+    };
+    kv_prefetch(0);
 #pragma unroll 1
     for (int il = 0; il < L; il++) {
+        kv_prefetch(il + 1);
         const DecodeLayerVec lv = A.layer_vecs[il];
         const uint32_t t_qkv = tag + 1, t_sc = tag + 2, t_att = tag + 3, t_x1 = tag + 4, t_ff = tag + 5, t_x2 = tag + 6;
         tag += 6;
@@ -701,181 +976,12 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
         tstamp<TM>(2);
         run_phase<WT, TM>(4 * il + 0, EP_QKV, il, t_qkv, 3);
 
-        // ---- P3 operands first: this thread's chain of V values of older positions (thread (v, dd): virtual lane v of output
-        // column dd) goes out before anything is waited for, so the loads drain while P2 runs ----
-        const int pv_v = tid >> 4, pv_dd = tid & 15;
-        const int col0 = pv_h * D + pv_c * 16;
-        float vlo[16], vhi[16]; float vl = 0.0f;              // chain steps 0..15 (positions < 512) now; 16..31 at the start of P3 (registers)
-        if (pv_cta) {
-            const float * Vc = A.mem_v + (size_t) il * ctx * E + col0;
-#pragma unroll
-            for (int c = 0; c < 16; c++) { const int k = pv_v + 32 * c; if (k < np && k < n_past) vlo[c] = __ldcg(Vc + (size_t) k * E + pv_dd); }
-            if (np + pv_v < n_past) vl = __ldcg(Vc + (size_t)(np + pv_v) * E + pv_dd);          // one element of the leftover rows k = np + v
-        }
-
-        // ---- P2: scores.  K rows of older positions are fetched before q arrives.  The CTAs that own a soft_max tile (P3) take no
-        // score tasks when enough other CTAs exist: they are the critical path of the layer (they still have the whole of P3 to do
-        // once the scores exist), and the V prefetch above already keeps their load queues busy. ----
+        // ---- P2 (scores) and P3 (soft_max + P.V), out of line (see p2_scores).  The CTAs that own a soft_max tile take no score tasks when
+        // enough other CTAs exist: they are the critical path of the layer (they still have the whole of P3 to do once the scores exist) ----
         if constexpr (kQ4) __syncthreads();                    // the q8 operand aliases `qs`: every warp must be done with its QKV rows before q lands there
-        if (score_cta) {
-            const float * Kc = A.mem_k + (size_t) il * ctx * E;
-            const int total = H * n_kv, gw = (int)(blockIdx.x - score_cta0) * kWarps + warp, nw = (int)(gridDim.x - score_cta0) * kWarps;
-            // (t / n_kv stays an integer division: a float-reciprocal version cost 216 bytes of extra spills in this register-capped kernel
-            // and +19 % per token — measured, round 2)
-            float kf[kMaxTasks][DSTEPS];
-#pragma unroll
-            for (int i = 0; i < kMaxTasks; i++) {
-                const int t = gw + i * nw;
-                if (t < total) {
-                    const int h = t / n_kv, k = t - h * n_kv;
-                    if (k < n_past) {
-#pragma unroll
-                        for (int c = 0; c < DSTEPS; c++) kf[i][c] = __ldcg(Kc + (size_t) k * E + h * D + c * 32 + lane);
-                    }
-                }
-            }
-            tstamp<TM>(6);
-            consume_to_smem<2>(s_bc.gq, E, t_qkv, qs, SINK_PLAIN, XT_Q);
-            tstamp<TM>(7);
-#pragma unroll
-            for (int i = 0; i < kMaxTasks; i++) {
-                const int t = gw + i * nw;
-                if (t < total) {
-                    const int h = t / n_kv, k = t - h * n_kv;
-                    float acc = 0.0f;
-#pragma unroll
-                    for (int c = 0; c < DSTEPS; c++) {
-                        const float kv = (k < n_past) ? kf[i][c] : consume1(s_bc.gk + h * D + c * 32 + lane, t_qkv);   // the new position's key comes through the exchange
-                        acc = __fmaf_rn(kv, qs[h * D + c * 32 + lane], acc);
-                    }
-                    const float r = lane_tree_reduce(acc);
-                    if (lane == 0) publish(s_bc.gscores + (size_t) h * ctx + k, __fmul_rn(r, scale), t_sc);
-                }
-            }
-#pragma unroll 1
-            for (int t = gw + kMaxTasks * nw; t < total; t += nw) {   // (not reached for the supported shapes; keeps the kernel total)
-                const int h = t / n_kv, k = t - h * n_kv;
-                float acc = 0.0f;
-#pragma unroll
-                for (int c = 0; c < DSTEPS; c++) {
-                    const float kv = (k < n_past) ? __ldcg(Kc + (size_t) k * E + h * D + c * 32 + lane) : consume1(s_bc.gk + h * D + c * 32 + lane, t_qkv);
-                    acc = __fmaf_rn(kv, qs[h * D + c * 32 + lane], acc);
-                }
-                const float r = lane_tree_reduce(acc);
-                if (lane == 0) publish(s_bc.gscores + (size_t) h * ctx + k, __fmul_rn(r, scale), t_sc);
-            }
-        }
+        if (score_cta) p2_scores<DSTEPS, TM>(il, H, n_kv, scale, t_qkv, t_sc, score_cta0);
         tstamp<TM>(8);
-
-        // ---- P3: soft_max + P.V, one CTA per (head, 16 columns of the head) ----
-        if (pv_cta) {
-            const int h = pv_h, v = pv_v, dd = pv_dd;
-            {
-                const float * Vc = A.mem_v + (size_t) il * ctx * E + col0;
-#pragma unroll
-                for (int c = 0; c < 16; c++) { const int k = v + 32 * (c + 16); if (k < np && k < n_past) vhi[c] = __ldcg(Vc + (size_t) k * E + dd); }
-            }
-            const float v_new = consume1(s_bc.gv + col0 + dd, t_qkv);     // value row of the new position
-            __syncthreads();                                         // slower warps may still be reading q (in `qs`) for their score tasks
-            tstamp<TM>(9);
-            float * p = qs;                                          // scores row -> exp(score - max); the 1/sum factor is applied on use
-            consume_row_to_smem(s_bc.gscores + (size_t) h * ctx, n_kv, t_sc, p);
-            tstamp<TM>(10);
-            float mx = __int_as_float(0xff800000);
-#pragma unroll 1
-            for (int i = tid; i < n_kv; i += kThreads) mx = fmaxf(mx, p[i]);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-            float * fred = reinterpret_cast<float *>(red);
-            if (lane == 0) fred[warp] = mx;
-            __syncthreads();
-            mx = fred[0];
-#pragma unroll
-            for (int w = 1; w < kWarps; w++) mx = fmaxf(mx, fred[w]);
-            tstamp<TM>(11);
-            // exp: whole chunks of 8 through the vector polynomial (ggml.c:2706-2746), the n_kv % 8 tail through libm expf
-            // (ggml.c:2880-2884) — one element per thread, every element independent of the others
-            const int nchunks = n_kv >> 3, n8 = nchunks << 3;
-#pragma unroll 1
-            for (int i = tid; i < n_kv; i += kThreads) {
-                const float d = __fsub_rn(p[i], mx);
-                p[i] = i < n8 ? ggml_v_expf_dev(d) : glibc_expf_dev(d);
-            }
-            __syncthreads();
-            tstamp<TM>(12);
-            // sum = sequential double accumulation of the chunk sums (in-chunk float tree of the 8-wide vector code), then the
-            // tail (ggml.c:2845-2888).  All terms are positive, so a tree sum S brackets the sequential one within
-            // +-2n*2^-53*S; if 1/sum rounds to the same float at both ends of the bracket the order cannot matter, else replay
-            // sequentially.  Done by warp 0, broadcast through bc[2].
-            if (warp == 0) {
-                auto chunk_sum = [&](int c) {
-                    const float4 lo4 = *reinterpret_cast<const float4 *>(p + c * 8), hi4 = *reinterpret_cast<const float4 *>(p + c * 8 + 4);
-                    const float t0 = __fadd_rn(hi4.x, lo4.x), t1 = __fadd_rn(hi4.y, lo4.y), t2 = __fadd_rn(hi4.z, lo4.z), t3 = __fadd_rn(hi4.w, lo4.w);
-                    return __fadd_rn(__fadd_rn(t0, t2), __fadd_rn(t1, t3));
-                };
-                double s = 0.0;
-#pragma unroll 1
-                for (int c = lane; c < nchunks; c += 32) s += (double) chunk_sum(c);
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                if (lane == 0) {
-                    const double dl = 2.0 * (double)(nchunks + 8) * 0x1p-53 * s * (1.0 + 1e-6);
-                    double lo = s - dl, hi = s + dl;
-#pragma unroll 1
-                    for (int i = n8; i < n_kv; i++) { const double tl = (double) p[i]; lo = __dadd_rn(lo, tl); hi = __dadd_rn(hi, tl); }
-                    // 1/sum without a double division: y ~ 1/mid to 2^-50, the bracket [lo, hi] and that error go into the half-width
-                    const double mid = 0.5 * (lo + hi), y = approx_rcp(mid);
-                    const double rw = (hi - lo) * y * 0.5 + 0x1p-48;                       // relative half-width
-                    float f_lo = __double2float_rn(y * (1.0 - rw));
-                    const float f_hi = __double2float_rn(y * (1.0 + rw));
-                    if (f_lo != f_hi) {
-                        double q2 = 0.0;
-#pragma unroll 1
-                        for (int c = 0; c < nchunks; c++) q2 = __dadd_rn(q2, (double) chunk_sum(c));
-#pragma unroll 1
-                        for (int i = n8; i < n_kv; i++) q2 = __dadd_rn(q2, (double) p[i]);
-                        f_lo = __double2float_rn(__ddiv_rn(1.0, q2));
-                        if (A.ln_fallbacks) atomicAdd(A.ln_fallbacks + 1, 1u);
-                    }
-                    bc[2] = f_lo;
-                }
-            }
-            __syncthreads();
-            tstamp<TM>(13);
-            const float sc_f = bc[2];                                // probabilities = p[k] * sc_f (ggml_vec_scale_f32), formed where they are used
-            float acc = 0.0f;
-#pragma unroll
-            for (int c = 0; c < 32; c++) {
-                const int k = v + 32 * c;
-                if (k < np) acc = __fmaf_rn(k < n_past ? (c < 16 ? vlo[c & 15] : vhi[c & 15]) : v_new, __fmul_rn(p[k], sc_f), acc);
-            }
-            part[v * 16 + dd] = acc;
-            // leftovers k = np .. n_kv-1 as the pinned build compiles them (oracle orc_vec_dot_f32): 8-groups and a 4-group of
-            // rounded multiply + add, then <= 3 fused multiply-adds.  Thread (v, dd) prepares term v: the rounded product where
-            // the chain adds one, the bare value where it fuses.
-            const int r = n_kv - np;
-            const int r8 = r & ~7, n4 = r8 + ((r - r8) >= 4 ? 4 : 0);
-            if (v < r) {
-                const float vv = (np + v < n_past) ? vl : v_new;
-                act[v * 16 + dd] = v < n4 ? __fmul_rn(vv, __fmul_rn(p[np + v], sc_f)) : vv;
-            }
-            __syncthreads();
-            tstamp<TM>(15);
-            if (tid < 16) {
-                float a32[32];
-#pragma unroll
-                for (int l = 0; l < 32; l++) a32[l] = part[l * 16 + tid];
-                float sum = lane_tree_reduce_local(a32);
-#pragma unroll 4
-                for (int j = 0; j < r; j++) {
-                    const float tj = act[j * 16 + tid];
-                    if (j < n4) sum = __fadd_rn(sum, tj); else sum = __fmaf_rn(tj, __fmul_rn(p[np + j], sc_f), sum);
-                }
-#pragma unroll
-                for (int rep = 0; rep < kReplicas; rep++) publish(s_bc.gatt + (size_t) rep * E + col0 + tid, sum, t_att);
-            }
-            __syncthreads();                                     // `act` / `qs` are reused by the next phase
-        }
+        if (pv_cta) p3_attention<DSTEPS, TM>(il, n_kv, np, pv_h, pv_c, t_qkv, t_sc, t_att, A.ln_fallbacks);
         tstamp<TM>(16);
 
         // ---- P4: c_proj + residual ----

@@ -126,6 +126,7 @@ static void decode_step(bark_context * ctx, GPTModel & m, int token, const int32
         a.samp_n = fs->n; a.samp_temp = fs->temp; a.samp_u = fs->d_u; a.samp_tok = fs->d_tok; a.samp_tok_add = fs->tok_add; a.samp_feed = fs->d_feed;
         a.samp_eos = fs->d_eos; a.samp_flags = fs->d_flags; a.samp_force = fs->force; a.done_counter = ctx->d_done_counter;
     }
+    a.kv_prefetch = ctx->kv_prefetch ? 1 : 0;
     a.timing_tid = ctx->timing_tid; a.poll_ns = ctx->poll_ns; a.first_ns = ctx->first_ns; a.att_ns = ctx->att_ns;
     const double es = m.wtype == W_Q4_0 ? 18.0 / 32.0 : m.wtype == W_F16 ? 2.0 : 4.0;
     const double E = m.n_embd, L = m.n_layer;

@@ -86,6 +86,7 @@ struct DecodeArgs {
     int samp_n; float samp_temp; const double * samp_u; int32_t * samp_tok; int samp_tok_add; int32_t * samp_feed; float * samp_eos; int32_t * samp_flags; int samp_force;
     unsigned * done_counter;
     unsigned headstart[6];               // fixed head start (ns) before the first poll of each exchange: q, att (CTAs without a soft_max tile), x1, ff, x2, scores
+    int kv_prefetch;                     // 1: every CTA asks the TMA engine to pull its slice of the NEXT layer's K / V rows into L2 (cp.async.bulk.prefetch.L2) one layer ahead
     unsigned * adapt;                    // [n_cta][8] adaptive head starts of the exchanges, carried from token to token (null: fixed knobs)
     int timing_tid; unsigned poll_ns, first_ns, att_ns;   // debug: stamping thread; back-off between polls of the tagged words; delay before the first poll of the residual exchanges (ns)
 };

@@ -59,6 +59,14 @@ def measure(pkg, path, pasts, tid, poll, first=0):
                 print(f"   -> {c:2d} {NAMES[c]:<28s} median {np.median(d):6.2f} us   min {d.min():6.2f}   max {d.max():6.2f}")
             d = (lay[1:L + 1, 0] - lay[:L, used[-1]]) / 1e3
             print(f"   ->  0 {'x arrived (next layer)':<28s} median {np.median(d):6.2f} us   min {d.min():6.2f}   max {d.max():6.2f}")
+            # finer stamps (tstamp2): rows 32 + layer = the four row phases (8 slots each), rows 48 + layer = LN1 / LN2 (16 slots each)
+            for row0, groups, names in ((32, ((0, "QKV"), (8, "c_proj"), (16, "fc"), (24, "proj")), {0: "entry", 1: "sched loaded, loop start", 2: "pair row_dot done", 3: "pair emitted", 4: "single row_dot done", 5: "single emitted"}),
+                                        (48, ((0, "LN1"), (16, "LN2")), {0: "entry", 1: "warp sums done", 2: "barrier 1 passed", 3: "tree done", 5: "variance warp sums done", 6: "barrier 2 passed", 7: "scale known", 8: "act written", 9: "final barrier passed"})):
+                sub = t[row0:row0 + L]
+                for g0, gname in groups:
+                    idx = [i for i in sorted(names) if sub[1, g0 + i] != 0]
+                    if not idx: continue
+                    print(f"   [{gname}] stamps relative to entry (median over layers, us): " + "  ".join(f"{names[i]}={np.median((sub[1:L, g0 + i] - sub[1:L, g0 + idx[0]]) / 1e3):.2f}" for i in idx))
             cta = t[64:64 + 148]
             base = cta[:, 0].min()
             for c in used:
