@@ -41,6 +41,7 @@ namespace {
 
 constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
+static_assert(kWarps == 16, "the soft_max tile is 16 columns wide: one warp finishes one column");
 constexpr int kWarpSlotBytes = 12 * 1024;       // per-warp staging area: two halves, phases alternate (rows are fetched two phases ahead)
 constexpr int kHalfSlotBytes = kWarpSlotBytes / 2;
 constexpr int kReplicas = kDecodeReplicas;      // copies of every all-to-all exchange vector (gpt_kernels.h)
@@ -350,7 +351,7 @@ template <> struct Unpack<float> {
 // latency: ncu showed the unpack instructions behind it waiting on the long scoreboard); otherwise they stream from global
 // memory.  The NR chains are independent, so two rows cost barely more than one.
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
-    uint4 v; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    uint4 v; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));   // volatile: stays behind the (volatile) mbarrier wait
     return v;
 }
 template <typename WT, bool SH, int NR>
@@ -366,6 +367,7 @@ __device__ __forceinline__ void row_dot(const unsigned char * row, int row_bytes
     for (int n = 0; n < NR; n++) acc[n] = 0.0f;
     if constexpr (G == 8) {
         const int ng = nsteps >> 3, tail = nsteps & 7;
+#pragma unroll 3
         for (int g = 0; g < ng; g++) {
             const float4 a0 = *reinterpret_cast<const float4 *>(act + ((g * 2) * 32 + lane) * 4);
             const float4 a1 = *reinterpret_cast<const float4 *>(act + ((g * 2 + 1) * 32 + lane) * 4);
@@ -556,7 +558,7 @@ __device__ __forceinline__ uint32_t staged_bytes_of(int phase, int warp) {
     }
     return bytes <= (uint32_t) kHalfSlotBytes ? bytes : 0u;
 }
-__device__ __forceinline__ void cp_async_f32(uint32_t dst, const float * src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const float * src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory"); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
@@ -756,24 +758,29 @@ __device__ __noinline__ void p3_attention(int il, int n_kv, int np, int pv_h, in
     double * red = reinterpret_cast<double *>(dsm + SmemLayout::red);
     float * bc = reinterpret_cast<float *>(red + kWarps + kWarps / 2 + kWarps);
     struct { float * mem_v; unsigned * ln_fallbacks; } A{s_bc.mem_v, ln_fallbacks};
-    // This thread's chain of V values of older positions (thread (v, dd): virtual lane v of output column dd, chain steps k = v + 32 c)
-    // is copied ASYNCHRONOUSLY (cp.async, 4 bytes per step) into the unused tail of this warp's own staging half — half 1 holds the
-    // warp's c_proj rows right now, at most a third of it — so the copies drain while the scores are computed elsewhere and cost
-    // neither registers nor waiting.  (Held in registers, the 33 values were spilled right after each load — LDG -> STL in the SASS,
-    // every load waiting for its data: 2.2-4.6 us per layer on exactly the CTAs that are the critical path; profiles/r02_decode_fine_stamps.txt.)
+    // V of older positions.  Thread (v, dd) owns virtual lane v of output column dd: chain steps k = v + 32 c.  A warp holds two values of
+    // v and all 16 columns, i.e. per chain step two 64-byte pieces of V rows — and copies exactly those, ASYNCHRONOUSLY (cp.async, 16 bytes per
+    // lane: one instruction moves four chain steps of the warp), into the unused tail of its own staging half: half 1 holds the warp's
+    // c_proj rows right now, at most a third of it.  The copies drain while the scores are computed elsewhere and cost neither registers
+    // nor waiting.  (Held in registers, the 33 values were spilled right after each load — LDG -> STL in the SASS, every load waiting for
+    // its data: 2.2-4.6 us per layer on exactly the CTAs that are the critical path; profiles/r02_decode_fine_stamps.txt.)
     // When the tail is too small (f32 weights and a long context) the P.V loop loads from global memory itself.
     const int v = tid >> 4, dd = tid & 15, h = pv_h;
     const int col0 = pv_h * D + pv_c * 16;
     const int nstep = np >> 5, r = n_kv - np;
-    const float * Vc = A.mem_v + (size_t) il * ctx * E + col0 + dd;
+    const int nstep_all = nstep + (r > 0 ? 1 : 0);           // the leftover rows k = np + v are chain step `nstep` of the same layout
+    const float * Vt = A.mem_v + (size_t) il * ctx * E + col0;       // row k of the tile: Vt + k * E, 16 floats
     const uint32_t voff = (staged_bytes_of(4 * il + 1, warp) + 127u) & ~127u;
-    const bool vs_ok = voff + (uint32_t)(nstep + (r > 0 ? 1 : 0)) * 128u <= (uint32_t) kHalfSlotBytes;
-    const float * vs = reinterpret_cast<const float *>(dsm + SmemLayout::wslot + (size_t) warp * kWarpSlotBytes + kHalfSlotBytes + voff) + lane;
+    const bool vs_ok = voff + (uint32_t) nstep_all * 128u <= (uint32_t) kHalfSlotBytes;
+    const float * vs = reinterpret_cast<const float *>(dsm + SmemLayout::wslot + (size_t) warp * kWarpSlotBytes + kHalfSlotBytes + voff);   // [step][2 x 16] floats
     if (vs_ok) {
         const uint32_t dst = smem_u32(vs);
-#pragma unroll 4
-        for (int c = 0; c < nstep; c++) { const int k = v + 32 * c; if (k < n_past) cp_async_f32(dst + c * 128, Vc + (size_t) k * E); }
-        if (np + v < n_past) cp_async_f32(dst + nstep * 128, Vc + (size_t)(np + v) * E);          // one element of the leftover rows k = np + v
+        const int sub = lane >> 3, vl2 = (lane >> 2) & 1, g = lane & 3;        // lane: chain step within a group of four, which of the warp's two rows, 16-byte piece of the row
+#pragma unroll 2
+        for (int c0 = 0; c0 < nstep_all; c0 += 4) {
+            const int c = c0 + sub, k = 2 * warp + vl2 + 32 * c;
+            if (c < nstep_all && k < n_past) cp_async_16(dst + (uint32_t)(((c * 2 + vl2) * 16 + g * 4) * 4), Vt + (size_t) k * E + g * 4);
+        }
         cp_async_commit();
     }
     const float v_new = consume1(s_bc.gv + col0 + dd, t_qkv);     // value row of the new position
@@ -844,37 +851,44 @@ __device__ __noinline__ void p3_attention(int il, int n_kv, int np, int pv_h, in
     __syncthreads();
     tstamp<TM>(13);
     const float sc_f = bc[2];                                // probabilities = p[k] * sc_f (ggml_vec_scale_f32), formed where they are used
-    if (vs_ok) cp_async_wait_all();                          // (each thread reads back only what it copied itself)
     float acc = 0.0f;
-#pragma unroll 4
-    for (int c = 0; c < nstep; c++) {
-        const int k = v + 32 * c;
-        const float vv = k < n_past ? (vs_ok ? vs[c * 32] : __ldcg(Vc + (size_t) k * E)) : v_new;
-        acc = __fmaf_rn(vv, __fmul_rn(p[k], sc_f), acc);
+    if (vs_ok) {
+        cp_async_wait_all(); __syncwarp();                   // the warp reads back only what its own lanes copied
+#pragma unroll 8
+        for (int c = 0; c < nstep; c++) {
+            const int k = v + 32 * c;
+            const float vv = k < n_past ? vs[c * 32 + lane] : v_new;       // (a slot that was not copied holds stale bytes: read, not used)
+            acc = __fmaf_rn(vv, __fmul_rn(p[k], sc_f), acc);
+        }
+    } else {
+#pragma unroll 8
+        for (int c = 0; c < nstep; c++) {
+            const int k = v + 32 * c;
+            const float vv = k < n_past ? __ldcg(Vt + (size_t) k * E + dd) : v_new;
+            acc = __fmaf_rn(vv, __fmul_rn(p[k], sc_f), acc);
+        }
     }
-    part[v * 16 + dd] = acc;
+    part[v * 17 + dd] = acc;                                 // (row stride 17: conflict-free for this store and for the column reads below)
     // leftovers k = np .. n_kv-1 as the pinned build compiles them (oracle orc_vec_dot_f32): 8-groups and a 4-group of
     // rounded multiply + add, then <= 3 fused multiply-adds.  Thread (v, dd) prepares term v: the rounded product where
     // the chain adds one, the bare value where it fuses.
     const int r8 = r & ~7, n4 = r8 + ((r - r8) >= 4 ? 4 : 0);
     if (v < r) {
-        const float vv = (np + v < n_past) ? (vs_ok ? vs[nstep * 32] : __ldcg(Vc + (size_t)(np + v) * E)) : v_new;
+        const float vv = (np + v < n_past) ? (vs_ok ? vs[nstep * 32 + lane] : __ldcg(Vt + (size_t)(np + v) * E + dd)) : v_new;
         act[v * 16 + dd] = v < n4 ? __fmul_rn(vv, __fmul_rn(p[np + v], sc_f)) : vv;
     }
     __syncthreads();
     tstamp<TM>(15);
-    if (tid < 16) {
-        float a32[32];
-#pragma unroll
-        for (int l = 0; l < 32; l++) a32[l] = part[l * 16 + tid];
-        float sum = lane_tree_reduce_local(a32);
+    {
+        // warp w finishes output column w: lane l holds virtual lane l's partial, the shuffle tree is lane_tree_reduce (the reference's
+        // order); every lane then runs the short leftover chain on the same values, and lanes 0..7 store the eight copies of the result
+        float sum = lane_tree_reduce(part[lane * 17 + warp]);
 #pragma unroll 4
         for (int j = 0; j < r; j++) {
-            const float tj = act[j * 16 + tid];
+            const float tj = act[j * 16 + warp];
             if (j < n4) sum = __fadd_rn(sum, tj); else sum = __fmaf_rn(tj, __fmul_rn(p[np + j], sc_f), sum);
         }
-#pragma unroll
-        for (int rep = 0; rep < kReplicas; rep++) publish(s_bc.gatt + (size_t) rep * E + col0 + tid, sum, t_att);
+        publish_all(s_bc.gatt, E, col0 + warp, sum, t_att, lane);
     }
     __syncthreads();                                     // `act` / `qs` are reused by the next phase
 }
