@@ -668,56 +668,83 @@ __device__ __noinline__ void run_phase(int phase, int ep, int layer, uint32_t ot
 // calls with their own register allocation.  Inlined into the 128-register kernel body the "prefetched" V values were spilled right after
 // each load (LDG -> STL in the SASS: every load waited for its data, 0.3 us each, 2.2-4.6 us per layer on the soft_max CTAs —
 // profiles/r02_decode_fine_stamps.txt); here they stay in registers.
+// Where this warp keeps the K rows of its score tasks: the tail of half 0 of its staging slot, behind the rows of the two phases that
+// use that half (c_attn and c_fc of every layer: the split of rows over CTAs and warps is the same in every layer).  cap = tasks that fit.
+template <int DSTEPS>
+__device__ __forceinline__ void key_tail(int warp, uint32_t & off, int & cap) {
+    constexpr int D = DSTEPS * 32;
+    off = (max(staged_bytes_of(0, warp), staged_bytes_of(2, warp)) + 127u) & ~127u;
+    cap = min(2 * kMaxTasks, (int)(((uint32_t) kHalfSlotBytes - min(off, (uint32_t) kHalfSlotBytes)) / (uint32_t)(D * 4)));
+}
+
+// Score CTAs, split mode: copy the K rows (older positions) of this warp's score tasks of `layer` into the key tail, asynchronously
+// (cp.async, 16 bytes per lane).  Called a whole layer ahead — right after the warp's scores of the previous layer are out, when these
+// CTAs have nothing to do but wait for the attention output — so the rows are in shared memory long before q arrives.  (Prefetched into
+// registers when q was about to arrive, they came back 1-3 us after q: the scores were the critical path of the layer.)
+template <int DSTEPS>
+__device__ __noinline__ void p2_stage_keys(int layer, int H, int n_kv, unsigned score_cta0) {
+    constexpr int D = DSTEPS * 32, GPT = D / 4;              // 16-byte pieces per task
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int E = s_bc.E, ctx = s_bc.ctx, n_past = s_bc.n_past;
+    uint32_t off; int cap; key_tail<DSTEPS>(warp, off, cap);
+    const float * Kc = s_bc.mem_k + (size_t) layer * ctx * E;
+    const int total = H * n_kv, gw = (int)(blockIdx.x - score_cta0) * kWarps + warp, nw = (int)(gridDim.x - score_cta0) * kWarps;
+    const uint32_t dst = smem_u32(dsm + SmemLayout::wslot + (size_t) warp * kWarpSlotBytes + off);
+#pragma unroll 2
+    for (int q = lane; q < cap * GPT; q += 32) {
+        const int i = q / GPT, g = q - i * GPT, t = gw + i * nw;
+        if (t < total) {
+            const int h = t / n_kv, k = t - h * n_kv;
+            if (k < n_past) cp_async_16(dst + (uint32_t) q * 16u, Kc + (size_t) k * E + h * D + g * 4);
+        }
+    }
+    cp_async_commit();
+}
+
+// P2 of a layer (scores) for the CTAs that take score tasks, and P3 (soft_max + P.V) for the CTAs that own a soft_max tile, are real
+// calls with their own register allocation.  Inlined into the 128-register kernel body the "prefetched" K / V values were spilled right
+// after each load (LDG -> STL in the SASS: every load waited for its data, 0.3 us each, 2.2-4.6 us per layer on the soft_max CTAs —
+// profiles/r02_decode_fine_stamps.txt); now neither lives in registers at all.
+// Task i of this warp is t = gw + i * nw = (h, k); (h, k) advance incrementally (one division for the stride instead of two per task; a
+// float-reciprocal divmod per task was measured at +216 bytes of spills and +19 % per token).  Eight dot products at a time are reduced
+// TOGETHER by a transposed butterfly: stage xor 16 swaps half of the eight partials, xor 8 a quarter, xor 4 one, then xor 1 / xor 2 on
+// the single survivor — per task exactly the additions of lane_tree_reduce (each add sees the same two values, addition is commutative),
+// 11 shuffles instead of 40, and eight lanes publish the eight scores at once.
 template <int DSTEPS, bool TM>
-__device__ __noinline__ void p2_scores(int il, int H, int n_kv, float scale, uint32_t t_qkv, uint32_t t_sc, unsigned score_cta0) {
+__device__ __noinline__ void p2_scores(int il, int H, int n_kv, float scale, uint32_t t_qkv, uint32_t t_sc, unsigned score_cta0, bool keys_staged) {
     constexpr int D = DSTEPS * 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int E = s_bc.E, ctx = s_bc.ctx, n_past = s_bc.n_past;
     float * qs = reinterpret_cast<float *>(dsm + SmemLayout::q);
-    struct { float * mem_k; } A{s_bc.mem_k};
-    const float * Kc = A.mem_k + (size_t) il * ctx * E;
+    const float * Kc = s_bc.mem_k + (size_t) il * ctx * E;
     const int total = H * n_kv, gw = (int)(blockIdx.x - score_cta0) * kWarps + warp, nw = (int)(gridDim.x - score_cta0) * kWarps;
-    // Task i of this warp is t = gw + i * nw = (h, k).  (h, k) advance incrementally (one division for the stride instead of two per
-    // task; a float-reciprocal divmod per task was measured at +216 bytes of spills and +19 % per token), and the eight dot products
-    // are reduced TOGETHER by a transposed butterfly: stage xor 16 swaps half of the eight partials, xor 8 a quarter, xor 4 one, then
-    // xor 1 / xor 2 on the single survivor — per task exactly the additions of lane_tree_reduce (each add sees the same two values,
-    // addition is commutative), 11 shuffles instead of 40, and eight lanes publish the eight scores at once.
     const int sq = nw / n_kv, sr = nw - sq * n_kv;
-    const int h0 = gw / n_kv, k0 = gw - h0 * n_kv;
-    float kf[kMaxTasks][DSTEPS];
-    {
-        int h = h0, k = k0;
-#pragma unroll
-        for (int i = 0; i < kMaxTasks; i++) {
-            if (h < H && k < n_past) {
-#pragma unroll
-                for (int c = 0; c < DSTEPS; c++) kf[i][c] = __ldcg(Kc + (size_t) k * E + h * D + c * 32 + lane);
-            }
-            k += sr; h += sq; if (k >= n_kv) { k -= n_kv; h++; }
-        }
-    }
+    uint32_t off; int cap; key_tail<DSTEPS>(warp, off, cap);
+    if (!keys_staged) cap = 0;
+    const float * ks = reinterpret_cast<const float *>(dsm + SmemLayout::wslot + (size_t) warp * kWarpSlotBytes + off) + lane;   // task i, chain step c: ks[i * D + c * 32]
     tstamp<TM>(6);
     consume_to_smem<2>(s_bc.gq, E, t_qkv, qs, SINK_PLAIN, XT_Q);
     tstamp<TM>(7);
-    float r[kMaxTasks];
-    {
-        int h = h0, k = k0;
+    if (cap > 0) { cp_async_wait_all(); __syncwarp(); }      // the warp reads back only what its own lanes copied
+    int h = gw / n_kv, k = gw - h * n_kv;                    // task 0
+    int done = 0;                                            // tasks handled through the staged rows
+#pragma unroll 1
+    for (int b0 = 0; b0 < cap && gw + b0 * nw < total; b0 += kMaxTasks) {
+        float r[kMaxTasks];
 #pragma unroll
         for (int i = 0; i < kMaxTasks; i++) {
             float acc = 0.0f;
-            if (h < H) {
+            if (b0 + i < cap && h < H) {
 #pragma unroll
                 for (int c = 0; c < DSTEPS; c++) {
-                    const float kv = (k < n_past) ? kf[i][c] : consume1(s_bc.gk + h * D + c * 32 + lane, t_qkv);   // the new position's key comes through the exchange
+                    const float kv = (k < n_past) ? ks[(b0 + i) * D + c * 32] : consume1(s_bc.gk + h * D + c * 32 + lane, t_qkv);   // the new position's key comes through the exchange
                     acc = __fmaf_rn(kv, qs[h * D + c * 32 + lane], acc);
                 }
             }
             r[i] = acc;
             k += sr; h += sq; if (k >= n_kv) { k -= n_kv; h++; }
         }
-    }
-    static_assert(kMaxTasks == 8, "the transposed butterfly below is written for eight tasks");
-    {
+        static_assert(kMaxTasks == 8, "the transposed butterfly below is written for eight tasks");
         const bool u16 = (lane & 16) != 0, u8 = (lane & 8) != 0, u4 = (lane & 4) != 0;
 #pragma unroll
         for (int i = 0; i < 4; i++) { const float keep = u16 ? r[i + 4] : r[i], send = u16 ? r[i] : r[i + 4]; r[i] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, 16)); }
@@ -726,24 +753,25 @@ __device__ __noinline__ void p2_scores(int il, int H, int n_kv, float scale, uin
         { const float keep = u4 ? r[1] : r[0], send = u4 ? r[0] : r[1]; r[0] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, 4)); }
         r[0] = __fadd_rn(r[0], __shfl_xor_sync(0xffffffffu, r[0], 1));
         r[0] = __fadd_rn(r[0], __shfl_xor_sync(0xffffffffu, r[0], 2));
-        const int mine = (u16 ? 4 : 0) + (u8 ? 2 : 0) + (u4 ? 1 : 0);          // the task whose complete sum this lane holds
+        const int mine = b0 + (u16 ? 4 : 0) + (u8 ? 2 : 0) + (u4 ? 1 : 0);     // the task whose complete sum this lane holds
         const int t = gw + mine * nw;
-        if ((lane & 3) == 0 && t < total) {
-            const int h = t / n_kv, k = t - h * n_kv;
-            publish(s_bc.gscores + (size_t) h * ctx + k, __fmul_rn(r[0], scale), t_sc);
+        if ((lane & 3) == 0 && mine < cap && t < total) {
+            const int hh = t / n_kv, kk = t - hh * n_kv;
+            publish(s_bc.gscores + (size_t) hh * ctx + kk, __fmul_rn(r[0], scale), t_sc);
         }
+        done = min(b0 + kMaxTasks, cap);
     }
 #pragma unroll 1
-    for (int t = gw + kMaxTasks * nw; t < total; t += nw) {   // (not reached for the supported shapes; keeps the kernel total)
-        const int h = t / n_kv, k = t - h * n_kv;
+    for (int t = gw + done * nw; t < total; t += nw) {       // tasks beyond the staged ones (none for bark-small; small grids, unsplit mode): straight from global memory
+        const int hh = t / n_kv, kk = t - hh * n_kv;
         float acc = 0.0f;
 #pragma unroll
         for (int c = 0; c < DSTEPS; c++) {
-            const float kv = (k < n_past) ? __ldcg(Kc + (size_t) k * E + h * D + c * 32 + lane) : consume1(s_bc.gk + h * D + c * 32 + lane, t_qkv);
-            acc = __fmaf_rn(kv, qs[h * D + c * 32 + lane], acc);
+            const float kv = (kk < n_past) ? __ldcg(Kc + (size_t) kk * E + hh * D + c * 32 + lane) : consume1(s_bc.gk + hh * D + c * 32 + lane, t_qkv);
+            acc = __fmaf_rn(kv, qs[hh * D + c * 32 + lane], acc);
         }
-        const float r = lane_tree_reduce(acc);
-        if (lane == 0) publish(s_bc.gscores + (size_t) h * ctx + k, __fmul_rn(r, scale), t_sc);
+        const float rr = lane_tree_reduce(acc);
+        if (lane == 0) publish(s_bc.gscores + (size_t) hh * ctx + kk, __fmul_rn(rr, scale), t_sc);
     }
 }
 
@@ -883,11 +911,10 @@ __device__ __noinline__ void p3_attention(int il, int n_kv, int np, int pv_h, in
         // warp w finishes output column w: lane l holds virtual lane l's partial, the shuffle tree is lane_tree_reduce (the reference's
         // order); every lane then runs the short leftover chain on the same values, and lanes 0..7 store the eight copies of the result
         float sum = lane_tree_reduce(part[lane * 17 + warp]);
-#pragma unroll 4
-        for (int j = 0; j < r; j++) {
-            const float tj = act[j * 16 + warp];
-            if (j < n4) sum = __fadd_rn(sum, tj); else sum = __fmaf_rn(tj, __fmul_rn(p[np + j], sc_f), sum);
-        }
+#pragma unroll 8
+        for (int j = 0; j < n4; j++) sum = __fadd_rn(sum, act[j * 16 + warp]);            // (16 warps run this at once: keep it to a load and an add per step)
+#pragma unroll 1
+        for (int j = n4; j < r; j++) sum = __fmaf_rn(act[j * 16 + warp], __fmul_rn(p[np + j], sc_f), sum);
         publish_all(s_bc.gatt, E, col0 + warp, sum, t_att, lane);
     }
     __syncthreads();                                     // `act` / `qs` are reused by the next phase
@@ -976,6 +1003,8 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
         l2_prefetch_bulk(reinterpret_cast<const unsigned char *>(A.mem_v + (size_t) layer * ctx * E) + off, bytes);
     };
     kv_prefetch(0);
+    const bool keys_staged = score_cta0 != 0 && score_cta;   // split mode: this CTA's staging tails are free for K rows (the soft_max CTAs keep V tiles in theirs)
+    if (keys_staged) p2_stage_keys<DSTEPS>(0, H, n_kv, score_cta0);
 #pragma unroll 1
     for (int il = 0; il < L; il++) {
         kv_prefetch(il + 1);
@@ -993,7 +1022,10 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
         // ---- P2 (scores) and P3 (soft_max + P.V), out of line (see p2_scores).  The CTAs that own a soft_max tile take no score tasks when
         // enough other CTAs exist: they are the critical path of the layer (they still have the whole of P3 to do once the scores exist) ----
         if constexpr (kQ4) __syncthreads();                    // the q8 operand aliases `qs`: every warp must be done with its QKV rows before q lands there
-        if (score_cta) p2_scores<DSTEPS, TM>(il, H, n_kv, scale, t_qkv, t_sc, score_cta0);
+        if (score_cta) {
+            p2_scores<DSTEPS, TM>(il, H, n_kv, scale, t_qkv, t_sc, score_cta0, keys_staged);
+            if (keys_staged && il + 1 < L) p2_stage_keys<DSTEPS>(il + 1, H, n_kv, score_cta0);      // next layer's K rows: these CTAs only wait for the attention output now
+        }
         tstamp<TM>(8);
         if (pv_cta) p3_attention<DSTEPS, TM>(il, n_kv, np, pv_h, pv_c, t_qkv, t_sc, t_att, A.ln_fallbacks);
         tstamp<TM>(16);
