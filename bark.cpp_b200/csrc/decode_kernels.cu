@@ -688,14 +688,14 @@ __device__ __noinline__ void p2_stage_keys(int layer, int H, int n_kv, unsigned 
     const int E = s_bc.E, ctx = s_bc.ctx, n_past = s_bc.n_past;
     uint32_t off; int cap; key_tail<DSTEPS>(warp, off, cap);
     const float * Kc = s_bc.mem_k + (size_t) layer * ctx * E;
-    const int total = H * n_kv, gw = (int)(blockIdx.x - score_cta0) * kWarps + warp, nw = (int)(gridDim.x - score_cta0) * kWarps;
+    const int total = H * n_past, gw = (int)(blockIdx.x - score_cta0) * kWarps + warp, nw = (int)(gridDim.x - score_cta0) * kWarps;   // tasks = (head, OLDER position)
     const uint32_t dst = smem_u32(dsm + SmemLayout::wslot + (size_t) warp * kWarpSlotBytes + off);
 #pragma unroll 2
     for (int q = lane; q < cap * GPT; q += 32) {
         const int i = q / GPT, g = q - i * GPT, t = gw + i * nw;
         if (t < total) {
-            const int h = t / n_kv, k = t - h * n_kv;
-            if (k < n_past) cp_async_16(dst + (uint32_t) q * 16u, Kc + (size_t) k * E + h * D + g * 4);
+            const int h = t / n_past, k = t - h * n_past;
+            cp_async_16(dst + (uint32_t) q * 16u, Kc + (size_t) k * E + h * D + g * 4);
         }
     }
     cp_async_commit();
@@ -717,8 +717,11 @@ __device__ __noinline__ void p2_scores(int il, int H, int n_kv, float scale, uin
     const int E = s_bc.E, ctx = s_bc.ctx, n_past = s_bc.n_past;
     float * qs = reinterpret_cast<float *>(dsm + SmemLayout::q);
     const float * Kc = s_bc.mem_k + (size_t) il * ctx * E;
-    const int total = H * n_kv, gw = (int)(blockIdx.x - score_cta0) * kWarps + warp, nw = (int)(gridDim.x - score_cta0) * kWarps;
-    const int sq = nw / n_kv, sr = nw - sq * n_kv;
+    // tasks t = gw + i * nw over (head, OLDER position) = (t / n_past, t % n_past); the H scores of the NEW position (its key arrives through
+    // the exchange) are one extra task each for the first H warps — kept out of the loop below: with the poll of the exchange word inlined
+    // sixteen times the loop was ~400 instructions per batch and sixteen warps per SM issue every one of them (1.3-2.3 us per layer)
+    const int total = H * n_past, gw = (int)(blockIdx.x - score_cta0) * kWarps + warp, nw = (int)(gridDim.x - score_cta0) * kWarps;
+    const int sq = nw / n_past, sr = nw - sq * n_past;
     uint32_t off; int cap; key_tail<DSTEPS>(warp, off, cap);
     if (!keys_staged) cap = 0;
     const float * ks = reinterpret_cast<const float *>(dsm + SmemLayout::wslot + (size_t) warp * kWarpSlotBytes + off) + lane;   // task i, chain step c: ks[i * D + c * 32]
@@ -726,7 +729,7 @@ __device__ __noinline__ void p2_scores(int il, int H, int n_kv, float scale, uin
     consume_to_smem<2>(s_bc.gq, E, t_qkv, qs, SINK_PLAIN, XT_Q);
     tstamp<TM>(7);
     if (cap > 0) { cp_async_wait_all(); __syncwarp(); }      // the warp reads back only what its own lanes copied
-    int h = gw / n_kv, k = gw - h * n_kv;                    // task 0
+    int h = gw / n_past, k = gw - h * n_past;                // task 0
     int done = 0;                                            // tasks handled through the staged rows
 #pragma unroll 1
     for (int b0 = 0; b0 < cap && gw + b0 * nw < total; b0 += kMaxTasks) {
@@ -736,13 +739,10 @@ __device__ __noinline__ void p2_scores(int il, int H, int n_kv, float scale, uin
             float acc = 0.0f;
             if (b0 + i < cap && h < H) {
 #pragma unroll
-                for (int c = 0; c < DSTEPS; c++) {
-                    const float kv = (k < n_past) ? ks[(b0 + i) * D + c * 32] : consume1(s_bc.gk + h * D + c * 32 + lane, t_qkv);   // the new position's key comes through the exchange
-                    acc = __fmaf_rn(kv, qs[h * D + c * 32 + lane], acc);
-                }
+                for (int c = 0; c < DSTEPS; c++) acc = __fmaf_rn(ks[(b0 + i) * D + c * 32], qs[h * D + c * 32 + lane], acc);
             }
             r[i] = acc;
-            k += sr; h += sq; if (k >= n_kv) { k -= n_kv; h++; }
+            k += sr; h += sq; if (k >= n_past) { k -= n_past; h++; }
         }
         static_assert(kMaxTasks == 8, "the transposed butterfly below is written for eight tasks");
         const bool u16 = (lane & 16) != 0, u8 = (lane & 8) != 0, u4 = (lane & 4) != 0;
@@ -756,22 +756,27 @@ __device__ __noinline__ void p2_scores(int il, int H, int n_kv, float scale, uin
         const int mine = b0 + (u16 ? 4 : 0) + (u8 ? 2 : 0) + (u4 ? 1 : 0);     // the task whose complete sum this lane holds
         const int t = gw + mine * nw;
         if ((lane & 3) == 0 && mine < cap && t < total) {
-            const int hh = t / n_kv, kk = t - hh * n_kv;
+            const int hh = t / n_past, kk = t - hh * n_past;
             publish(s_bc.gscores + (size_t) hh * ctx + kk, __fmul_rn(r[0], scale), t_sc);
         }
         done = min(b0 + kMaxTasks, cap);
     }
 #pragma unroll 1
     for (int t = gw + done * nw; t < total; t += nw) {       // tasks beyond the staged ones (none for bark-small; small grids, unsplit mode): straight from global memory
-        const int hh = t / n_kv, kk = t - hh * n_kv;
+        const int hh = t / n_past, kk = t - hh * n_past;
         float acc = 0.0f;
 #pragma unroll
-        for (int c = 0; c < DSTEPS; c++) {
-            const float kv = (kk < n_past) ? __ldcg(Kc + (size_t) kk * E + hh * D + c * 32 + lane) : consume1(s_bc.gk + hh * D + c * 32 + lane, t_qkv);
-            acc = __fmaf_rn(kv, qs[hh * D + c * 32 + lane], acc);
-        }
+        for (int c = 0; c < DSTEPS; c++) acc = __fmaf_rn(__ldcg(Kc + (size_t) kk * E + hh * D + c * 32 + lane), qs[hh * D + c * 32 + lane], acc);
         const float rr = lane_tree_reduce(acc);
         if (lane == 0) publish(s_bc.gscores + (size_t) hh * ctx + kk, __fmul_rn(rr, scale), t_sc);
+    }
+#pragma unroll 1
+    for (int hh = gw; hh < H; hh += nw) {                    // the new position against itself, head hh
+        float acc = 0.0f;
+#pragma unroll
+        for (int c = 0; c < DSTEPS; c++) acc = __fmaf_rn(consume1(s_bc.gk + hh * D + c * 32 + lane, t_qkv), qs[hh * D + c * 32 + lane], acc);
+        const float rr = lane_tree_reduce(acc);
+        if (lane == 0) publish(s_bc.gscores + (size_t) hh * ctx + n_past, __fmul_rn(rr, scale), t_sc);
     }
 }
 
@@ -1024,9 +1029,11 @@ __global__ void __launch_bounds__(kThreads, 1) gpt_decode_step_kernel(DecodeArgs
         if constexpr (kQ4) __syncthreads();                    // the q8 operand aliases `qs`: every warp must be done with its QKV rows before q lands there
         if (score_cta) {
             p2_scores<DSTEPS, TM>(il, H, n_kv, scale, t_qkv, t_sc, score_cta0, keys_staged);
+            tstamp<TM>(8);
             if (keys_staged && il + 1 < L) p2_stage_keys<DSTEPS>(il + 1, H, n_kv, score_cta0);      // next layer's K rows: these CTAs only wait for the attention output now
+        } else {
+            tstamp<TM>(8);
         }
-        tstamp<TM>(8);
         if (pv_cta) p3_attention<DSTEPS, TM>(il, n_kv, np, pv_h, pv_c, t_qkv, t_sc, t_att, A.ln_fallbacks);
         tstamp<TM>(16);
 
